@@ -1,0 +1,64 @@
+"""Synthetic data of the BASELINE.json config shapes.
+
+Every generator is deterministic in its seed and returns a `spec` dict
+{family, hyper, <arrays>} understood by blangsdk_b200.engine (and, in tests,
+by the oracle).  Sizes default to the full configs; tests pass smaller ones.
+"""
+import math
+
+import numpy as np
+
+SEED_C1, SEED_C2, SEED_C3, SEED_C4, SEED_C5 = 20240001, 20240002, 20240003, 20240004, 20240005
+
+
+def normal_meanvar(n=1000, seed=SEED_C1):
+    """C1: y_i ~ N(1.5, 4); mu ~ Normal(0,100), sigma2 ~ Exponential(0.1)."""
+    rng = np.random.default_rng(seed)
+    y = rng.normal(1.5, 2.0, n)
+    return dict(family="normal", hyper=dict(m0=0.0, v0=100.0, rate=0.1), y=y)
+
+
+def logistic_regression(n=100_000, p=32, seed=SEED_C2):
+    """C2: X ~ N(0,1) with column 0 == 1, w* ~ N(0, 0.5^2), y ~ Bernoulli(logistic(X w*)); w_j ~ Normal(0,10)."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, p))
+    x[:, 0] = 1.0
+    w = rng.normal(0.0, 0.5, p)
+    eta = x @ w
+    y = (rng.random(n) < 1.0 / (1.0 + np.exp(-eta))).astype(np.int32)
+    return dict(family="logistic", hyper=dict(v0=10.0), x=x, y=y, w_true=w)
+
+
+def gaussian_mixture(n=1_000_000, K=4, seed=SEED_C3):
+    """C3: equal-weight N(-6,1), N(-2,.25), N(2,.25), N(6,1); indicators marginalised."""
+    rng = np.random.default_rng(seed)
+    means = np.array([-6.0, -2.0, 2.0, 6.0])
+    sds = np.array([1.0, 0.5, 0.5, 1.0])
+    if K != 4:
+        means = np.linspace(-6.0, 6.0, K)
+        sds = np.full(K, 0.75)
+    comp = rng.integers(0, K, n)
+    y = means[comp] + sds[comp] * rng.standard_normal(n)
+    return dict(family="mixture", hyper=dict(K=K, m0=0.0, v0=100.0, gshape=1.0, grate=1.0, conc=1.0), y=y)
+
+
+def ising(N=256, moment=0.0, coupling=None):
+    """C4: F/Ising.bl on an N x N periodic lattice at the critical coupling log(1+sqrt 2)/2."""
+    if coupling is None:
+        coupling = math.log(1.0 + math.sqrt(2.0)) / 2.0
+    return dict(family="ising", hyper=dict(N=N, coupling=coupling, moment=moment))
+
+
+def beta_binomial(replica=0, groups=32, trials=50, seed=SEED_C5):
+    """C5, one replica: theta_g ~ Beta(2,5), y_g ~ Binomial(50, theta_g); alpha, beta ~ Exponential(0.1)."""
+    rng = np.random.default_rng(seed + replica)
+    theta = rng.beta(2.0, 5.0, groups)
+    y = rng.binomial(trials, theta).astype(np.int32)
+    return dict(family="betabinomial", hyper=dict(rate=0.1), y=y, ntrials=np.full(groups, trials, dtype=np.int32))
+
+
+def beta_binomial_batch(n_replicas=4096, groups=32, trials=50, seed=SEED_C5):
+    """C5, all replicas stacked: y[r, g]."""
+    ys = np.stack([beta_binomial(r, groups, trials, seed)["y"] for r in range(n_replicas)])
+    return dict(family="betabinomial", hyper=dict(rate=0.1), y=ys,
+                ntrials=np.full((n_replicas, groups), trials, dtype=np.int32))

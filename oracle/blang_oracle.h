@@ -1,0 +1,172 @@
+/*
+ * blang_oracle.h -- CPU restatement of blangSDK's NRPT hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under blangsdk_b200/ (the product) may
+ * include, link or call this.  Allowed users: tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs.
+ *
+ * PARITY STATUS: "parity unpinned" with respect to the JVM reference.  There
+ * is no JVM in the build container, so the restatement was never compared
+ * with outputs of the Java engine.  It is pinned instead against the known
+ * answers the reference's own tests hold for this path (see
+ * tests/test_oracle_pins.py): ladder lists (T/TestLadders.java:44-81), the
+ * rounds() worked example (PT.java:239-265), density normalisation to 1e-6
+ * (T/TestSDKNormalizations.java:20-45), cache == from-scratch density
+ * (SampledModel.java:178-188), Ising log Z against exhaustive enumeration
+ * (T/TestEndToEnd.xtend:139-167, factories/Exact.java:82-92) and the
+ * Random123 Philox known-answer vectors.
+ *
+ * Third-party arithmetic that is NOT in /root/reference (bayonet 4.1.13,
+ * build.gradle:35): lnGamma, logistic, logAdd, isClose, Random.  Restated
+ * from their published definitions; see the notes at each function.
+ *
+ * Path shorthands in citations:  R/ = src/main/java/blang/ ,
+ * F/ = src/main/java/blang/validation/internals/fixtures/ .
+ */
+#ifndef BLANG_ORACLE_H
+#define BLANG_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- model families (closed catalogue) ---- */
+enum {
+  ORC_FAM_NORMAL = 1,       /* C1: mu ~ Normal(m0,v0), s2 ~ Exponential(rate), y_i ~ Normal(mu,s2) */
+  ORC_FAM_LOGISTIC = 2,     /* C2: w_j ~ Normal(0,v0), y_i ~ Bernoulli(logistic(x_i.w))           */
+  ORC_FAM_MIXTURE = 3,      /* C3: marginalised K-component Gaussian mixture                       */
+  ORC_FAM_ISING = 4,        /* C4: F/Ising.bl                                                      */
+  ORC_FAM_BETABINOMIAL = 5  /* C5: a,b ~ Exponential(rate), y_g ~ BetaBinomial(n_g,a,b)            */
+};
+
+enum { ORC_INIT_COPIES = 0, ORC_INIT_FORWARD = 1 };
+enum { ORC_ORDER_REFERENCE = 0, ORC_ORDER_CHECKERBOARD = 1 };
+
+typedef struct orc_model orc_model;
+typedef struct orc_pt orc_pt;
+
+/* Philox4x32-10 block function (Random123); exported for the KAT test. */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* special functions exported for pin tests */
+double orc_lngamma(double x);            /* libm lgamma (documented choice)         */
+double orc_lngamma_pike_hill(double x);  /* Pike & Hill (1966) Alg. 291, cross-check */
+double orc_logistic(double x);
+double orc_log_add(double a, double b);
+
+/* ---- model construction ------------------------------------------------
+ * data pointers are copied.  hyper: family specific, see blang_oracle.c.   */
+orc_model* orc_model_normal(const double* y, int n, double m0, double v0, double rate);
+orc_model* orc_model_logistic(const double* x_rowmajor, const int32_t* y, int n, int p, double v0);
+orc_model* orc_model_mixture(const double* y, int n, int K, double m0, double v0,
+                             double gshape, double grate, double conc);
+orc_model* orc_model_ising(int N, double coupling, double moment);
+orc_model* orc_model_betabinomial(const int32_t* y, const int32_t* ntrials, int n, double rate);
+void orc_model_free(orc_model*);
+int orc_model_n_reals(const orc_model*);
+int orc_model_n_ints(const orc_model*);
+int orc_model_n_samplers(const orc_model*);
+int orc_model_n_factors(const orc_model*);
+
+/* One-shot density evaluation on a given state (from-scratch sum over all
+ * factors, SampledModel.updateAll + logDensity, SampledModel.java:161-176,340-364).
+ * out[0]=logDensity(beta) out[1]=sumPreannealedFinite out[2]=nOutOfSupport out[3]=sumFixed */
+void orc_model_log_density(const orc_model*, const double* reals, const int32_t* ints,
+                           double beta, int anneal_support, double out[4]);
+/* single factor value (pre-annealing), for normalisation tests */
+double orc_model_factor_value(const orc_model*, int factor, const double* reals, const int32_t* ints);
+int orc_model_factor_is_annealed(const orc_model*, int factor);
+
+/* ---- PT engine ---------------------------------------------------------- */
+typedef struct {
+  int32_t n_chains;            /* ParallelTempering.nChains, default 8            */
+  int32_t use_prior_samples;   /* default 1                                        */
+  int32_t reversible;          /* default 0                                        */
+  int32_t anneal_support;      /* Runner.xtend:72-73 default 1                     */
+  int32_t n_threads;           /* BriefParallel threads; 0 = all cores             */
+  int32_t sweep_order;         /* ORC_ORDER_*; CHECKERBOARD only for Ising          */
+  double  n_passes_per_scan;   /* PT.nPassesPerScan default 3                      */
+  uint64_t seed;               /* PT.random default 1                              */
+  uint32_t replica;            /* replica id folded into the Philox key            */
+} orc_pt_config;
+
+orc_pt* orc_pt_create(const orc_model*, const orc_pt_config*);
+void orc_pt_free(orc_pt*);
+/* EquallySpaced ladder (ladders/EquallySpaced.java:9-18) */
+void orc_ladder_equally_spaced(int n_chains, double* out_desc);
+void orc_pt_set_ladder(orc_pt*, const double* betas, int n);   /* setAnnealingParameters */
+void orc_pt_get_ladder(const orc_pt*, double* out_desc);
+void orc_pt_set_state(orc_pt*, int position, const double* reals, const int32_t* ints);
+void orc_pt_get_state(const orc_pt*, int position, double* reals, int32_t* ints);
+void orc_pt_initialize(orc_pt*, int init_type);
+/* per-position: logDensity at own beta, preAnnealedLogLikelihood, nOutOfSupport, sumFixed */
+void orc_pt_densities(const orc_pt*, double* logdens, double* loglik, int32_t* noos, double* fixed);
+/* from-scratch check of the caches: max abs difference cache vs recomputed (SampledModel.check) */
+double orc_pt_check_caches(const orc_pt*);
+
+/* one scan = moveKernel + (nChains>1 ? swapKernel : nothing); PT.java:93-102.
+ * energies_out[nChains] (after move, before swap), indicators_out[nChains] may be NULL */
+void orc_pt_scan(orc_pt*, double* energies_out, int32_t* indicators_out);
+void orc_pt_move_kernel(orc_pt*);
+void orc_pt_swap_kernel(orc_pt*, int32_t* indicators_out);
+/* trace of the last sampler execution statistics */
+uint64_t orc_pt_n_evals(const orc_pt*);         /* sampler logDensity() calls     */
+uint64_t orc_pt_n_factor_evals(const orc_pt*);  /* individual factor evaluations  */
+uint64_t orc_pt_n_scans(const orc_pt*);
+
+typedef struct {
+  int32_t n_chains;
+  int32_t n_scans_in_round;
+  double* swap_accept_mean;   /* [n-1] swapAcceptPrs[i].getMean()                  */
+  double* energy_mean;        /* [n]                                               */
+  double* energy_var;         /* [n] commons-math3 variance (n-1)                  */
+  double* energy_cov;         /* [n] CovarAccumulator.sampleCovariance (C/n)       */
+  double* log_sum;            /* [n-1] LogSumAccumulator.logSum                    */
+  int64_t* log_sum_n;         /* [n-1]                                             */
+  int64_t round_trips;        /* Paths.nRejuvenations over this round              */
+  double Lambda;              /* PT.java:434                                       */
+  double log_z_stepping_stone;/* ParallelTempering.java:143-153 (NaN if n==1)      */
+  double log_z_thermo;        /* :130-141 (NaN if support annealed was detected)   */
+} orc_round_stats;
+/* arrays in *out must be caller-allocated */
+void orc_pt_round_stats(const orc_pt*, orc_round_stats* out);
+/* PT.adapt (PT.java:148-171): new ladder from mean acceptance; resets accumulators.
+ * lambda_knots_xy (nullable) receives 2*n doubles: x (ascending beta) then cumulative Lambda */
+void orc_pt_adapt(orc_pt*, double* lambda_knots_xy);
+
+/* PT.rounds (PT.java:239-265); returns number of rounds; arrays sized >= 64 */
+int orc_rounds(int n_scans, double adapt_fraction, int32_t* round_n_scans, int32_t* round_is_adapt);
+
+/* full driver (PT.performInference, PT.java:85-113) with in-memory outputs.
+ * samples_out: [total_scans][n_reals] of the beta=1 chain (nullable) */
+typedef struct {
+  int32_t n_rounds;
+  int32_t round_n_scans[64];
+  int32_t round_is_adapt[64];
+  double  round_Lambda[64];
+  double  round_log_z[64];
+  int64_t round_trips[64];
+  double  round_min_accept[64];
+  double  round_mean_accept[64];
+} orc_run_summary;
+int orc_pt_perform_inference(orc_pt*, int n_scans, double adapt_fraction,
+                             double* samples_out, int32_t* int_samples_out,
+                             double* energies_out, int32_t* indicators_out,
+                             orc_run_summary* summary);
+
+/* schedule maths exposed for unit pins */
+void orc_monotone_spline_build(const double* x, const double* y, int n, double* m_out);
+double orc_monotone_spline_eval(const double* x, const double* y, const double* m, int n, double at);
+/* EngineStaticUtils: given ascending betas[n] and accept[n-1] (ascending order) -> new ascending ladder[n] */
+void orc_adapt_ladder(const double* betas_asc, const double* accept_asc, int n, double* out_asc,
+                      double* cum_lambda_out);
+
+/* exhaustive log normalisation for tiny Ising (factories/Exact.java:82-92) */
+double orc_ising_exact_log_z(int N, double coupling, double moment, double beta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
