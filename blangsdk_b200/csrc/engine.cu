@@ -1,0 +1,779 @@
+// engine.cu -- host side of libblangpt.so: the C ABI of include/blangpt.h.
+//
+// Mirrors the reference's engine objects (same option names and semantics):
+//   blangpt_config            <- ParallelTempering @Arg fields (R/engines/ParallelTempering.java:25-40)
+//   blangpt_run_scans         <- the scan loop of PT.performInference (R/engines/internals/factories/PT.java:93-102)
+//   blangpt_get_round_stats   <- reportParallelTemperingDiagnostics (PT.java:387-505)
+//   blangpt_adapt             <- PT.adapt (PT.java:148-171)
+//   blangpt_perform_inference <- PT.performInference (PT.java:85-113)
+// There is no CPU path: every compute call launches the sm_100a kernels of kernels.cuh.
+#include "../../include/blangpt.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <chrono>
+
+#include "kernels.cuh"
+#include "ising.cuh"
+#include "schedule.hpp"
+
+using namespace bpt;
+
+static thread_local std::string g_create_error;
+
+struct blangpt_handle {
+  blangpt_config cfg;
+  std::string error;
+  int family = 0;
+  int n_reals = 0, n_ints = 0, n_samplers = 0;
+  int G = 1;                      // CTAs per chain
+  bool model_set = false, tables_valid = false;
+  cudaStream_t stream = nullptr;  // nullptr = legacy default stream
+  bool own_stream = false;
+
+  DevEngine E{};
+  DevStats St{};
+  // family data
+  NormalFam::Data normal{};
+  LogisticFam::Data logistic{};
+  MixtureFam<4>::Data mixture{};
+  BetaBinomialFam::Data betabin{};
+  IsingData ising{};
+  std::vector<void*> allocs;      // every device allocation (freed in destroy)
+  std::vector<double> ladder;     // host copy [R][N]
+  uint64_t n_scans = 0, n_launches = 0;
+  int64_t scans_in_round = 0;
+  int64_t M_total = 0;
+};
+
+#define FAIL(h, code, ...) do { set_error((h), __VA_ARGS__); return (code); } while (0)
+#define CUDA_OK(h, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
+    set_error((h), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); return BLANGPT_ECUDA; } } while (0)
+
+static void set_error(blangpt_handle* h, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (h) h->error = buf; else g_create_error = buf;
+}
+
+template <class T>
+static int dev_alloc(blangpt_handle* h, T** out, size_t n, bool zero = true) {
+  void* p = nullptr;
+  const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+  CUDA_OK(h, cudaMalloc(&p, bytes));
+  if (zero) CUDA_OK(h, cudaMemsetAsync(p, 0, bytes, h->stream));
+  h->allocs.push_back(p);
+  *out = (T*)p;
+  return 0;
+}
+
+extern "C" void blangpt_default_config(blangpt_config* c) {
+  memset(c, 0, sizeof *c);
+  c->nChains = 8; c->nReplicas = 1; c->random = 1; c->nPassesPerScan = 3.0;
+  c->usePriorSamples = 1; c->reversible = 0; c->annealSupport = 1; c->treatNaNAsNegativeInfinity = 0;
+  c->device = 0; c->rank = 0; c->worldSize = 1; c->ctasPerChain = 0; c->replicaOffset = 0;
+  c->statisticRecordedMaxChainIndex = 100;
+}
+
+extern "C" const char* blangpt_last_error(const blangpt_handle* h) {
+  return h ? h->error.c_str() : g_create_error.c_str();
+}
+
+extern "C" int blangpt_create(const blangpt_config* cfg, blangpt_handle** out) {
+  if (!cfg || !out) { set_error(nullptr, "null argument"); return BLANGPT_EINVAL; }
+  if (cfg->nChains < 1) { set_error(nullptr, "Number of tempering chains must be greater than zero."); return BLANGPT_EINVAL; }
+  if (cfg->nReplicas < 1 || cfg->worldSize < 1 || cfg->rank < 0 || cfg->rank >= cfg->worldSize) { set_error(nullptr, "bad nReplicas/rank/worldSize"); return BLANGPT_EINVAL; }
+  if (cfg->worldSize > 1 && cfg->nReplicas != 1) { set_error(nullptr, "chain sharding (worldSize > 1) requires nReplicas == 1; shard replicas with one handle per rank"); return BLANGPT_EINVAL; }
+  if (cfg->worldSize > 1 && cfg->nChains % cfg->worldSize != 0) { set_error(nullptr, "nChains must be a multiple of worldSize"); return BLANGPT_EINVAL; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(nullptr, "no CUDA device: libblangpt has no CPU fallback (%s)", cudaGetErrorString(e));
+    return BLANGPT_ECUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { set_error(nullptr, "device %d out of range", cfg->device); return BLANGPT_EINVAL; }
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) { set_error(nullptr, "cudaSetDevice: %s", cudaGetErrorString(e)); return BLANGPT_ECUDA; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major < 10) { set_error(nullptr, "device sm_%d%d is not Blackwell (kernels are built for sm_100a only)", prop.major, prop.minor); return BLANGPT_ECUDA; }
+  blangpt_handle* h = new blangpt_handle();
+  h->cfg = *cfg;
+  h->M_total = (int64_t)cfg->nReplicas * cfg->nChains;
+  *out = h;
+  return BLANGPT_OK;
+}
+
+extern "C" void blangpt_destroy(blangpt_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int blangpt_n_reals(const blangpt_handle* h) { return h ? h->n_reals : -1; }
+extern "C" int blangpt_n_ints(const blangpt_handle* h) { return h ? h->n_ints : -1; }
+extern "C" int blangpt_n_samplers(const blangpt_handle* h) { return h ? h->n_samplers : -1; }
+
+// ---------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------
+template <class Fam>
+static int launch_explore_t(blangpt_handle* h, const typename Fam::Data& D, int mode) {
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3((unsigned)(h->E.M_local * h->G));
+  lc.blockDim = dim3(Fam::kThreads);
+  lc.dynamicSmemBytes = 0;
+  lc.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)h->G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = h->G > 1 ? 1 : 0;
+  CUDA_OK(h, cudaLaunchKernelEx(&lc, explore_kernel<Fam>, h->E, D, h->G, mode));
+  h->n_launches++;
+  return 0;
+}
+
+static int launch_explore(blangpt_handle* h, int mode) {
+  switch (h->family) {
+    case BLANGPT_FAM_NORMAL: return launch_explore_t<NormalFam>(h, h->normal, mode);
+    case BLANGPT_FAM_LOGISTIC: return launch_explore_t<LogisticFam>(h, h->logistic, mode);
+    case BLANGPT_FAM_MIXTURE:
+      if (h->mixture.K <= 4) return launch_explore_t<MixtureFam<4>>(h, h->mixture, mode);
+      else { MixtureFam<8>::Data d8; memcpy(&d8, &h->mixture, sizeof d8); return launch_explore_t<MixtureFam<8>>(h, d8, mode); }
+    case BLANGPT_FAM_BETABINOMIAL: return launch_explore_t<BetaBinomialFam>(h, h->betabin, mode);
+    case BLANGPT_FAM_ISING: {
+      int rc = ising_launch(h->E, h->ising, mode, h->stream);
+      if (rc != 0) FAIL(h, BLANGPT_ECUDA, "ising launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+      h->n_launches += 1;
+      return 0;
+    }
+  }
+  FAIL(h, BLANGPT_ESTATE, "no model set");
+}
+
+static int launch_swap(blangpt_handle* h, const DevOut& O) {
+  const int threads = std::min(256, std::max(32, ((h->cfg.nChains + 31) / 32) * 32));
+  swap_kernel<<<h->cfg.nReplicas, threads, 0, h->stream>>>(h->E, h->St, O);
+  CUDA_OK(h, cudaGetLastError());
+  h->n_launches++;
+  return 0;
+}
+
+static int check_device_errors(blangpt_handle* h) {
+  int err = 0;
+  CUDA_OK(h, cudaMemcpyAsync(&err, h->E.err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  if (err & ERR_SLICE_DIVERGED)
+    FAIL(h, BLANGPT_ENUMERIC, "Slice diverged to infinity. Possible cause is that a variable has no distribution attached to it, i.e. the model is improper.");
+  if ((err & ERR_NAN) && !h->cfg.treatNaNAsNegativeInfinity)
+    FAIL(h, BLANGPT_ENUMERIC, "Factors should not return NaN. Use NEGATIVE_INFINITY to forbid configurations. If you are sure this NaN is OK, you can use the option 'treatNaNAsNegativeInfinity'.");
+  return 0;
+}
+
+static int ensure_tables(blangpt_handle* h) {
+  if (h->tables_valid) return 0;
+  int rc = launch_explore(h, MODE_EVAL);
+  if (rc) return rc;
+  if (h->cfg.worldSize == 1) {
+    prime_prev_kernel<<<(unsigned)((h->M_total + 255) / 256), 256, 0, h->stream>>>(h->E);
+    CUDA_OK(h, cudaGetLastError());
+    h->n_launches++;
+  }
+  h->tables_valid = h->cfg.worldSize == 1;
+  return 0;
+}
+
+static int reset_round(blangpt_handle* h) {
+  reset_round_kernel<<<h->cfg.nReplicas, 128, 0, h->stream>>>(h->E, h->St);
+  CUDA_OK(h, cudaGetLastError());
+  h->n_launches++;
+  h->scans_in_round = 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------
+__global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int n, int p, int npad) {
+  __shared__ double tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int r = r0 + dy, c = c0 + threadIdx.x;
+    tile[dy][threadIdx.x] = (r < n && c < p) ? in[(size_t)r * p + c] : 0.0;
+  }
+  __syncthreads();
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int c = c0 + dy, r = r0 + threadIdx.x;
+    if (c < p && r < npad) out[(size_t)c * npad + r] = tile[threadIdx.x][dy];
+  }
+}
+
+__global__ void init_perm_kernel(DevEngine E, int s_max_used) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < E.R * E.N) { const int p = i % E.N; E.pos_of_slot[i] = p; E.slot_of_pos[i] = p; }
+  if (i < E.M_local) {
+    E.curpos[i] = -1;
+    for (int k = 0; k < s_max_used; k++) E.order[(size_t)i * E.s_max + k] = k;
+  }
+}
+
+static int alloc_engine(blangpt_handle* h) {
+  const blangpt_config& c = h->cfg;
+  DevEngine& E = h->E;
+  const int64_t M = h->M_total;
+  E.N = c.nChains; E.R = c.nReplicas;
+  E.M_local = (int)(M / c.worldSize);
+  E.slot_lo = c.rank * E.M_local;
+  E.key0 = (uint32_t)c.random; E.key1 = (uint32_t)(c.random >> 32);
+  E.replica_offset = (uint32_t)c.replicaOffset;
+  E.n_passes = c.nPassesPerScan; E.use_prior = c.usePriorSamples; E.anneal_support = c.annealSupport;
+  E.s_max = h->family == BLANGPT_FAM_ISING ? 1 : std::max(1, h->n_samplers);
+  double* ladder; int rc;
+  if ((rc = dev_alloc(h, &ladder, M))) return rc;
+  E.ladder = ladder;
+  if ((rc = dev_alloc(h, &E.pos_of_slot, M))) return rc;
+  if ((rc = dev_alloc(h, &E.slot_of_pos, M))) return rc;
+  if ((rc = dev_alloc(h, &E.table, M * 4))) return rc;
+  if ((rc = dev_alloc(h, &E.send, (size_t)E.M_local * 4))) return rc;
+  if ((rc = dev_alloc(h, &E.prev_loglik, M))) return rc;
+  if ((rc = dev_alloc(h, &E.reals, (size_t)std::max(1, h->n_reals) * E.M_local))) return rc;
+  if ((rc = dev_alloc(h, &E.order, (size_t)E.M_local * E.s_max))) return rc;
+  if ((rc = dev_alloc(h, &E.curpos, E.M_local))) return rc;
+  if ((rc = dev_alloc(h, &E.evals, E.M_local))) return rc;
+  if ((rc = dev_alloc(h, &E.execs, E.M_local))) return rc;
+  if ((rc = dev_alloc(h, &E.err, 1))) return rc;
+  if ((rc = dev_alloc(h, &E.scan_counter, c.nReplicas))) return rc;
+  if ((rc = dev_alloc(h, &E.swap_counter, c.nReplicas))) return rc;
+  if ((rc = dev_alloc(h, &E.batch_counter, c.nReplicas))) return rc;
+  DevStats& S = h->St;
+  if ((rc = dev_alloc(h, &S.en_n, M))) return rc;
+  if ((rc = dev_alloc(h, &S.en_m1, M))) return rc;
+  if ((rc = dev_alloc(h, &S.en_m2, M))) return rc;
+  if ((rc = dev_alloc(h, &S.cov_mx, M))) return rc;
+  if ((rc = dev_alloc(h, &S.cov_my, M))) return rc;
+  if ((rc = dev_alloc(h, &S.cov_c, M))) return rc;
+  if ((rc = dev_alloc(h, &S.cov_n, M))) return rc;
+  if ((rc = dev_alloc(h, &S.acc_n, M))) return rc;
+  if ((rc = dev_alloc(h, &S.acc_m1, M))) return rc;
+  if ((rc = dev_alloc(h, &S.ls_sum, M))) return rc;
+  if ((rc = dev_alloc(h, &S.ls_n, M))) return rc;
+  if ((rc = dev_alloc(h, &S.path_flag, M))) return rc;
+  if ((rc = dev_alloc(h, &S.rejuv, c.nReplicas))) return rc;
+  if ((rc = dev_alloc(h, &S.total_evals, 1))) return rc;
+  init_perm_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(E, h->family == BLANGPT_FAM_ISING ? 0 : h->n_samplers);
+  CUDA_OK(h, cudaGetLastError());
+  // default ladder: EquallySpaced
+  std::vector<double> one = equally_spaced(c.nChains);
+  h->ladder.resize(M);
+  for (int r = 0; r < c.nReplicas; r++) std::copy(one.begin(), one.end(), h->ladder.begin() + (size_t)r * c.nChains);
+  CUDA_OK(h, cudaMemcpyAsync((void*)E.ladder, h->ladder.data(), M * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return reset_round(h);
+}
+
+static int pick_ctas_per_chain(const blangpt_handle* h, int64_t rows) {
+  if (h->cfg.ctasPerChain > 0) return h->cfg.ctasPerChain;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+  const int64_t local = h->M_total / h->cfg.worldSize;
+  int G = 1;
+  // widest cluster that still fits one wave and leaves every CTA >= 8k rows
+  while (G < 8 && local * (G * 2) <= sms && rows / (G * 2) >= 8192) G *= 2;
+  return G;
+}
+
+extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangpt_array* a, int32_t na,
+                                 const double* hyper, int32_t nh) {
+  if (!h) return BLANGPT_EINVAL;
+  if (h->model_set) FAIL(h, BLANGPT_ESTATE, "model already set");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  const blangpt_config& c = h->cfg;
+  h->family = family;
+  int rc;
+  int64_t rows = 1;
+  switch (family) {
+    case BLANGPT_FAM_NORMAL: {
+      if (na != 1 || nh != 3 || a[0].dtype != BLANGPT_F64) FAIL(h, BLANGPT_EINVAL, "normal: expects y[f64], hyper (m0, v0, rate)");
+      const int n = (int)a[0].n_elem;
+      double* y; if ((rc = dev_alloc(h, &y, n + 2))) return rc;
+      CUDA_OK(h, cudaMemcpyAsync(y, a[0].data, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      h->normal = {y, n, hyper[0], hyper[1], hyper[2]};
+      h->n_reals = 2; h->n_samplers = 2; rows = n;
+    } break;
+    case BLANGPT_FAM_LOGISTIC: {
+      if (na != 2 || nh != 1 || a[0].dtype != BLANGPT_F64 || a[1].dtype != BLANGPT_I32) FAIL(h, BLANGPT_EINVAL, "logistic: expects x[f64 n*p], y[i32 n], hyper (v0)");
+      const int n = (int)a[1].n_elem;
+      if (n <= 0 || a[0].n_elem % n != 0) FAIL(h, BLANGPT_EINVAL, "logistic: x size is not a multiple of n");
+      const int p = (int)(a[0].n_elem / n);
+      if (p > kMaxParams) FAIL(h, BLANGPT_EUNSUPPORTED, "logistic: at most %d coefficients", kMaxParams);
+      const int npad = (n + 1) & ~1;
+      double *xr, *xt, *eta; uint8_t* y8;
+      if ((rc = dev_alloc(h, &xr, (size_t)n * p, false))) return rc;
+      if ((rc = dev_alloc(h, &xt, (size_t)npad * p))) return rc;
+      if ((rc = dev_alloc(h, &y8, npad))) return rc;
+      const int64_t local = h->M_total / c.worldSize;
+      if ((rc = dev_alloc(h, &eta, (size_t)npad * local))) return rc;
+      CUDA_OK(h, cudaMemcpyAsync(xr, a[0].data, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      dim3 grid((n + 31) / 32, (p + 31) / 32), block(32, 8);
+      transpose_kernel<<<grid, block, 0, h->stream>>>(xr, xt, n, p, npad);
+      CUDA_OK(h, cudaGetLastError());
+      std::vector<uint8_t> yb(npad, 0);
+      const int32_t* yi = (const int32_t*)a[1].data;
+      for (int i = 0; i < n; i++) yb[i] = yi[i] == 1 ? 1 : 0;
+      CUDA_OK(h, cudaMemcpyAsync(y8, yb.data(), npad, cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(h, cudaStreamSynchronize(h->stream));
+      CUDA_OK(h, cudaFree(xr)); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), (void*)xr));
+      h->logistic = {xt, y8, eta, n, npad, p, hyper[0]};
+      h->n_reals = p; h->n_samplers = p; rows = n;
+    } break;
+    case BLANGPT_FAM_MIXTURE: {
+      if (na != 1 || nh != 6 || a[0].dtype != BLANGPT_F64) FAIL(h, BLANGPT_EINVAL, "mixture: expects y[f64], hyper (K, m0, v0, gshape, grate, conc)");
+      const int n = (int)a[0].n_elem, K = (int)hyper[0];
+      if (K < 2 || K > 8) FAIL(h, BLANGPT_EUNSUPPORTED, "mixture: 2 <= K <= 8");
+      double* y; if ((rc = dev_alloc(h, &y, n + 2))) return rc;
+      CUDA_OK(h, cudaMemcpyAsync(y, a[0].data, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      h->mixture = {y, n, K, hyper[1], hyper[2], hyper[3], hyper[4], hyper[5]};
+      h->n_reals = 3 * K; h->n_samplers = 2 * K + 1; rows = n;
+    } break;
+    case BLANGPT_FAM_BETABINOMIAL: {
+      if (na != 2 || nh != 1 || a[0].dtype != BLANGPT_I32 || a[1].dtype != BLANGPT_I32) FAIL(h, BLANGPT_EINVAL, "betabinomial: expects y[i32 R*n], ntrials[i32 R*n], hyper (rate)");
+      if (a[0].n_elem % c.nReplicas != 0 || a[0].n_elem != a[1].n_elem) FAIL(h, BLANGPT_EINVAL, "betabinomial: data size must be nReplicas * n");
+      const int n = (int)(a[0].n_elem / c.nReplicas);
+      const size_t tot = (size_t)a[0].n_elem;
+      int32_t *y, *nt; double* cst;
+      if ((rc = dev_alloc(h, &y, tot))) return rc;
+      if ((rc = dev_alloc(h, &nt, tot))) return rc;
+      if ((rc = dev_alloc(h, &cst, tot))) return rc;
+      std::vector<double> cs(tot);
+      const int32_t *yh = (const int32_t*)a[0].data, *nh_ = (const int32_t*)a[1].data;
+      for (size_t i = 0; i < tot; i++) {   // BetaBinomial.bl:19-20 support checks + the three data-only lnGamma terms
+        const double x = yh[i], n_ = nh_[i];
+        cs[i] = (x < 0.0 || n_ <= 0.0 || x > n_) ? -INFINITY : lgamma(n_ + 1) - lgamma(x + 1) - lgamma(n_ - x + 1);
+      }
+      CUDA_OK(h, cudaMemcpyAsync(y, yh, tot * 4, cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(h, cudaMemcpyAsync(nt, nh_, tot * 4, cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(h, cudaMemcpyAsync(cst, cs.data(), tot * 8, cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(h, cudaStreamSynchronize(h->stream));
+      h->betabin = {y, nt, cst, n, c.nChains, hyper[0]};
+      h->n_reals = 2; h->n_samplers = 2; rows = n;
+    } break;
+    case BLANGPT_FAM_ISING: {
+      if (nh != 3) FAIL(h, BLANGPT_EINVAL, "ising: hyper (N, coupling, moment)");
+      const int N = (int)hyper[0];
+      if (N < 2 || (N & 1)) FAIL(h, BLANGPT_EUNSUPPORTED, "ising: the checkerboard sweep needs an even lattice side >= 2");
+      h->ising.N = N; h->ising.coupling = hyper[1]; h->ising.moment = hyper[2];
+      h->ising.p1 = 1.0 / (1.0 + exp(2.0 * hyper[2]));   // logistic(-2*moment), F/Ising.bl:28
+      h->n_reals = 0; h->n_ints = N * N; h->n_samplers = N * N; rows = 1;
+      const int64_t local = h->M_total / c.worldSize;
+      if ((rc = dev_alloc(h, &h->ising.spins, (size_t)local * N * N))) return rc;
+    } break;
+    default: FAIL(h, BLANGPT_EUNSUPPORTED, "unknown model family %d: the engine only runs the closed catalogue (no CPU fallback)", family);
+  }
+  h->G = family == BLANGPT_FAM_ISING ? 1 : pick_ctas_per_chain(h, rows);
+  if (h->G != 1 && h->G != 2 && h->G != 4 && h->G != 8) FAIL(h, BLANGPT_EINVAL, "ctasPerChain must be 1, 2, 4 or 8");
+  if ((rc = alloc_engine(h))) return rc;
+  // initial state: reals as in the oracle's prototypes (latent scalars start at their constructor value)
+  std::vector<double> init((size_t)std::max(1, h->n_reals) * h->E.M_local, 0.0);
+  auto fill = [&](int v, double x) { for (int l = 0; l < h->E.M_local; l++) init[(size_t)v * h->E.M_local + l] = x; };
+  if (family == BLANGPT_FAM_NORMAL) { fill(0, 0.0); fill(1, 1.0); }
+  if (family == BLANGPT_FAM_BETABINOMIAL) { fill(0, 1.0); fill(1, 1.0); }
+  if (family == BLANGPT_FAM_MIXTURE) { const int K = h->mixture.K; for (int k = 0; k < K; k++) { fill(k, 0.0); fill(K + k, 1.0); fill(2 * K + k, 1.0 / K); } }
+  if (h->n_reals) CUDA_OK(h, cudaMemcpyAsync(h->E.reals, init.data(), init.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  h->model_set = true; h->tables_valid = false;
+  return BLANGPT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// ladder / states
+// ---------------------------------------------------------------------------
+extern "C" int blangpt_set_ladder(blangpt_handle* h, const double* betas, int64_t n) {
+  if (!h || !betas) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  const int N = h->cfg.nChains, R = h->cfg.nReplicas;
+  if (n != N && n != (int64_t)N * R) FAIL(h, BLANGPT_EINVAL, "ladder length must be nChains or nReplicas*nChains");
+  for (int r = 0; r < R; r++) {
+    const double* src = betas + (n == N ? 0 : (size_t)r * N);
+    std::vector<double> v(src, src + N);
+    std::sort(v.begin(), v.end(), [](double a, double b) { return a > b; });
+    if (v[0] != 1.0) FAIL(h, BLANGPT_EINVAL, "the ladder must start at exactly 1.0 (ParallelTempering.java:191-192)");
+    std::copy(v.begin(), v.end(), h->ladder.begin() + (size_t)r * N);
+  }
+  CUDA_OK(h, cudaMemcpyAsync((void*)h->E.ladder, h->ladder.data(), h->ladder.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return reset_round(h);
+}
+
+extern "C" int blangpt_get_ladder(const blangpt_handle* h, double* out, int64_t n) {
+  if (!h || !out) return BLANGPT_EINVAL;
+  if (n != (int64_t)h->ladder.size() && n != h->cfg.nChains) return BLANGPT_EINVAL;
+  memcpy(out, h->ladder.data(), n * sizeof(double));
+  return BLANGPT_OK;
+}
+
+static int slot_of(blangpt_handle* h, int64_t replica, int position, int* local) {
+  if (replica < 0 || replica >= h->cfg.nReplicas || position < 0 || position >= h->cfg.nChains) FAIL(h, BLANGPT_EINVAL, "replica/position out of range");
+  int s = 0;
+  CUDA_OK(h, cudaMemcpyAsync(&s, h->E.slot_of_pos + replica * h->cfg.nChains + position, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  const int64_t g = replica * h->cfg.nChains + s;
+  const int64_t l = g - h->E.slot_lo;
+  if (l < 0 || l >= h->E.M_local) FAIL(h, BLANGPT_EINVAL, "position %d lives on another rank", position);
+  *local = (int)l;
+  return 0;
+}
+
+extern "C" int blangpt_set_state(blangpt_handle* h, int64_t replica, int32_t position, const double* reals, const int32_t* ints) {
+  if (!h) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  int l, rc;
+  if ((rc = slot_of(h, replica, position, &l))) return rc;
+  if (reals && h->n_reals)
+    CUDA_OK(h, cudaMemcpy2DAsync(h->E.reals + l, (size_t)h->E.M_local * sizeof(double), reals, sizeof(double), sizeof(double), h->n_reals, cudaMemcpyHostToDevice, h->stream));
+  if (ints && h->n_ints) {
+    std::vector<uint8_t> b(h->n_ints);
+    for (int i = 0; i < h->n_ints; i++) {
+      if (ints[i] < 0 || ints[i] > 1) FAIL(h, BLANGPT_EINVAL, "ising spins must be 0 or 1");
+      b[i] = (uint8_t)ints[i];
+    }
+    CUDA_OK(h, cudaMemcpyAsync(h->ising.spins + (size_t)l * h->n_ints, b.data(), h->n_ints, cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  h->tables_valid = false;
+  return BLANGPT_OK;
+}
+
+extern "C" int blangpt_get_state(blangpt_handle* h, int64_t replica, int32_t position, double* reals, int32_t* ints) {
+  if (!h) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  int l, rc;
+  if ((rc = slot_of(h, replica, position, &l))) return rc;
+  if (reals && h->n_reals)
+    CUDA_OK(h, cudaMemcpy2DAsync(reals, sizeof(double), h->E.reals + l, (size_t)h->E.M_local * sizeof(double), sizeof(double), h->n_reals, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<uint8_t> b;
+  if (ints && h->n_ints) {
+    b.resize(h->n_ints);
+    CUDA_OK(h, cudaMemcpyAsync(b.data(), h->ising.spins + (size_t)l * h->n_ints, h->n_ints, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  if (ints && h->n_ints) for (int i = 0; i < h->n_ints; i++) ints[i] = b[i];
+  return BLANGPT_OK;
+}
+
+extern "C" int blangpt_initialize(blangpt_handle* h, int32_t init_type) {
+  if (!h) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  if (init_type == BLANGPT_INIT_SCM) FAIL(h, BLANGPT_EUNSUPPORTED, "initialization SCM is not implemented on the GPU engine; use FORWARD or COPIES");
+  if (init_type == BLANGPT_INIT_COPIES) { h->tables_valid = false; return ensure_tables(h); }
+  if (init_type != BLANGPT_INIT_FORWARD) FAIL(h, BLANGPT_EINVAL, "unknown initialization");
+  int rc = launch_explore(h, MODE_FORWARD_INIT);
+  if (rc) return rc;
+  if (h->cfg.worldSize == 1) {
+    prime_prev_kernel<<<(unsigned)((h->M_total + 255) / 256), 256, 0, h->stream>>>(h->E);
+    CUDA_OK(h, cudaGetLastError());
+    h->n_launches++;
+  }
+  h->tables_valid = h->cfg.worldSize == 1;
+  return check_device_errors(h);
+}
+
+extern "C" int blangpt_log_density(blangpt_handle* h, double* out_logdens, double* out_loglik, int32_t* out_noos, double* out_fixed) {
+  if (!h) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  if (h->cfg.worldSize > 1) FAIL(h, BLANGPT_EUNSUPPORTED, "log_density is a single-process call; with worldSize > 1 gather the table (blangpt_table_ptr)");
+  h->tables_valid = false;
+  int rc = ensure_tables(h);
+  if (rc) return rc;
+  const int64_t M = h->M_total; const int N = h->cfg.nChains;
+  std::vector<double> tab(M * 4); std::vector<int> sop(M);
+  CUDA_OK(h, cudaMemcpyAsync(tab.data(), h->E.table, M * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaMemcpyAsync(sop.data(), h->E.slot_of_pos, M * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if ((rc = check_device_errors(h))) return rc;
+  for (int64_t i = 0; i < M; i++) {
+    const int64_t r = i / N; const int p = (int)(i % N);
+    const double* t = &tab[(r * N + sop[i]) * 4];
+    if (out_loglik) out_loglik[i] = t[0];
+    if (out_noos) out_noos[i] = (int32_t)t[1];
+    if (out_fixed) out_fixed[i] = t[2];
+    if (out_logdens) out_logdens[i] = annealed_log_density(t[2], t[0], t[1], h->ladder[r * N + p], h->cfg.annealSupport);
+  }
+  return BLANGPT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// scans
+// ---------------------------------------------------------------------------
+extern "C" int blangpt_run_scans(blangpt_handle* h, int32_t n_scans, const blangpt_scan_outputs* out) {
+  if (!h) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  if (h->cfg.worldSize > 1) FAIL(h, BLANGPT_EINVAL, "run_scans is the single-GPU path; use blangpt_explore / blangpt_swap with worldSize > 1");
+  if (n_scans <= 0) return BLANGPT_OK;
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  int rc;
+  if ((rc = ensure_tables(h))) return rc;
+  const int64_t M = h->M_total; const int R = h->cfg.nReplicas;
+  DevOut O{}; O.n_reals = h->n_reals; O.reversible = h->cfg.reversible;
+  std::vector<void*> tmp;
+  auto alloc_out = [&](auto** dptr, const void* hostptr, size_t n) -> int {
+    if (!hostptr) return 0;
+    using T = std::remove_pointer_t<std::remove_pointer_t<decltype(dptr)>>;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(1, n) * sizeof(T));
+    if (e != cudaSuccess) { set_error(h, "cudaMalloc(outputs): %s", cudaGetErrorString(e)); return BLANGPT_ECUDA; }
+    cudaMemsetAsync(p, 0, std::max<size_t>(1, n) * sizeof(T), h->stream);
+    tmp.push_back(p); *dptr = (T*)p; return 0;
+  };
+  uint8_t* d_ising_samples = nullptr;
+  if (out) {
+    if ((rc = alloc_out(&O.energy, out->energy, (size_t)n_scans * M))) return rc;
+    if ((rc = alloc_out(&O.logdens, out->logDensity, (size_t)n_scans * M))) return rc;
+    if ((rc = alloc_out(&O.noos, out->nOutOfSupport, (size_t)n_scans * M))) return rc;
+    if ((rc = alloc_out(&O.indicators, out->swapIndicators, (size_t)n_scans * M))) return rc;
+    if (h->n_reals && (rc = alloc_out(&O.samples, out->samples, (size_t)n_scans * R * h->n_reals))) return rc;
+    if (h->n_ints && out->intSamples) {
+      void* p = nullptr;
+      CUDA_OK(h, cudaMalloc(&p, (size_t)n_scans * R * h->n_ints));
+      tmp.push_back(p); d_ising_samples = (uint8_t*)p;
+    }
+  }
+  CUDA_OK(h, cudaMemsetAsync(h->E.batch_counter, 0, sizeof(uint32_t) * R, h->stream));
+  for (int s = 0; s < n_scans; s++) {
+    if ((rc = launch_explore(h, MODE_EXPLORE))) return rc;
+    if (d_ising_samples) {
+      ising_record_target(h->E, h->ising, d_ising_samples, s, h->stream);
+      h->n_launches++;
+    }
+    if ((rc = launch_swap(h, O))) return rc;
+  }
+  h->n_scans += n_scans; h->scans_in_round += n_scans;
+  if (out) {
+    auto back = [&](void* host, const void* dev, size_t bytes) { if (host && dev) cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, h->stream); };
+    back(out->energy, O.energy, (size_t)n_scans * M * 8);
+    back(out->logDensity, O.logdens, (size_t)n_scans * M * 8);
+    back(out->nOutOfSupport, O.noos, (size_t)n_scans * M * 4);
+    back(out->swapIndicators, O.indicators, (size_t)n_scans * M * 4);
+    if (h->n_reals) back(out->samples, O.samples, (size_t)n_scans * R * h->n_reals * 8);
+  }
+  rc = check_device_errors(h);   // synchronises the stream
+  if (!rc && d_ising_samples) {
+    std::vector<uint8_t> b((size_t)n_scans * R * h->n_ints);
+    cudaMemcpy(b.data(), d_ising_samples, b.size(), cudaMemcpyDeviceToHost);
+    for (size_t i = 0; i < b.size(); i++) out->intSamples[i] = b[i];
+  }
+  cudaError_t e = cudaGetLastError();
+  for (void* p : tmp) cudaFree(p);
+  if (!rc && e != cudaSuccess) FAIL(h, BLANGPT_ECUDA, "run_scans: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+extern "C" int blangpt_get_round_stats(blangpt_handle* h, blangpt_round_stats* o) {
+  if (!h || !o) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  const int64_t M = h->M_total; const int N = h->cfg.nChains, R = h->cfg.nReplicas;
+  std::vector<long long> en_n(M), acc_n(M), ls_n(M); std::vector<double> en_m1(M), en_m2(M), cov_c(M), acc_m1(M), ls_sum(M);
+  std::vector<int> cov_n(M); std::vector<unsigned long long> rej(R); std::vector<double> tab(M * 4);
+  auto get = [&](void* dst, const void* src, size_t b) { return cudaMemcpyAsync(dst, src, b, cudaMemcpyDeviceToHost, h->stream); };
+  CUDA_OK(h, get(en_n.data(), h->St.en_n, M * 8)); CUDA_OK(h, get(en_m1.data(), h->St.en_m1, M * 8));
+  CUDA_OK(h, get(en_m2.data(), h->St.en_m2, M * 8)); CUDA_OK(h, get(cov_c.data(), h->St.cov_c, M * 8));
+  CUDA_OK(h, get(cov_n.data(), h->St.cov_n, M * 4)); CUDA_OK(h, get(acc_n.data(), h->St.acc_n, M * 8));
+  CUDA_OK(h, get(acc_m1.data(), h->St.acc_m1, M * 8)); CUDA_OK(h, get(ls_sum.data(), h->St.ls_sum, M * 8));
+  CUDA_OK(h, get(ls_n.data(), h->St.ls_n, M * 8)); CUDA_OK(h, get(rej.data(), h->St.rejuv, R * 8));
+  CUDA_OK(h, get(tab.data(), h->E.table, M * 4 * 8));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  o->nScansInRound = h->scans_in_round;
+  const double nan = std::nan("");
+  for (int r = 0; r < R; r++) {
+    double Lambda = 0.0, ss = 0.0, thermo = 0.0; bool oos = false;
+    for (int p = 0; p < N; p++) {
+      const size_t i = (size_t)r * N + p;
+      const double mean = en_n[i] ? en_m1[i] : nan;
+      if (o->energyMean) o->energyMean[i] = mean;
+      if (o->energyVariance) o->energyVariance[i] = en_n[i] == 0 ? nan : (en_n[i] == 1 ? 0.0 : en_m2[i] / ((double)en_n[i] - 1.0));
+      if (o->energyCovariance) o->energyCovariance[i] = cov_c[i] / cov_n[i];
+      if (tab[i * 4 + 1] > 0 && h->cfg.annealSupport) oos = true;
+      if (p < N - 1) {
+        const double a = acc_n[i] ? acc_m1[i] : nan;
+        if (o->swapAcceptMean) o->swapAcceptMean[i] = a;
+        if (o->logSum) o->logSum[i] = ls_sum[i];
+        if (o->logSumN) o->logSumN[i] = ls_n[i];
+        Lambda += 1.0 - a;
+        ss += ls_sum[i] - log((double)ls_n[i]);
+        const double next_mean = en_n[i + 1] ? en_m1[i + 1] : nan;
+        thermo += (h->ladder[i] - h->ladder[i + 1]) * (mean + next_mean) / 2.0;
+      } else {
+        if (o->swapAcceptMean) o->swapAcceptMean[i] = nan;
+        if (o->logSum) o->logSum[i] = nan;
+        if (o->logSumN) o->logSumN[i] = 0;
+      }
+    }
+    if (o->roundTrips) o->roundTrips[r] = (int64_t)rej[r];
+    if (o->Lambda) o->Lambda[r] = Lambda;
+    if (o->logZSteppingStone) o->logZSteppingStone[r] = N == 1 ? nan : ss;
+    if (o->logZThermodynamic) o->logZThermodynamic[r] = oos ? nan : -thermo;
+  }
+  return BLANGPT_OK;
+}
+
+extern "C" int blangpt_reset_round(blangpt_handle* h) {
+  if (!h) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  return reset_round(h);
+}
+
+extern "C" int blangpt_adapt(blangpt_handle* h, double* cum_xy) {
+  if (!h) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  const int64_t M = h->M_total; const int N = h->cfg.nChains, R = h->cfg.nReplicas;
+  if (N < 2) return reset_round(h);
+  std::vector<long long> acc_n(M); std::vector<double> acc_m1(M);
+  CUDA_OK(h, cudaMemcpyAsync(acc_n.data(), h->St.acc_n, M * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaMemcpyAsync(acc_m1.data(), h->St.acc_m1, M * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < R; r++) {
+    std::vector<double> betas(h->ladder.begin() + (size_t)r * N, h->ladder.begin() + (size_t)(r + 1) * N);
+    std::vector<double> acc(N - 1);
+    for (int i = 0; i < N - 1; i++) acc[i] = acc_n[(size_t)r * N + i] ? acc_m1[(size_t)r * N + i] : std::nan("");
+    std::vector<double> cx, cy;
+    std::vector<double> upd = adapt_ladder(betas, acc, &cx, &cy);
+    for (int i = 0; i < N; i++) if (!(upd[i] >= 0.0 && upd[i] <= 1.0)) FAIL(h, BLANGPT_ENUMERIC, "adapt produced an invalid ladder");
+    upd[0] = 1.0;
+    std::copy(upd.begin(), upd.end(), h->ladder.begin() + (size_t)r * N);
+    if (cum_xy) { std::copy(cx.begin(), cx.end(), cum_xy + (size_t)r * 2 * N); std::copy(cy.begin(), cy.end(), cum_xy + (size_t)r * 2 * N + N); }
+  }
+  CUDA_OK(h, cudaMemcpyAsync((void*)h->E.ladder, h->ladder.data(), M * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return reset_round(h);
+}
+
+extern "C" int blangpt_rounds(int32_t nScans, double f, int32_t* rn, int32_t* ra) {
+  if (f < 0.0 || f >= 1.0 || !rn || !ra) return -1;
+  std::vector<Round> r = rounds(nScans, f);
+  if (r.size() > 64) return -1;
+  for (size_t i = 0; i < r.size(); i++) { rn[i] = r[i].n_scans; ra[i] = r[i].is_adapt ? 1 : 0; }
+  return (int)r.size();
+}
+
+extern "C" int blangpt_perform_inference(blangpt_handle* h, int32_t nScans, double adaptFraction, int32_t thinning,
+                                         const blangpt_scan_outputs* out, blangpt_inference_summary* sum) {
+  if (!h) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  if (adaptFraction < 0.0 || adaptFraction >= 1.0) FAIL(h, BLANGPT_EINVAL, "adaptFraction must be in [0,1)");
+  (void)thinning;   // samples are recorded every scan; thinning is applied by the writer
+  const int N = h->cfg.nChains, R = h->cfg.nReplicas; const int64_t M = h->M_total;
+  const double f = N == 1 ? 0.0 : adaptFraction;   // PT.java:235
+  std::vector<Round> rs = rounds(nScans, f);
+  if (rs.size() > 64) FAIL(h, BLANGPT_EINVAL, "too many rounds");
+  if (sum) { sum->nRounds = (int)rs.size(); }
+  int64_t scan = 0; int rc;
+  std::vector<double> acc(M), Lam(R), lz(R), lzt(R); std::vector<int64_t> rt(R);
+  for (size_t r = 0; r < rs.size(); r++) {
+    auto t0 = std::chrono::steady_clock::now();
+    blangpt_scan_outputs o{};
+    if (out) {
+      if (out->energy) o.energy = out->energy + scan * M;
+      if (out->logDensity) o.logDensity = out->logDensity + scan * M;
+      if (out->nOutOfSupport) o.nOutOfSupport = out->nOutOfSupport + scan * M;
+      if (out->swapIndicators) o.swapIndicators = out->swapIndicators + scan * M;
+      if (out->samples) o.samples = out->samples + scan * R * h->n_reals;
+      if (out->intSamples) o.intSamples = out->intSamples + scan * R * h->n_ints;
+    }
+    if ((rc = blangpt_run_scans(h, rs[r].n_scans, out ? &o : nullptr))) return rc;
+    scan += rs[r].n_scans;
+    if (sum) { sum->roundNScans[r] = rs[r].n_scans; sum->roundIsAdapt[r] = rs[r].is_adapt; }
+    if (N > 1) {
+      blangpt_round_stats st{};
+      st.swapAcceptMean = acc.data(); st.Lambda = Lam.data(); st.logZSteppingStone = lz.data();
+      st.logZThermodynamic = lzt.data(); st.roundTrips = rt.data();
+      if ((rc = blangpt_get_round_stats(h, &st))) return rc;
+      if (sum) for (int q = 0; q < R; q++) {
+        if (sum->Lambda) sum->Lambda[r * R + q] = Lam[q];
+        if (sum->logZ) sum->logZ[r * R + q] = lz[q];
+        if (sum->roundTrips) sum->roundTrips[r * R + q] = rt[q];
+        double mn = INFINITY, mean = 0.0;
+        for (int i = 0; i < N - 1; i++) { const double a = acc[(size_t)q * N + i]; if (a < mn) mn = a; mean += a; }
+        if (sum->minAccept) sum->minAccept[r * R + q] = mn;
+        if (sum->meanAccept) sum->meanAccept[r * R + q] = mean / (N - 1);
+      }
+      // the reference also adapts after the last round "for instrumentation" (PT.java:103-107);
+      // we keep the final round's accumulators readable instead
+      if (r + 1 < rs.size() && (rc = blangpt_adapt(h, nullptr))) return rc;
+    }
+    if (sum) sum->roundMillis[r] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+  return BLANGPT_OK;
+}
+
+extern "C" int blangpt_counters(blangpt_handle* h, uint64_t out[4]) {
+  if (!h || !out) return BLANGPT_EINVAL;
+  out[0] = out[1] = out[2] = out[3] = 0;
+  if (!h->model_set) return BLANGPT_OK;
+  std::vector<unsigned long long> ev(h->E.M_local), ex(h->E.M_local);
+  CUDA_OK(h, cudaMemcpyAsync(ev.data(), h->E.evals, ev.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaMemcpyAsync(ex.data(), h->E.execs, ex.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  for (auto v : ev) out[0] += v;
+  for (auto v : ex) out[3] += v;
+  out[1] = h->n_scans; out[2] = h->n_launches;
+  return BLANGPT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// split-phase multi-GPU path
+// ---------------------------------------------------------------------------
+extern "C" int blangpt_set_stream(blangpt_handle* h, void* s) {
+  if (!h) return BLANGPT_EINVAL;
+  h->stream = (cudaStream_t)s;
+  return BLANGPT_OK;
+}
+extern "C" int blangpt_evaluate(blangpt_handle* h) {
+  if (!h) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  return launch_explore(h, MODE_EVAL);
+}
+extern "C" int blangpt_prime(blangpt_handle* h) {
+  if (!h) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  prime_prev_kernel<<<(unsigned)((h->M_total + 255) / 256), 256, 0, h->stream>>>(h->E);
+  CUDA_OK(h, cudaGetLastError());
+  h->n_launches++;
+  h->tables_valid = true;
+  return BLANGPT_OK;
+}
+extern "C" int blangpt_explore(blangpt_handle* h) {
+  if (!h) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  if (!h->tables_valid) FAIL(h, BLANGPT_ESTATE, "call blangpt_evaluate, gather the table and blangpt_prime before the first blangpt_explore");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  return launch_explore(h, MODE_EXPLORE);
+}
+extern "C" void* blangpt_table_ptr(blangpt_handle* h, int32_t which) {
+  if (!h || !h->model_set) return nullptr;
+  return which == 0 ? (void*)h->E.table : (void*)h->E.send;
+}
+extern "C" int64_t blangpt_local_chains(const blangpt_handle* h, int64_t* first) {
+  if (!h || !h->model_set) return -1;
+  if (first) *first = h->E.slot_lo;
+  return h->E.M_local;
+}
+extern "C" int blangpt_swap(blangpt_handle* h, const blangpt_scan_outputs* out) {
+  if (!h) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  (void)out;
+  CUDA_OK(h, cudaMemsetAsync(h->E.batch_counter, 0, sizeof(uint32_t) * h->cfg.nReplicas, h->stream));
+  DevOut O{}; O.n_reals = h->n_reals; O.reversible = h->cfg.reversible;
+  int rc = launch_swap(h, O);
+  if (rc) return rc;
+  h->n_scans++; h->scans_in_round++;
+  return BLANGPT_OK;
+}
+extern "C" int blangpt_synchronize(blangpt_handle* h) {
+  if (!h) return BLANGPT_EINVAL;
+  return check_device_errors(h);
+}

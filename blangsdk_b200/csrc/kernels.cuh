@@ -1,0 +1,295 @@
+// kernels.cuh -- the three kernels of one NRPT scan.
+//
+//   explore_kernel<Fam>  local exploration of every chain slot: the reference's
+//                        ParallelTempering.moveKernel (R/engines/ParallelTempering.java:77-92)
+//                        = SampledModel.posteriorSamplingScan (R/runtime/SampledModel.java:249-282)
+//                        or forwardSample at beta = 0 (:284-291).  One thread-block
+//                        cluster per chain; ends with a from-scratch evaluation of
+//                        (loglik, nOutOfSupport, fixed) into the per-slot table.
+//   swap_kernel          energy accumulators + DEO swap pass + index process:
+//                        ParallelTempering.swapKernel / swapAcceptPr / doSwap (:64-75,99-124,155-164),
+//                        the accumulators of :88-90 and Paths.nRejuvenations
+//                        (R/engines/internals/ptanalysis/Paths.xtend:40-50).  Swaps permute
+//                        temperature POSITIONS between fixed slots; states never move.
+//   reset_round_kernel   ParallelTempering.setAnnealingParameters :197-204.
+#pragma once
+#include "common.cuh"
+#include "reduce.cuh"
+#include "slice.cuh"
+#include "families.cuh"
+
+namespace bpt {
+
+enum ExploreMode : int { MODE_EXPLORE = 0, MODE_EVAL = 1, MODE_FORWARD_INIT = 2 };
+
+struct DevEngine {
+  int N, R;                 // chains per replica, replicas in this handle
+  int slot_lo, M_local;     // first local global-slot, number of local slots
+  uint32_t key0, key1;      // Philox key: (seed lo, seed hi); replica folded into key1
+  uint32_t replica_offset;
+  double n_passes;
+  int use_prior, anneal_support;
+  int s_max;                // stride of the order array
+  const double* ladder;     // [R][N] descending
+  int* pos_of_slot;         // [R][N] (slot-in-replica -> position)
+  int* slot_of_pos;         // [R][N]
+  double* table;            // [R*N][4]: loglik, noos, fixed, evals-this-scan
+  double* send;             // [M_local][4] copy of the local segment (multi-GPU all-gather source)
+  double* prev_loglik;      // [R*N] loglik at the start of the scan (energy "before")
+  double* reals;            // [nReals][M_local] structure of arrays
+  int* order;               // [M_local][s_max] SampledModel.currentSamplingOrder
+  int* curpos;              // [M_local]        SampledModel.currentPosition
+  unsigned long long* evals;// [M_local]
+  unsigned long long* execs;// [M_local]
+  int* err;                 // sticky error bits
+  uint32_t* scan_counter;   // [R] scans done (Philox `scan`)
+  uint32_t* swap_counter;   // [R] ParallelTempering.swapIndex
+  uint32_t* batch_counter;  // [R] scan index inside the current run_scans batch
+};
+
+struct DevStats {     // all indexed [R][N] by temperature position unless noted
+  long long* en_n; double* en_m1; double* en_m2;              // energies (SummaryStatistics)
+  double* cov_mx; double* cov_my; double* cov_c; int* cov_n;  // CovarAccumulator
+  long long* acc_n; double* acc_m1;                           // swapAcceptPrs
+  double* ls_sum; long long* ls_n;                            // LogSumAccumulator
+  int* path_flag;                                             // [R][N] by slot: Paths "newSample"
+  unsigned long long* rejuv;                                  // [R]
+  unsigned long long* total_evals;                            // [1]
+};
+
+struct DevOut {       // per-scan outputs of the current batch (nullable)
+  double* energy; double* logdens; int* noos; int* indicators; double* samples; int n_reals;
+  int reversible;
+};
+
+template <class Fam>
+__global__ void __launch_bounds__(Fam::kThreads)
+explore_kernel(DevEngine E, typename Fam::Data D, int G, int mode) {
+  __shared__ ReduceSmem rs;
+  __shared__ double P[kMaxParams + 4 * 8];
+  __shared__ int order[kMaxSamplers];
+
+  const int tid = threadIdx.x;
+  const int l = blockIdx.x / G;
+  const int crank = blockIdx.x % G;
+  const int g = E.slot_lo + l;
+  const int rep = g / E.N, s_in_rep = g - rep * E.N;
+  const int pos = E.pos_of_slot[rep * E.N + s_in_rep];
+  const double beta = E.ladder[rep * E.N + pos];
+  const uint32_t scan = E.scan_counter[rep];
+  const uint32_t key1 = E.key1 ^ (E.replica_offset + (uint32_t)rep);
+
+  Fam fam;
+  fam.init(D, l, P, G, crank, E.err);
+  const int nR = Fam::n_reals(D), S = Fam::n_samplers(D);
+  for (int v = tid; v < nR; v += blockDim.x) P[v] = E.reals[(size_t)v * E.M_local + l];
+  for (int k = tid; k < S; k += blockDim.x) order[k] = E.order[(size_t)l * E.s_max + k];
+  int curpos = E.curpos[l];
+  __syncthreads();
+
+  GroupReducer red;
+  red.init(&rs, G, crank);
+  unsigned long long evals = 0, execs = 0;
+  int err = 0;
+
+  if (mode == MODE_FORWARD_INIT) {
+    Rng rng(E.key0, key1, P_INIT, (uint32_t)pos, 0u, 0u);
+    fam.forward(rng);
+  } else if (mode == MODE_EXPLORE) {
+    if (beta == 0.0 && E.use_prior) {
+      Rng rng(E.key0, key1, P_FORWARD, (uint32_t)pos, scan, 0u);
+      fam.forward(rng);
+    } else {
+      const int n_steps = (int)floor(E.n_passes * S);
+      for (int t = 0; t < n_steps; t++) {
+        __syncthreads();
+        if (curpos == -1) {   // Collections.shuffle(order, rnd); SampledModel.java:267-272
+          if (tid == 0) {
+            Rng sh(E.key0, key1, P_SHUFFLE, (uint32_t)pos, scan, (uint32_t)t);
+            for (int i = S; i > 1; i--) {
+              const int j = sh.next_int(i);
+              const int tmp = order[i - 1]; order[i - 1] = order[j]; order[j] = tmp;
+            }
+          }
+          __syncthreads();
+          curpos = S - 1;
+        }
+        const int k = order[curpos--];
+        Rng rng(E.key0, key1, P_MOVE, (uint32_t)pos, scan, (uint32_t)t);
+        int aux = 0;
+        // RealSliceSampler.logDensity :156-161 over ExponentiatedFactor.logDensity :70-80
+        auto lp = [&](double x) -> double {
+          evals++;
+          const double fx = fam.fixed(k, x, aux);
+          if (beta == 0.0 || fx == BPT_NEG_INF) return fx;
+          double s; int c;
+          fam.annealed(k, x, aux, red, s, c);
+          double a = beta * s;
+          if (c) a += E.anneal_support ? c * annealed_minus_infinity(beta) : BPT_NEG_INF;
+          return fx + a;
+        };
+        execs++;
+        if (fam.sampler_type(k) == S_REAL_SLICE) {
+          const double x0 = P[fam.sampler_var(k)];
+          const double xn = real_slice(lp, rng, x0, false, 0.0, 0.0, err);
+          fam.commit(k, xn, 0);
+        } else {   // SimplexSampler.xtend:21-28
+          const int K = fam.simplex_dim();
+          aux = rng.next_int(K);
+          const int base = fam.sampler_var(k);
+          const int nx = aux == K - 1 ? 0 : aux + 1;
+          const double x0 = P[base + aux];
+          const double sum = P[base + aux] + P[base + nx];
+          const double xn = real_slice(lp, rng, x0, true, 0.0, sum, err);
+          fam.commit(k, xn, aux);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  double loglik, logprior; int noos;
+  fam.full(red, loglik, noos, logprior);
+  __syncthreads();
+  if (crank == 0) {
+    for (int v = tid; v < nR; v += blockDim.x) E.reals[(size_t)v * E.M_local + l] = P[v];
+    for (int k = tid; k < S; k += blockDim.x) E.order[(size_t)l * E.s_max + k] = order[k];
+    if (tid == 0) {
+      double* t = E.table + (size_t)g * 4;
+      t[0] = loglik; t[1] = (double)noos; t[2] = logprior; t[3] = (double)evals;
+      double* sd = E.send + (size_t)l * 4;
+      sd[0] = loglik; sd[1] = (double)noos; sd[2] = logprior; sd[3] = (double)evals;
+      E.curpos[l] = curpos;
+      E.evals[l] += evals;
+      E.execs[l] += execs;
+      if (err) atomicOr(E.err, err);
+    }
+  }
+}
+
+// commons-math3 SummaryStatistics first/second moment recurrences
+BPT_D void summary_add(long long& n, double& m1, double& m2, double x) {
+  if (n == 0) { m1 = 0.0; m2 = 0.0; }
+  n++;
+  const double dev = x - m1, ndev = dev / (double)n;
+  m1 += ndev;
+  m2 += ((double)n - 1.0) * dev * ndev;
+}
+
+__global__ void swap_kernel(DevEngine E, DevStats St, DevOut O) {
+  const int rep = blockIdx.x, N = E.N, tid = threadIdx.x;
+  const size_t base = (size_t)rep * N;
+  const double* ladder = E.ladder + base;
+  int* sop = E.slot_of_pos + base;
+  int* pos_of = E.pos_of_slot + base;
+  const uint32_t scan = E.scan_counter[rep];
+  const uint32_t swap_index = E.swap_counter[rep];
+  const uint32_t b = E.batch_counter[rep];
+  const uint32_t key1 = E.key1 ^ (E.replica_offset + (uint32_t)rep);
+  const size_t obase = ((size_t)b * E.R + rep) * N;
+
+  // ---- A: accumulators of moveKernel :88-90 and the per-scan records (PT.java:116-143,360-372)
+  unsigned long long ev = 0;
+  for (int p = tid; p < N; p += blockDim.x) {
+    const int s = sop[p];
+    const size_t g = base + s;
+    const double ll = E.table[g * 4 + 0], no = E.table[g * 4 + 1], fx = E.table[g * 4 + 2];
+    ev += (unsigned long long)E.table[g * 4 + 3];
+    const double after = -ll, before = -E.prev_loglik[g];
+    E.prev_loglik[g] = ll;
+    summary_add(St.en_n[base + p], St.en_m1[base + p], St.en_m2[base + p], after);
+    {   // CovarAccumulator.add :7-13
+      int n = St.cov_n[base + p] + 1;
+      double mx = St.cov_mx[base + p], my = St.cov_my[base + p];
+      const double dx = before - mx;
+      mx += dx / n; my += (after - my) / n;
+      St.cov_c[base + p] += dx * (after - my);
+      St.cov_mx[base + p] = mx; St.cov_my[base + p] = my; St.cov_n[base + p] = n;
+    }
+    if (O.energy) O.energy[obase + p] = after;
+    if (O.logdens) O.logdens[obase + p] = annealed_log_density(fx, ll, no, ladder[p], E.anneal_support);
+    if (O.noos) O.noos[obase + p] = (int)no;
+    if (O.indicators) O.indicators[obase + p] = 0;
+    if (p == 0 && O.samples) {
+      const int l = (int)g - E.slot_lo;
+      if (l >= 0 && l < E.M_local)
+        for (int v = 0; v < O.n_reals; v++)
+          O.samples[((size_t)b * E.R + rep) * O.n_reals + v] = E.reals[(size_t)v * E.M_local + l];
+    }
+  }
+  if (ev) atomicAdd(St.total_evals, ev);
+  __syncthreads();
+
+  // ---- B: swapKernel :64-75
+  if (N > 1) {
+    int offset;
+    if (O.reversible) { Rng r(E.key0, key1, P_SWAPDIR, 0u, scan, 0u); offset = r.next_int(2); }
+    else offset = (int)(swap_index & 1u);
+    const int n_pairs = (N - offset) / 2;
+    for (int q = tid; q < n_pairs; q += blockDim.x) {
+      const int i = offset + 2 * q, j = i + 1;
+      const int si = sop[i], sj = sop[j];
+      const double* ti = E.table + (base + si) * 4;
+      const double* tj = E.table + (base + sj) * 4;
+      const double bi = ladder[i], bj = ladder[j];
+      // swapAcceptPr :107-124
+      const double ss = annealed_log_density(tj[2], tj[0], tj[1], bi, E.anneal_support) -
+                        annealed_log_density(tj[2], tj[0], tj[1], bj, E.anneal_support);
+      St.ls_sum[base + i] = log_add(St.ls_sum[base + i], ss);
+      St.ls_n[base + i] += 1;
+      const double log_ratio = ss + annealed_log_density(ti[2], ti[0], ti[1], bj, E.anneal_support) -
+                               annealed_log_density(ti[2], ti[0], ti[1], bi, E.anneal_support);
+      double a = fmin(1.0, exp(log_ratio));
+      if (log_ratio != log_ratio || a != a) a = 0.0;
+      Rng r(E.key0, key1, P_SWAP, (uint32_t)i, scan, 0u);
+      if (r.bernoulli(a)) {   // doSwap :155-164
+        sop[i] = sj; sop[j] = si;
+        pos_of[sj] = i; pos_of[si] = j;
+        if (O.indicators) O.indicators[obase + i] = 1;
+      }
+      double m2_unused = 0.0;
+      summary_add(St.acc_n[base + i], St.acc_m1[base + i], m2_unused, a);
+    }
+    __syncthreads();
+    // ---- C: index process, Paths.xtend:40-50 (particle identity = slot)
+    unsigned long long rj = 0;
+    for (int p = tid; p < N; p += blockDim.x) {
+      const int s = sop[p];
+      int f = St.path_flag[base + s];
+      if (p == 0 && f) { f = 0; rj++; }
+      else if (p == N - 1) f = 1;
+      St.path_flag[base + s] = f;
+    }
+    if (rj) atomicAdd(&St.rejuv[rep], rj);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    E.scan_counter[rep] = scan + 1;
+    if (N > 1) E.swap_counter[rep] = swap_index + 1;
+    E.batch_counter[rep] = b + 1;
+  }
+}
+
+// energy "before" of the next scan = current table (called after an evaluation-only pass)
+__global__ void prime_prev_kernel(DevEngine E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < E.R * E.N) E.prev_loglik[i] = E.table[(size_t)i * 4];
+}
+
+// ParallelTempering.setAnnealingParameters :197-204 + Paths.initPaths :131-139
+__global__ void reset_round_kernel(DevEngine E, DevStats St) {
+  const int rep = blockIdx.x, N = E.N;
+  const size_t base = (size_t)rep * N;
+  for (int p = threadIdx.x; p < N; p += blockDim.x) {
+    St.en_n[base + p] = 0; St.en_m1[base + p] = 0.0; St.en_m2[base + p] = 0.0;
+    St.cov_mx[base + p] = 0.0; St.cov_my[base + p] = 0.0; St.cov_c[base + p] = 0.0; St.cov_n[base + p] = 0;
+    St.acc_n[base + p] = 0; St.acc_m1[base + p] = 0.0;
+    St.ls_sum[base + p] = BPT_NEG_INF; St.ls_n[base + p] = 0;
+    // initial visit of the particle sitting at position p
+    const int s = E.slot_of_pos[base + p];
+    St.path_flag[base + s] = (p == N - 1) ? 1 : 0;
+  }
+  if (threadIdx.x == 0) St.rejuv[rep] = 0;
+}
+
+}  // namespace bpt

@@ -1,0 +1,359 @@
+"""ctypes binding of libblangpt.so + a Python mirror of the reference's PT engine options.
+
+`PT` keeps the option names of blang.engines.internals.factories.PT
+(R/engines/internals/factories/PT.java:47-82) and blang.engines.ParallelTempering
+(R/engines/ParallelTempering.java:25-40) so a test reads like the reference's own:
+
+    pt = PT(nChains=8, nScans=1000, adaptFraction=0.5, random=1, initialization="FORWARD")
+    pt.setSampledModel(datasets.normal_meanvar())
+    result = pt.performInference()
+
+Everything numeric happens inside the CUDA library; this module only marshals
+pointers.  There is no CPU fallback: if the library or a GPU is missing the
+constructor raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libblangpt.so")
+
+FAMILIES = {"normal": 1, "logistic": 2, "mixture": 3, "ising": 4, "betabinomial": 5}
+INIT = {"COPIES": 0, "FORWARD": 1, "SCM": 2}
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+
+class BlangPTError(RuntimeError):
+    """Raised for every non-zero status of the C ABI (the reference throws RuntimeException)."""
+
+
+class Config(C.Structure):
+    _fields_ = [("nChains", C.c_int32), ("nReplicas", C.c_int32), ("random", C.c_uint64),
+                ("nPassesPerScan", C.c_double), ("usePriorSamples", C.c_int32), ("reversible", C.c_int32),
+                ("annealSupport", C.c_int32), ("treatNaNAsNegativeInfinity", C.c_int32), ("device", C.c_int32),
+                ("rank", C.c_int32), ("worldSize", C.c_int32), ("ctasPerChain", C.c_int32),
+                ("replicaOffset", C.c_int64), ("statisticRecordedMaxChainIndex", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class Array(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("n_elem", C.c_int64), ("dtype", C.c_int32), ("rows", C.c_int32),
+                ("cols", C.c_int32)]
+
+
+class ScanOutputs(C.Structure):
+    _fields_ = [("energy", _dp), ("logDensity", _dp), ("nOutOfSupport", _ip), ("swapIndicators", _ip),
+                ("samples", _dp), ("intSamples", _ip)]
+
+
+class RoundStats(C.Structure):
+    _fields_ = [("nScansInRound", C.c_int64), ("swapAcceptMean", _dp), ("energyMean", _dp),
+                ("energyVariance", _dp), ("energyCovariance", _dp), ("logSum", _dp), ("logSumN", _lp),
+                ("roundTrips", _lp), ("Lambda", _dp), ("logZSteppingStone", _dp), ("logZThermodynamic", _dp)]
+
+
+class InferenceSummary(C.Structure):
+    _fields_ = [("nRounds", C.c_int32), ("roundNScans", C.c_int32 * 64), ("roundIsAdapt", C.c_int32 * 64),
+                ("Lambda", _dp), ("logZ", _dp), ("roundTrips", _lp), ("minAccept", _dp), ("meanAccept", _dp),
+                ("roundMillis", C.c_double * 64)]
+
+
+EXPORTS = [
+    "blangpt_default_config", "blangpt_create", "blangpt_destroy", "blangpt_last_error", "blangpt_set_model",
+    "blangpt_n_reals", "blangpt_n_ints", "blangpt_n_samplers", "blangpt_set_ladder", "blangpt_get_ladder",
+    "blangpt_set_state", "blangpt_get_state", "blangpt_initialize", "blangpt_log_density", "blangpt_run_scans",
+    "blangpt_get_round_stats", "blangpt_adapt", "blangpt_reset_round", "blangpt_rounds",
+    "blangpt_perform_inference", "blangpt_counters", "blangpt_set_stream", "blangpt_evaluate", "blangpt_prime",
+    "blangpt_explore", "blangpt_table_ptr", "blangpt_local_chains", "blangpt_swap", "blangpt_synchronize",
+]
+
+_LIB = None
+
+
+def load_library():
+    """dlopen libblangpt.so (built in-tree by __graft_entry__.build()).  Fails loudly when absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise BlangPTError("libblangpt.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.blangpt_default_config.argtypes = [C.POINTER(Config)]
+    L.blangpt_default_config.restype = None
+    L.blangpt_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.blangpt_destroy.argtypes = [vp]
+    L.blangpt_destroy.restype = None
+    L.blangpt_last_error.argtypes = [vp]
+    L.blangpt_last_error.restype = C.c_char_p
+    L.blangpt_set_model.argtypes = [vp, C.c_int32, C.POINTER(Array), C.c_int32, _dp, C.c_int32]
+    for f in ("blangpt_n_reals", "blangpt_n_ints", "blangpt_n_samplers"):
+        getattr(L, f).argtypes = [vp]
+    L.blangpt_set_ladder.argtypes = [vp, _dp, C.c_int64]
+    L.blangpt_get_ladder.argtypes = [vp, _dp, C.c_int64]
+    L.blangpt_set_state.argtypes = [vp, C.c_int64, C.c_int32, _dp, _ip]
+    L.blangpt_get_state.argtypes = [vp, C.c_int64, C.c_int32, _dp, _ip]
+    L.blangpt_initialize.argtypes = [vp, C.c_int32]
+    L.blangpt_log_density.argtypes = [vp, _dp, _dp, _ip, _dp]
+    L.blangpt_run_scans.argtypes = [vp, C.c_int32, C.POINTER(ScanOutputs)]
+    L.blangpt_get_round_stats.argtypes = [vp, C.POINTER(RoundStats)]
+    L.blangpt_adapt.argtypes = [vp, _dp]
+    L.blangpt_reset_round.argtypes = [vp]
+    L.blangpt_rounds.argtypes = [C.c_int32, C.c_double, _ip, _ip]
+    L.blangpt_perform_inference.argtypes = [vp, C.c_int32, C.c_double, C.c_int32, C.POINTER(ScanOutputs),
+                                            C.POINTER(InferenceSummary)]
+    L.blangpt_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.blangpt_set_stream.argtypes = [vp, vp]
+    for f in ("blangpt_evaluate", "blangpt_prime", "blangpt_explore", "blangpt_synchronize"):
+        getattr(L, f).argtypes = [vp]
+    L.blangpt_table_ptr.argtypes = [vp, C.c_int32]
+    L.blangpt_table_ptr.restype = vp
+    L.blangpt_local_chains.argtypes = [vp, _lp]
+    L.blangpt_local_chains.restype = C.c_int64
+    L.blangpt_swap.argtypes = [vp, C.POINTER(ScanOutputs)]
+    _LIB = L
+    return L
+
+
+def rounds(nScans, adaptFraction):
+    """PT.rounds (PT.java:239-265) -> [(nScans, isAdapt), ...]"""
+    rn = (C.c_int32 * 64)()
+    ra = (C.c_int32 * 64)()
+    k = load_library().blangpt_rounds(nScans, adaptFraction, rn, ra)
+    if k < 0:
+        raise BlangPTError("adaptFraction must be in [0,1)")
+    return [(int(rn[i]), bool(ra[i])) for i in range(k)]
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+class Engine:
+    """Thin object wrapper over one blangpt_handle."""
+
+    def __init__(self, nChains=8, nReplicas=1, random=1, nPassesPerScan=3.0, usePriorSamples=True,
+                 reversible=False, annealSupport=True, treatNaNAsNegativeInfinity=False, device=0, rank=0,
+                 worldSize=1, ctasPerChain=0, replicaOffset=0):
+        self.L = load_library()
+        cfg = Config()
+        self.L.blangpt_default_config(C.byref(cfg))
+        cfg.nChains, cfg.nReplicas, cfg.random = int(nChains), int(nReplicas), int(random)
+        cfg.nPassesPerScan = float(nPassesPerScan)
+        cfg.usePriorSamples, cfg.reversible = int(usePriorSamples), int(reversible)
+        cfg.annealSupport, cfg.treatNaNAsNegativeInfinity = int(annealSupport), int(treatNaNAsNegativeInfinity)
+        cfg.device, cfg.rank, cfg.worldSize = int(device), int(rank), int(worldSize)
+        cfg.ctasPerChain, cfg.replicaOffset = int(ctasPerChain), int(replicaOffset)
+        self.cfg = cfg
+        self.N, self.R = int(nChains), int(nReplicas)
+        self.h = C.c_void_p()
+        rc = self.L.blangpt_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            self.h = C.c_void_p()
+            raise BlangPTError(self.L.blangpt_last_error(None).decode())
+        self.n_reals = self.n_ints = self.n_samplers = 0
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.blangpt_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BlangPTError(self.L.blangpt_last_error(self.h).decode())
+
+    # ---- model ----
+    def set_model(self, spec):
+        fam = spec["family"]
+        h = spec["hyper"]
+        keep = []
+
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dtype=np.float64 if dt == 0 else np.int32)
+            keep.append(a)
+            return Array(a.ctypes.data, a.size, dt, a.shape[0] if a.ndim else 1, a.shape[1] if a.ndim > 1 else 1)
+
+        if fam == "normal":
+            arrays, hyper = [arr(spec["y"], 0)], [h["m0"], h["v0"], h["rate"]]
+        elif fam == "logistic":
+            arrays, hyper = [arr(spec["x"], 0), arr(spec["y"], 1)], [h["v0"]]
+        elif fam == "mixture":
+            arrays = [arr(spec["y"], 0)]
+            hyper = [float(h["K"]), h["m0"], h["v0"], h["gshape"], h["grate"], h["conc"]]
+        elif fam == "ising":
+            arrays, hyper = [], [float(h["N"]), h["coupling"], h["moment"]]
+        elif fam == "betabinomial":
+            arrays, hyper = [arr(spec["y"], 1), arr(spec["ntrials"], 1)], [h["rate"]]
+        else:
+            raise BlangPTError("unsupported model family %r (closed catalogue; no CPU fallback)" % fam)
+        ca = (Array * max(1, len(arrays)))(*arrays)
+        hy = np.asarray(hyper, dtype=np.float64)
+        self._check(self.L.blangpt_set_model(self.h, FAMILIES[fam], ca, len(arrays), _d(hy), len(hy)))
+        self.n_reals = self.L.blangpt_n_reals(self.h)
+        self.n_ints = self.L.blangpt_n_ints(self.h)
+        self.n_samplers = self.L.blangpt_n_samplers(self.h)
+        self.family = fam
+
+    def set_ladder(self, betas):
+        b = np.ascontiguousarray(betas, dtype=np.float64).ravel()
+        self._check(self.L.blangpt_set_ladder(self.h, _d(b), b.size))
+
+    def get_ladder(self):
+        out = np.zeros(self.R * self.N)
+        self._check(self.L.blangpt_get_ladder(self.h, _d(out), out.size))
+        return out.reshape(self.R, self.N)
+
+    def set_state(self, position, reals=None, ints=None, replica=0):
+        re = None if reals is None else np.ascontiguousarray(reals, dtype=np.float64)
+        it = None if ints is None else np.ascontiguousarray(ints, dtype=np.int32)
+        self._check(self.L.blangpt_set_state(self.h, replica, position, _d(re), _i(it)))
+
+    def get_state(self, position, replica=0):
+        re = np.zeros(max(1, self.n_reals))
+        it = np.zeros(max(1, self.n_ints), dtype=np.int32)
+        self._check(self.L.blangpt_get_state(self.h, replica, position, _d(re), _i(it)))
+        return re[:self.n_reals], it[:self.n_ints]
+
+    def initialize(self, initialization="FORWARD"):
+        self._check(self.L.blangpt_initialize(self.h, INIT[initialization]))
+
+    def log_density(self):
+        M = self.R * self.N
+        ld, ll, fx = np.zeros(M), np.zeros(M), np.zeros(M)
+        no = np.zeros(M, dtype=np.int32)
+        self._check(self.L.blangpt_log_density(self.h, _d(ld), _d(ll), _i(no), _d(fx)))
+        sh = (self.R, self.N)
+        return dict(logdens=ld.reshape(sh), loglik=ll.reshape(sh), noos=no.reshape(sh), fixed=fx.reshape(sh))
+
+    def _outputs(self, n, want):
+        R, N = self.R, self.N
+        bufs = {}
+        so = ScanOutputs()
+        if "energy" in want:
+            bufs["energy"] = np.zeros((n, R, N)); so.energy = _d(bufs["energy"])
+        if "logDensity" in want:
+            bufs["logDensity"] = np.zeros((n, R, N)); so.logDensity = _d(bufs["logDensity"])
+        if "nOutOfSupport" in want:
+            bufs["nOutOfSupport"] = np.zeros((n, R, N), dtype=np.int32); so.nOutOfSupport = _i(bufs["nOutOfSupport"])
+        if "swapIndicators" in want:
+            bufs["swapIndicators"] = np.zeros((n, R, N), dtype=np.int32); so.swapIndicators = _i(bufs["swapIndicators"])
+        if "samples" in want and self.n_reals:
+            bufs["samples"] = np.zeros((n, R, self.n_reals)); so.samples = _d(bufs["samples"])
+        if "samples" in want and self.n_ints:
+            bufs["intSamples"] = np.zeros((n, R, self.n_ints), dtype=np.int32); so.intSamples = _i(bufs["intSamples"])
+        return so, bufs
+
+    def run_scans(self, n, want=("energy", "swapIndicators", "samples")):
+        so, bufs = self._outputs(n, want)
+        self._check(self.L.blangpt_run_scans(self.h, n, C.byref(so) if want else None))
+        return bufs
+
+    def round_stats(self):
+        R, N = self.R, self.N
+        a = {k: np.zeros((R, N)) for k in ("swapAcceptMean", "energyMean", "energyVariance", "energyCovariance", "logSum")}
+        lsn = np.zeros((R, N), dtype=np.int64)
+        rt = np.zeros(R, dtype=np.int64)
+        per = {k: np.zeros(R) for k in ("Lambda", "logZSteppingStone", "logZThermodynamic")}
+        st = RoundStats()
+        for k, v in a.items():
+            setattr(st, k, _d(v))
+        for k, v in per.items():
+            setattr(st, k, _d(v))
+        st.logSumN = lsn.ctypes.data_as(_lp)
+        st.roundTrips = rt.ctypes.data_as(_lp)
+        self._check(self.L.blangpt_get_round_stats(self.h, C.byref(st)))
+        out = dict(a)
+        out["swapAcceptMean"] = a["swapAcceptMean"][:, :N - 1]
+        out["logSum"] = a["logSum"][:, :N - 1]
+        out.update(per, logSumN=lsn[:, :N - 1], roundTrips=rt, nScansInRound=int(st.nScansInRound))
+        return out
+
+    def adapt(self):
+        knots = np.zeros((self.R, 2, self.N))
+        self._check(self.L.blangpt_adapt(self.h, _d(knots)))
+        return knots
+
+    def reset_round(self):
+        self._check(self.L.blangpt_reset_round(self.h))
+
+    def counters(self):
+        out = (C.c_uint64 * 4)()
+        self._check(self.L.blangpt_counters(self.h, out))
+        return dict(evals=int(out[0]), scans=int(out[1]), launches=int(out[2]), executions=int(out[3]))
+
+    def perform_inference(self, nScans, adaptFraction, thinning=1, want=("energy", "swapIndicators", "samples")):
+        rs = rounds(nScans, adaptFraction if self.N > 1 else 0.0)
+        total = sum(r[0] for r in rs)
+        so, bufs = self._outputs(total, want)
+        R = self.R
+        summ = InferenceSummary()
+        keep = {k: np.zeros((64, R)) for k in ("Lambda", "logZ", "minAccept", "meanAccept")}
+        rt = np.zeros((64, R), dtype=np.int64)
+        for k, v in keep.items():
+            setattr(summ, k, _d(v))
+        summ.roundTrips = rt.ctypes.data_as(_lp)
+        self._check(self.L.blangpt_perform_inference(self.h, nScans, adaptFraction, thinning,
+                                                     C.byref(so) if want else None, C.byref(summ)))
+        k = summ.nRounds
+        out_rounds = [dict(nScans=int(summ.roundNScans[i]), isAdapt=bool(summ.roundIsAdapt[i]),
+                           Lambda=keep["Lambda"][i].copy(), logZ=keep["logZ"][i].copy(), roundTrips=rt[i].copy(),
+                           minAccept=keep["minAccept"][i].copy(), meanAccept=keep["meanAccept"][i].copy(),
+                           millis=summ.roundMillis[i]) for i in range(k)]
+        bufs["rounds"] = out_rounds
+        return bufs
+
+
+class PT:
+    """Python mirror of blang.engines.internals.factories.PT (option names and defaults kept).
+
+    Differences, all loud: `initialization` defaults to FORWARD because SCM initialisation is a
+    "next" row and is rejected; `targetAccept` is rejected; `nThreads` is ignored.
+    """
+
+    def __init__(self, nChains=8, nScans=1000, adaptFraction=0.5, nPassesPerScan=3.0, thinning=1, random=1,
+                 usePriorSamples=True, reversible=False, initialization="FORWARD", targetAccept=None,
+                 logNormalizationEstimator="steppingStone", nThreads=None, ladder="EquallySpaced",
+                 annealSupport=True, treatNaNAsNegativeInfinity=False, nReplicas=1, device=0, ctasPerChain=0):
+        if targetAccept is not None:
+            raise BlangPTError("targetAccept (PT.java:156-163) is not supported by the GPU engine yet")
+        if logNormalizationEstimator not in ("steppingStone", "thermodynamicIntegration"):
+            raise BlangPTError("unknown logNormalizationEstimator")
+        self.nChains, self.nScans, self.adaptFraction = nChains, nScans, adaptFraction
+        self.nPassesPerScan, self.thinning, self.random = nPassesPerScan, thinning, random
+        self.initialization, self.ladder = initialization, ladder
+        self.logNormalizationEstimator = logNormalizationEstimator
+        self.engine = Engine(nChains=nChains, nReplicas=nReplicas, random=random, nPassesPerScan=nPassesPerScan,
+                             usePriorSamples=usePriorSamples, reversible=reversible, annealSupport=annealSupport,
+                             treatNaNAsNegativeInfinity=treatNaNAsNegativeInfinity, device=device,
+                             ctasPerChain=ctasPerChain)
+
+    def setSampledModel(self, spec):
+        """PT.setSampledModel (PT.java:270-281): lower the model, ladder, informed initialisation."""
+        self.engine.set_model(spec)
+        if not isinstance(self.ladder, str):
+            self.engine.set_ladder(self.ladder)
+        elif self.ladder != "EquallySpaced":
+            raise BlangPTError("only the EquallySpaced ladder or an explicit list is built in")
+        self.engine.initialize(self.initialization)
+
+    def performInference(self, want=("energy", "swapIndicators", "samples")):
+        res = self.engine.perform_inference(self.nScans, self.adaptFraction, self.thinning, want)
+        res["finalStats"] = self.engine.round_stats()
+        res["ladder"] = self.engine.get_ladder()
+        res["counters"] = self.engine.counters()
+        return res

@@ -1,0 +1,209 @@
+/*
+ * blangpt.h -- C ABI of libblangpt.so, the B200 (sm_100a) engine for Blang's
+ * non-reversible parallel tempering (NRPT) scan.
+ *
+ * This is the drop-in boundary: exactly the entry points a Java shim
+ * (`GpuPT implements PosteriorInferenceEngine`) binds through
+ * JNI / Panama.  Plain pointers and sizes only; the library owns all device
+ * memory behind the opaque handle; every host buffer is copied during the
+ * call; no callbacks.  Not thread-safe: one host thread drives one handle
+ * (the reference calls performInference once on the main thread,
+ * R/runtime/Runner.xtend:238-240).  Every function returns 0 on success and a
+ * BLANGPT_E* code otherwise; blangpt_last_error() gives the message the shim
+ * turns into a RuntimeException (the reference's error convention,
+ * Runner.xtend:164-168).  There is NO CPU fallback: without a CUDA device
+ * blangpt_create fails.
+ *
+ * Citations: R/ = /root/reference/src/main/java/blang/.
+ */
+#ifndef BLANGPT_H
+#define BLANGPT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLANGPT_VERSION 100
+
+/* status codes */
+enum {
+  BLANGPT_OK = 0,
+  BLANGPT_EINVAL = 1,       /* bad argument / unsupported option                         */
+  BLANGPT_ECUDA = 2,        /* CUDA runtime error (message in last_error)                */
+  BLANGPT_ESTATE = 3,       /* call order violated (e.g. run before set_model)           */
+  BLANGPT_ENUMERIC = 4,     /* device-side condition that throws in Java: NaN factor
+                               (ExponentiatedFactor.java:26-29) or slice diverged to
+                               infinity (RealSliceSampler.java:81-82,88-89)              */
+  BLANGPT_EUNSUPPORTED = 5  /* model / option outside the closed catalogue               */
+};
+
+/* model families: the closed catalogue the shim's check() recognises
+ * (replaces per-factor virtual dispatch, R/runtime/SampledModel.java:258-282) */
+enum {
+  BLANGPT_FAM_NORMAL = 1,       /* data: y[n] f64.            hyper: m0, v0, rate        */
+  BLANGPT_FAM_LOGISTIC = 2,     /* data: x[n*p] f64 row-major, y[n] i32. hyper: v0       */
+  BLANGPT_FAM_MIXTURE = 3,      /* data: y[n] f64. hyper: K, m0, v0, gshape, grate, conc */
+  BLANGPT_FAM_ISING = 4,        /* no data.       hyper: N, coupling, moment             */
+  BLANGPT_FAM_BETABINOMIAL = 5  /* data: y[R*n] i32, ntrials[R*n] i32. hyper: rate       */
+};
+
+/* PT.InitType (R/engines/internals/factories/PT.java:267) */
+enum { BLANGPT_INIT_COPIES = 0, BLANGPT_INIT_FORWARD = 1, BLANGPT_INIT_SCM = 2 /* rejected: EUNSUPPORTED */ };
+
+enum { BLANGPT_F64 = 0, BLANGPT_I32 = 1 };
+
+typedef struct {
+  const void* data;   /* host pointer */
+  int64_t n_elem;
+  int32_t dtype;      /* BLANGPT_F64 | BLANGPT_I32 */
+  int32_t rows, cols; /* optional shape hint (row-major) */
+} blangpt_array;
+
+/* Engine options.  Field names follow the reference's @Arg names
+ * (R/engines/ParallelTempering.java:25-40, PT.java:47-82, Runner.xtend:69-73). */
+typedef struct {
+  int32_t nChains;                 /* default 8                                        */
+  int32_t nReplicas;               /* independent PT replicas in this handle (1)       */
+  uint64_t random;                 /* seed, default 1                                   */
+  double nPassesPerScan;           /* default 3                                        */
+  int32_t usePriorSamples;         /* default 1                                        */
+  int32_t reversible;              /* default 0                                        */
+  int32_t annealSupport;           /* default 1                                        */
+  int32_t treatNaNAsNegativeInfinity; /* default 0                                     */
+  int32_t device;                  /* CUDA ordinal                                     */
+  int32_t rank, worldSize;         /* chain sharding: this process owns a contiguous
+                                      block of chain slots (nReplicas must be 1 when
+                                      worldSize > 1)                                   */
+  int32_t ctasPerChain;            /* 0 = auto; 1,2,4,8 = thread-block cluster size     */
+  int64_t replicaOffset;           /* global index of local replica 0 (RNG keying)      */
+  int32_t statisticRecordedMaxChainIndex; /* PT.java:76-78; default 100 (outputs only)  */
+  int32_t reserved;
+} blangpt_config;
+
+typedef struct blangpt_handle blangpt_handle;
+
+/* fills *cfg with the reference defaults */
+void blangpt_default_config(blangpt_config* cfg);
+
+int blangpt_create(const blangpt_config* cfg, blangpt_handle** out);
+void blangpt_destroy(blangpt_handle* h);
+const char* blangpt_last_error(const blangpt_handle* h);   /* h may be NULL: last create error */
+
+/* Lower a recognised model (what GpuPT.setSampledModel does after walking the
+ * SampledModel once, R/runtime/SampledModel.java:106-148).  Arrays in the
+ * family's documented order. */
+int blangpt_set_model(blangpt_handle* h, int32_t family, const blangpt_array* arrays, int32_t n_arrays,
+                      const double* hyper, int32_t n_hyper);
+int blangpt_n_reals(const blangpt_handle* h);      /* latent reals per chain, declaration order */
+int blangpt_n_ints(const blangpt_handle* h);
+int blangpt_n_samplers(const blangpt_handle* h);   /* SampledModel.nPosteriorSamplers :155-158  */
+
+/* Ladder, descending, betas[replica][position]; position 0 is beta = 1
+ * (ParallelTempering.setAnnealingParameters :183-205: sorts, requires betas[0]==1,
+ * resets every accumulator).  n == nChains broadcasts one ladder to all replicas. */
+int blangpt_set_ladder(blangpt_handle* h, const double* betas_desc, int64_t n);
+int blangpt_get_ladder(const blangpt_handle* h, double* out, int64_t n);
+
+/* States are addressed by temperature POSITION like ParallelTempering.states[i].
+ * reals[nReals], ints[nInts].  Only positions whose slot is local to this rank may be
+ * written/read when worldSize > 1 (others return EINVAL). */
+int blangpt_set_state(blangpt_handle* h, int64_t replica, int32_t position, const double* reals, const int32_t* ints);
+int blangpt_get_state(blangpt_handle* h, int64_t replica, int32_t position, double* reals, int32_t* ints);
+/* PT.informedInitialization :284-329 (COPIES keeps the states as set; FORWARD draws
+ * every chain from the prior) */
+int blangpt_initialize(blangpt_handle* h, int32_t init_type);
+
+/* Parity hook: annealed log-densities of the CURRENT states, per position:
+ * out_logdens = SampledModel.logDensity() at the chain's own beta (:161-176),
+ * out_loglik = preAnnealedLogLikelihood (:209-212), out_noos = nOutOfSupport (:214-217),
+ * out_fixed = sum of the fixed (prior) factors.  Arrays [nReplicas*nChains], nullable. */
+int blangpt_log_density(blangpt_handle* h, double* out_logdens, double* out_loglik, int32_t* out_noos,
+                        double* out_fixed);
+
+/* Per-scan outputs of blangpt_run_scans (all nullable; sized for n_scans):
+ * what PT.recordEnergyStatistics / recordSamples / swapAndRecordStatistics write
+ * every scan (PT.java:116-143,360-385). */
+typedef struct {
+  double* energy;        /* [n_scans][nReplicas][nChains]  -preAnnealedLogLikelihood after the move */
+  double* logDensity;    /* [n_scans][nReplicas][nChains]  allLogDensities                          */
+  int32_t* nOutOfSupport;/* [n_scans][nReplicas][nChains]                                           */
+  int32_t* swapIndicators;/*[n_scans][nReplicas][nChains]  1 at the lower index of a swapped pair   */
+  double* samples;       /* [n_scans][nReplicas][nReals]   beta=1 chain, before the swap            */
+  int32_t* intSamples;   /* [n_scans][nReplicas][nInts]                                             */
+} blangpt_scan_outputs;
+
+/* n_scans x { moveKernel ; record ; swapKernel }  (PT.java:93-102).  Single-GPU path. */
+int blangpt_run_scans(blangpt_handle* h, int32_t n_scans, const blangpt_scan_outputs* out);
+
+/* Round statistics (accumulators are per temperature position and per round,
+ * ParallelTempering.java:197-204).  All arrays [nReplicas][nChains] (pairs use
+ * the first nChains-1 entries), nullable. */
+typedef struct {
+  int64_t nScansInRound;
+  double* swapAcceptMean;     /* swapAcceptPrs[i].getMean()                  */
+  double* energyMean;         /* energies[c].getMean()                       */
+  double* energyVariance;     /* energies[c].getVariance() (n-1)             */
+  double* energyCovariance;   /* CovarAccumulator.sampleCovariance (C/n)     */
+  double* logSum;             /* LogSumAccumulator.logSum                    */
+  int64_t* logSumN;           /* LogSumAccumulator.numberOfTerms             */
+  int64_t* roundTrips;        /* [nReplicas] Paths.nRejuvenations            */
+  double* Lambda;             /* [nReplicas] PT.java:434                     */
+  double* logZSteppingStone;  /* [nReplicas] ParallelTempering.java:143-153  */
+  double* logZThermodynamic;  /* [nReplicas] :130-141, NaN if support annealed */
+} blangpt_round_stats;
+int blangpt_get_round_stats(blangpt_handle* h, blangpt_round_stats* out);
+
+/* PT.adapt (PT.java:148-171): new ladder from the round's mean swap acceptance
+ * (EngineStaticUtils.java:95-168, Spline.java:129-203), then resets the accumulators.
+ * cum_lambda_xy (nullable): [nReplicas][2][nChains] knots (ascending beta, cumulative Lambda). */
+int blangpt_adapt(blangpt_handle* h, double* cum_lambda_xy);
+/* reset accumulators without changing the ladder */
+int blangpt_reset_round(blangpt_handle* h);
+
+/* PT.rounds (PT.java:239-265).  Arrays sized >= 64.  Returns the number of rounds. */
+int blangpt_rounds(int32_t nScans, double adaptFraction, int32_t* round_nscans, int32_t* round_is_adapt);
+
+/* PT.performInference (PT.java:85-113) in one call; per-round diagnostics
+ * (reportParallelTemperingDiagnostics :387-505) for replica 0..nReplicas-1. */
+typedef struct {
+  int32_t nRounds;
+  int32_t roundNScans[64];
+  int32_t roundIsAdapt[64];
+  /* [64][nReplicas] arrays, caller-allocated, nullable */
+  double* Lambda;
+  double* logZ;
+  int64_t* roundTrips;
+  double* minAccept;
+  double* meanAccept;
+  double roundMillis[64];
+} blangpt_inference_summary;
+int blangpt_perform_inference(blangpt_handle* h, int32_t nScans, double adaptFraction, int32_t thinning,
+                              const blangpt_scan_outputs* out, blangpt_inference_summary* summary);
+
+/* Work counters since create: [0] log-density evaluations (one per sampler logDensity()
+ * call, RealSliceSampler.java:156-161) [1] scans [2] kernel launches [3] sampler executions */
+int blangpt_counters(blangpt_handle* h, uint64_t out[4]);
+
+/* ---- split-phase calls for the multi-GPU path (one process per GPU) ----
+ * scan = blangpt_explore -> all-gather of the local table segment (NCCL, by the
+ * caller, on `stream`) -> blangpt_swap on the replicated table.  Every rank takes the
+ * same swap decisions from the same Philox key, so no second message is needed. */
+int blangpt_set_stream(blangpt_handle* h, void* cuda_stream);
+/* evaluation-only pass over the local chains (after set_state / initialize): fills the
+ * local table segment; the caller all-gathers it and then calls blangpt_prime once. */
+int blangpt_evaluate(blangpt_handle* h);
+int blangpt_prime(blangpt_handle* h);
+int blangpt_explore(blangpt_handle* h);
+/* which: 0 = full table [nChains][4] f64 (loglik, noos, logprior, evals),
+ *        1 = local send segment [localChains][4]                              */
+void* blangpt_table_ptr(blangpt_handle* h, int32_t which);
+int64_t blangpt_local_chains(const blangpt_handle* h, int64_t* first_slot);
+int blangpt_swap(blangpt_handle* h, const blangpt_scan_outputs* out_one_scan_or_null);
+int blangpt_synchronize(blangpt_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
