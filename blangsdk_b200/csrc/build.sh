@@ -7,4 +7,4 @@ CCBIN="${CCBIN:-/usr/bin/g++}"
 "$NVCC" -ccbin "$CCBIN" -std=c++17 -O3 -lineinfo \
   -gencode arch=compute_100a,code=sm_100a \
   -Xcompiler -fPIC -shared $EXTRA_NVCC_FLAGS \
-  -o "$HERE/../libblangpt.so" "$HERE/engine.cu" -lcudart
+  -o "$HERE/../libblangpt.so" "$HERE/engine.cu"

@@ -119,6 +119,7 @@ extern "C" void blangpt_destroy(blangpt_handle* h) {
 extern "C" int blangpt_n_reals(const blangpt_handle* h) { return h ? h->n_reals : -1; }
 extern "C" int blangpt_n_ints(const blangpt_handle* h) { return h ? h->n_ints : -1; }
 extern "C" int blangpt_n_samplers(const blangpt_handle* h) { return h ? h->n_samplers : -1; }
+extern "C" int blangpt_ctas_per_chain(const blangpt_handle* h) { return h ? h->G : -1; }
 
 // ---------------------------------------------------------------------------
 // launches
@@ -181,7 +182,7 @@ static int ensure_tables(blangpt_handle* h) {
   int rc = launch_explore(h, MODE_EVAL);
   if (rc) return rc;
   if (h->cfg.worldSize == 1) {
-    prime_prev_kernel<<<(unsigned)((h->M_total + 255) / 256), 256, 0, h->stream>>>(h->E);
+    prime_prev_kernel<<<(unsigned)((h->M_total + 255) / 256), 256, 0, h->stream>>>(h->E, h->St);
     CUDA_OK(h, cudaGetLastError());
     h->n_launches++;
   }
@@ -266,6 +267,7 @@ static int alloc_engine(blangpt_handle* h) {
   if ((rc = dev_alloc(h, &S.path_flag, M))) return rc;
   if ((rc = dev_alloc(h, &S.rejuv, c.nReplicas))) return rc;
   if ((rc = dev_alloc(h, &S.total_evals, 1))) return rc;
+  if ((rc = dev_alloc(h, &S.oos_seen, c.nReplicas))) return rc;
   init_perm_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(E, h->family == BLANGPT_FAM_ISING ? 0 : h->n_samplers);
   CUDA_OK(h, cudaGetLastError());
   // default ladder: EquallySpaced
@@ -475,7 +477,7 @@ extern "C" int blangpt_initialize(blangpt_handle* h, int32_t init_type) {
   int rc = launch_explore(h, MODE_FORWARD_INIT);
   if (rc) return rc;
   if (h->cfg.worldSize == 1) {
-    prime_prev_kernel<<<(unsigned)((h->M_total + 255) / 256), 256, 0, h->stream>>>(h->E);
+    prime_prev_kernel<<<(unsigned)((h->M_total + 255) / 256), 256, 0, h->stream>>>(h->E, h->St);
     CUDA_OK(h, cudaGetLastError());
     h->n_launches++;
   }
@@ -577,7 +579,7 @@ extern "C" int blangpt_get_round_stats(blangpt_handle* h, blangpt_round_stats* o
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
   const int64_t M = h->M_total; const int N = h->cfg.nChains, R = h->cfg.nReplicas;
   std::vector<long long> en_n(M), acc_n(M), ls_n(M); std::vector<double> en_m1(M), en_m2(M), cov_c(M), acc_m1(M), ls_sum(M);
-  std::vector<int> cov_n(M); std::vector<unsigned long long> rej(R); std::vector<double> tab(M * 4);
+  std::vector<int> cov_n(M), oos_seen(R); std::vector<unsigned long long> rej(R); std::vector<double> tab(M * 4);
   auto get = [&](void* dst, const void* src, size_t b) { return cudaMemcpyAsync(dst, src, b, cudaMemcpyDeviceToHost, h->stream); };
   CUDA_OK(h, get(en_n.data(), h->St.en_n, M * 8)); CUDA_OK(h, get(en_m1.data(), h->St.en_m1, M * 8));
   CUDA_OK(h, get(en_m2.data(), h->St.en_m2, M * 8)); CUDA_OK(h, get(cov_c.data(), h->St.cov_c, M * 8));
@@ -585,11 +587,12 @@ extern "C" int blangpt_get_round_stats(blangpt_handle* h, blangpt_round_stats* o
   CUDA_OK(h, get(acc_m1.data(), h->St.acc_m1, M * 8)); CUDA_OK(h, get(ls_sum.data(), h->St.ls_sum, M * 8));
   CUDA_OK(h, get(ls_n.data(), h->St.ls_n, M * 8)); CUDA_OK(h, get(rej.data(), h->St.rejuv, R * 8));
   CUDA_OK(h, get(tab.data(), h->E.table, M * 4 * 8));
+  CUDA_OK(h, get(oos_seen.data(), h->St.oos_seen, R * 4));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
   o->nScansInRound = h->scans_in_round;
   const double nan = std::nan("");
   for (int r = 0; r < R; r++) {
-    double Lambda = 0.0, ss = 0.0, thermo = 0.0; bool oos = false;
+    double Lambda = 0.0, ss = 0.0, thermo = 0.0; bool oos = oos_seen[r] != 0;
     for (int p = 0; p < N; p++) {
       const size_t i = (size_t)r * N + p;
       const double mean = en_n[i] ? en_m1[i] : nan;
@@ -740,7 +743,7 @@ extern "C" int blangpt_evaluate(blangpt_handle* h) {
 extern "C" int blangpt_prime(blangpt_handle* h) {
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
-  prime_prev_kernel<<<(unsigned)((h->M_total + 255) / 256), 256, 0, h->stream>>>(h->E);
+  prime_prev_kernel<<<(unsigned)((h->M_total + 255) / 256), 256, 0, h->stream>>>(h->E, h->St);
   CUDA_OK(h, cudaGetLastError());
   h->n_launches++;
   h->tables_valid = true;
@@ -776,4 +779,52 @@ extern "C" int blangpt_swap(blangpt_handle* h, const blangpt_scan_outputs* out) 
 extern "C" int blangpt_synchronize(blangpt_handle* h) {
   if (!h) return BLANGPT_EINVAL;
   return check_device_errors(h);
+}
+
+// ---------------------------------------------------------------------------
+// micro-benchmarks: the measured fp64 compute ceilings bench.py reports next to
+// the HBM roofline (MEASURED_PEAKS.json has no fp64 figure)
+// ---------------------------------------------------------------------------
+__global__ void mb_dfma_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void mb_logit_kernel(double* out, int iters) {
+  __shared__ int serr;
+  double z0 = -3.0 + 6.0 * threadIdx.x / blockDim.x, z1 = -z0, acc = 0.0; int cnt = 0;
+  LogisticFam fam; fam.err = &serr;
+  for (int i = 0; i < iters; i++) {
+    fam.row_term(z0, i & 1, acc, cnt); fam.row_term(z1, (i >> 1) & 1, acc, cnt);
+    z0 += 1e-6; z1 -= 1e-6;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc + cnt;
+}
+// which: 0 = fp64 FMA TFLOP/s, 1 = logistic row terms per second (compute-only ceiling of the C2 kernel)
+extern "C" int blangpt_microbench(int32_t device, int32_t which, double* out_rate) {
+  if (!out_rate) return BLANGPT_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return BLANGPT_ECUDA;
+  int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int threads = 512, blocks = sms * 2, iters = which == 0 ? 20000 : 2000;
+  double* d = nullptr;
+  if (cudaMalloc(&d, (size_t)threads * blocks * sizeof(double)) != cudaSuccess) return BLANGPT_ECUDA;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0);
+    if (which == 0) mb_dfma_kernel<<<blocks, threads>>>(d, iters); else mb_logit_kernel<<<blocks, threads>>>(d, iters);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaError_t e = cudaGetLastError();
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  if (e != cudaSuccess) return BLANGPT_ECUDA;
+  const double n = (double)threads * blocks * iters;
+  *out_rate = which == 0 ? n * 8 * 2 / (best * 1e-3) / 1e12 : n * 2 / (best * 1e-3);
+  return BLANGPT_OK;
 }

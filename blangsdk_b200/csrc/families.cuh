@@ -186,6 +186,7 @@ struct LogisticFam {
           *reinterpret_cast<double2*>(eta + i) = e;
         } else eta[i] = fma(delta, col[i], eta[i]);
       }
+    __syncthreads();   // every thread has read P[k] for its delta before anyone overwrites it
     P[k] = x;
   }
   // rebuild eta from scratch: sum_j w_j * X[i][j], j ascending from 0.0 (F/SpikedGLM.bl:29-33)

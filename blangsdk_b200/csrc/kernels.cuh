@@ -55,6 +55,7 @@ struct DevStats {     // all indexed [R][N] by temperature position unless noted
   int* path_flag;                                             // [R][N] by slot: Paths "newSample"
   unsigned long long* rejuv;                                  // [R]
   unsigned long long* total_evals;                            // [1]
+  int* oos_seen;                                              // [R] sticky SampledModel.annealedOutOfSupportDetected
 };
 
 struct DevOut {       // per-scan outputs of the current batch (nullable)
@@ -126,7 +127,9 @@ explore_kernel(DevEngine E, typename Fam::Data D, int G, int mode) {
           fam.annealed(k, x, aux, red, s, c);
           double a = beta * s;
           if (c) a += E.anneal_support ? c * annealed_minus_infinity(beta) : BPT_NEG_INF;
-          return fx + a;
+          const double r = fx + a;
+          if (r != r) err |= ERR_NAN;   // ExponentiatedFactor.java:26-29
+          return r;
         };
         execs++;
         if (fam.sampler_type(k) == S_REAL_SLICE) {
@@ -150,6 +153,7 @@ explore_kernel(DevEngine E, typename Fam::Data D, int G, int mode) {
 
   double loglik, logprior; int noos;
   fam.full(red, loglik, noos, logprior);
+  if (loglik != loglik || logprior != logprior) err |= ERR_NAN;
   __syncthreads();
   if (crank == 0) {
     for (int v = tid; v < nR; v += blockDim.x) E.reals[(size_t)v * E.M_local + l] = P[v];
@@ -195,6 +199,7 @@ __global__ void swap_kernel(DevEngine E, DevStats St, DevOut O) {
     const size_t g = base + s;
     const double ll = E.table[g * 4 + 0], no = E.table[g * 4 + 1], fx = E.table[g * 4 + 2];
     ev += (unsigned long long)E.table[g * 4 + 3];
+    if (no > 0 && E.anneal_support) atomicOr(&St.oos_seen[rep], 1);   // SampledModel.java:361-362,396-398
     const double after = -ll, before = -E.prev_loglik[g];
     E.prev_loglik[g] = ll;
     summary_add(St.en_n[base + p], St.en_m1[base + p], St.en_m2[base + p], after);
@@ -271,9 +276,12 @@ __global__ void swap_kernel(DevEngine E, DevStats St, DevOut O) {
 }
 
 // energy "before" of the next scan = current table (called after an evaluation-only pass)
-__global__ void prime_prev_kernel(DevEngine E) {
+__global__ void prime_prev_kernel(DevEngine E, DevStats St) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < E.R * E.N) E.prev_loglik[i] = E.table[(size_t)i * 4];
+  if (i < E.R * E.N) {
+    E.prev_loglik[i] = E.table[(size_t)i * 4];
+    if (E.table[(size_t)i * 4 + 1] > 0 && E.anneal_support) atomicOr(&St.oos_seen[i / E.N], 1);
+  }
 }
 
 // ParallelTempering.setAnnealingParameters :197-204 + Paths.initPaths :131-139

@@ -65,11 +65,12 @@ class InferenceSummary(C.Structure):
 
 EXPORTS = [
     "blangpt_default_config", "blangpt_create", "blangpt_destroy", "blangpt_last_error", "blangpt_set_model",
-    "blangpt_n_reals", "blangpt_n_ints", "blangpt_n_samplers", "blangpt_set_ladder", "blangpt_get_ladder",
+    "blangpt_n_reals", "blangpt_n_ints", "blangpt_n_samplers", "blangpt_ctas_per_chain", "blangpt_set_ladder", "blangpt_get_ladder",
     "blangpt_set_state", "blangpt_get_state", "blangpt_initialize", "blangpt_log_density", "blangpt_run_scans",
     "blangpt_get_round_stats", "blangpt_adapt", "blangpt_reset_round", "blangpt_rounds",
     "blangpt_perform_inference", "blangpt_counters", "blangpt_set_stream", "blangpt_evaluate", "blangpt_prime",
     "blangpt_explore", "blangpt_table_ptr", "blangpt_local_chains", "blangpt_swap", "blangpt_synchronize",
+    "blangpt_microbench",
 ]
 
 _LIB = None
@@ -92,7 +93,7 @@ def load_library():
     L.blangpt_last_error.argtypes = [vp]
     L.blangpt_last_error.restype = C.c_char_p
     L.blangpt_set_model.argtypes = [vp, C.c_int32, C.POINTER(Array), C.c_int32, _dp, C.c_int32]
-    for f in ("blangpt_n_reals", "blangpt_n_ints", "blangpt_n_samplers"):
+    for f in ("blangpt_n_reals", "blangpt_n_ints", "blangpt_n_samplers", "blangpt_ctas_per_chain"):
         getattr(L, f).argtypes = [vp]
     L.blangpt_set_ladder.argtypes = [vp, _dp, C.c_int64]
     L.blangpt_get_ladder.argtypes = [vp, _dp, C.c_int64]
@@ -116,8 +117,18 @@ def load_library():
     L.blangpt_local_chains.argtypes = [vp, _lp]
     L.blangpt_local_chains.restype = C.c_int64
     L.blangpt_swap.argtypes = [vp, C.POINTER(ScanOutputs)]
+    L.blangpt_microbench.argtypes = [C.c_int32, C.c_int32, _dp]
     _LIB = L
     return L
+
+
+def microbench(which, device=0):
+    """Measured compute ceiling: which=0 fp64 FMA TFLOP/s, which=1 logistic row terms/s."""
+    out = C.c_double()
+    rc = load_library().blangpt_microbench(device, which, C.byref(out))
+    if rc != 0:
+        raise BlangPTError("microbench failed (no GPU?)")
+    return out.value
 
 
 def rounds(nScans, adaptFraction):
@@ -207,6 +218,7 @@ class Engine:
         self.n_reals = self.L.blangpt_n_reals(self.h)
         self.n_ints = self.L.blangpt_n_ints(self.h)
         self.n_samplers = self.L.blangpt_n_samplers(self.h)
+        self.ctas_per_chain = self.L.blangpt_ctas_per_chain(self.h)
         self.family = fam
 
     def set_ladder(self, betas):

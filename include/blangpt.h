@@ -99,6 +99,7 @@ int blangpt_set_model(blangpt_handle* h, int32_t family, const blangpt_array* ar
 int blangpt_n_reals(const blangpt_handle* h);      /* latent reals per chain, declaration order */
 int blangpt_n_ints(const blangpt_handle* h);
 int blangpt_n_samplers(const blangpt_handle* h);   /* SampledModel.nPosteriorSamplers :155-158  */
+int blangpt_ctas_per_chain(const blangpt_handle* h); /* thread-block cluster size chosen for this model */
 
 /* Ladder, descending, betas[replica][position]; position 0 is beta = 1
  * (ParallelTempering.setAnnealingParameters :183-205: sorts, requires betas[0]==1,
@@ -202,6 +203,11 @@ void* blangpt_table_ptr(blangpt_handle* h, int32_t which);
 int64_t blangpt_local_chains(const blangpt_handle* h, int64_t* first_slot);
 int blangpt_swap(blangpt_handle* h, const blangpt_scan_outputs* out_one_scan_or_null);
 int blangpt_synchronize(blangpt_handle* h);
+
+/* Measured compute ceilings on `device` (no handle needed): which = 0 -> fp64 FMA TFLOP/s,
+ * which = 1 -> logistic-regression row terms per second with operands in registers (the
+ * compute-only bound of the C2 likelihood kernel). */
+int blangpt_microbench(int32_t device, int32_t which, double* out_rate);
 
 #ifdef __cplusplus
 }

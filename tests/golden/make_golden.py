@@ -1,0 +1,72 @@
+"""Generates tests/golden/nrpt_golden.json from the CPU oracle (oracle/blang_oracle.c).
+
+The reference ships no numeric golden vector for the NRPT path and no JVM exists in the
+build container, so these vectors are produced by the oracle -- which is itself pinned on the reference's
+known answers by tests/test_oracle_pins.py.  Run from the repo root:  python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from blangsdk_b200 import datasets as D  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+def spec_to_json(spec):
+    out = {"family": spec["family"], "hyper": spec["hyper"]}
+    for k in ("y", "x", "ntrials"):
+        if k in spec:
+            out[k] = np.asarray(spec[k]).tolist()
+    return out
+
+
+def main():
+    specs = {
+        "normal": D.normal_meanvar(n=40),
+        "logistic": D.logistic_regression(60, 4),
+        "mixture": D.gaussian_mixture(50),
+        "betabinomial": D.beta_binomial(1, groups=8),
+        "ising": D.ising(4),
+    }
+    rng = np.random.default_rng(20240600)
+    cases = []
+    for name, spec in specs.items():
+        m = O.Model(spec)
+        dens = []
+        for beta in (1.0, 0.37, 0.0):
+            if name == "ising":
+                re, it = None, rng.integers(0, 2, m.n_ints).tolist()
+            elif name == "mixture":
+                K = m.n_reals // 3
+                re = np.concatenate([rng.normal(0, 3, K), rng.gamma(2, 1, K), rng.dirichlet(np.ones(K))]).tolist()
+                it = None
+            elif name == "logistic":
+                re, it = rng.normal(0, 1.5, m.n_reals).tolist(), None
+            else:
+                re, it = rng.gamma(2.0, 1.0, m.n_reals).tolist(), None
+            d = m.log_density(re, it, beta=beta)
+            dens.append(dict(beta=beta, reals=re, ints=it, logdens=d["logdens"], loglik=d["loglik"],
+                             noos=d["noos"], fixed=d["fixed"]))
+        pt = O.PT(m, nChains=4, seed=2024,
+                  sweepOrder=O.ORDER_CHECKERBOARD if name == "ising" else O.ORDER_REFERENCE)
+        pt.initialize()
+        res = pt.perform_inference(40, 0.5, want_samples=False)
+        st = pt.round_stats()
+        cases.append(dict(name=name, spec=spec_to_json(spec), densities=dens,
+                          run=dict(nChains=4, seed=2024, nScans=40, adaptFraction=0.5,
+                                   energies=res["energies"].tolist(), indicators=res["indicators"].tolist(),
+                                   ladder=pt.get_ladder().tolist(), nEvals=pt.n_evals(),
+                                   Lambda=st["Lambda"], logZ=st["log_z_stepping_stone"],
+                                   roundTrips=st["round_trips"],
+                                   swapAcceptMean=st["swap_accept_mean"].tolist())))
+    with open(os.path.join(ROOT, "tests", "golden", "nrpt_golden.json"), "w") as f:
+        json.dump(dict(generator="tests/golden/make_golden.py", cases=cases), f)
+    print("wrote", len(cases), "cases")
+
+
+if __name__ == "__main__":
+    main()
