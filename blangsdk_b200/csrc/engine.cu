@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <chrono>
@@ -30,6 +31,7 @@ struct blangpt_handle {
   int family = 0;
   int n_reals = 0, n_ints = 0, n_samplers = 0;
   int G = 1;                      // CTAs per chain
+  int logistic_threads = 1024;    // CTA size of the C2 kernel (BLANGPT_LOGISTIC_THREADS=512|1024)
   bool model_set = false, tables_valid = false;
   cudaStream_t stream = nullptr;  // nullptr = legacy default stream
   bool own_stream = false;
@@ -102,6 +104,7 @@ extern "C" int blangpt_create(const blangpt_config* cfg, blangpt_handle** out) {
   if (prop.major < 10) { set_error(nullptr, "device sm_%d%d is not Blackwell (kernels are built for sm_100a only)", prop.major, prop.minor); return BLANGPT_ECUDA; }
   blangpt_handle* h = new blangpt_handle();
   h->cfg = *cfg;
+  if (const char* t = getenv("BLANGPT_LOGISTIC_THREADS")) h->logistic_threads = atoi(t) == 512 ? 512 : 1024;
   h->M_total = (int64_t)cfg->nReplicas * cfg->nChains;
   *out = h;
   return BLANGPT_OK;
@@ -143,7 +146,12 @@ static int launch_explore_t(blangpt_handle* h, const typename Fam::Data& D, int 
 static int launch_explore(blangpt_handle* h, int mode) {
   switch (h->family) {
     case BLANGPT_FAM_NORMAL: return launch_explore_t<NormalFam>(h, h->normal, mode);
-    case BLANGPT_FAM_LOGISTIC: return launch_explore_t<LogisticFam>(h, h->logistic, mode);
+    case BLANGPT_FAM_LOGISTIC:
+      if (h->logistic_threads == 1024) {
+        LogisticFamT<1024>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
+        return launch_explore_t<LogisticFamT<1024>>(h, d2, mode);
+      }
+      return launch_explore_t<LogisticFam>(h, h->logistic, mode);
     case BLANGPT_FAM_MIXTURE:
       if (h->mixture.K <= 4) return launch_explore_t<MixtureFam<4>>(h, h->mixture, mode);
       else { MixtureFam<8>::Data d8; memcpy(&d8, &h->mixture, sizeof d8); return launch_explore_t<MixtureFam<8>>(h, d8, mode); }
@@ -201,12 +209,14 @@ static int reset_round(blangpt_handle* h) {
 // ---------------------------------------------------------------------------
 // model
 // ---------------------------------------------------------------------------
-__global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int n, int p, int npad) {
+// row-major [n][p] -> column-major [p][npad]; rows with y == 0 are negated (sign folding, exact)
+__global__ void transpose_kernel(const double* __restrict__ in, const uint8_t* __restrict__ y, double* __restrict__ out, int n, int p, int npad) {
   __shared__ double tile[32][33];
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
     const int r = r0 + dy, c = c0 + threadIdx.x;
-    tile[dy][threadIdx.x] = (r < n && c < p) ? in[(size_t)r * p + c] : 0.0;
+    const double v = (r < n && c < p) ? in[(size_t)r * p + c] : 0.0;
+    tile[dy][threadIdx.x] = (r < n && y[r] == 0) ? -v : v;
   }
   __syncthreads();
   for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
@@ -322,13 +332,13 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
       const int64_t local = h->M_total / c.worldSize;
       if ((rc = dev_alloc(h, &eta, (size_t)npad * local))) return rc;
       CUDA_OK(h, cudaMemcpyAsync(xr, a[0].data, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      dim3 grid((n + 31) / 32, (p + 31) / 32), block(32, 8);
-      transpose_kernel<<<grid, block, 0, h->stream>>>(xr, xt, n, p, npad);
-      CUDA_OK(h, cudaGetLastError());
       std::vector<uint8_t> yb(npad, 0);
       const int32_t* yi = (const int32_t*)a[1].data;
       for (int i = 0; i < n; i++) yb[i] = yi[i] == 1 ? 1 : 0;
       CUDA_OK(h, cudaMemcpyAsync(y8, yb.data(), npad, cudaMemcpyHostToDevice, h->stream));
+      dim3 grid((n + 31) / 32, (p + 31) / 32), block(32, 8);
+      transpose_kernel<<<grid, block, 0, h->stream>>>(xr, y8, xt, n, p, npad);
+      CUDA_OK(h, cudaGetLastError());
       CUDA_OK(h, cudaStreamSynchronize(h->stream));
       CUDA_OK(h, cudaFree(xr)); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), (void*)xr));
       h->logistic = {xt, y8, eta, n, npad, p, hyper[0]};
@@ -796,10 +806,11 @@ __global__ void mb_dfma_kernel(double* out, int iters) {
 }
 __global__ void mb_logit_kernel(double* out, int iters) {
   __shared__ int serr;
-  double z0 = -3.0 + 6.0 * threadIdx.x / blockDim.x, z1 = -z0, acc = 0.0; int cnt = 0;
+  double z0 = -3.0 + 9.0 * threadIdx.x / blockDim.x, z1 = 1.0 - z0, acc = 0.0; int cnt = 0;
+  __shared__ uint8_t sy[2];
   LogisticFam fam; fam.err = &serr;
   for (int i = 0; i < iters; i++) {
-    fam.row_term(z0, i & 1, acc, cnt); fam.row_term(z1, (i >> 1) & 1, acc, cnt);
+    fam.row_term(z0, sy, acc, cnt); fam.row_term(z1, sy + 1, acc, cnt);
     z0 += 1e-6; z1 -= 1e-6;
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc + cnt;
@@ -827,4 +838,28 @@ extern "C" int blangpt_microbench(int32_t device, int32_t which, double* out_rat
   const double n = (double)threads * blocks * iters;
   *out_rate = which == 0 ? n * 8 * 2 / (best * 1e-3) / 1e12 : n * 2 / (best * 1e-3);
   return BLANGPT_OK;
+}
+
+// debugging / accuracy hook: the per-row Bernoulli(logistic(z)) term exactly as the C2 kernels evaluate it.
+// out_term[i] = value (or -inf when the row is out of support)
+__global__ void debug_logit_kernel(const double* z, const int* y, int n, double* out) {
+  __shared__ int serr;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0; int c = 0;
+  const uint8_t yb = (uint8_t)y[i];
+  logit_term(y[i] ? z[i] : -z[i], &yb, s, c, &serr);
+  out[i] = c ? -HUGE_VAL : s;
+}
+extern "C" int blangpt_debug_logit_terms(int32_t device, const double* z, const int32_t* y, int64_t n, double* out) {
+  if (!z || !y || !out || n <= 0) return BLANGPT_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return BLANGPT_ECUDA;
+  double *dz = nullptr, *dout = nullptr; int* dy = nullptr;
+  if (cudaMalloc(&dz, n * 8) != cudaSuccess || cudaMalloc(&dout, n * 8) != cudaSuccess || cudaMalloc(&dy, n * 4) != cudaSuccess) return BLANGPT_ECUDA;
+  cudaMemcpy(dz, z, n * 8, cudaMemcpyHostToDevice); cudaMemcpy(dy, y, n * 4, cudaMemcpyHostToDevice);
+  debug_logit_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dz, dy, (int)n, dout);
+  cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaGetLastError();
+  cudaFree(dz); cudaFree(dy); cudaFree(dout);
+  return e == cudaSuccess ? BLANGPT_OK : BLANGPT_ECUDA;
 }

@@ -43,6 +43,75 @@ BPT_D void acc_term(double t, double& s, int& c, int* err) {
   else { c++; if (t != t) atomicOr(err, ERR_NAN); }
 }
 
+// ---------------------------------------------------------------------------
+// log-likelihood of one Bernoulli(logistic(z)) observation
+// ---------------------------------------------------------------------------
+// The reference evaluates the NAIVE form  log(y ? p : 1 - p),  p = 1/(1+exp(-z))
+// (SURVEY.md section 10, C2).  In fp64 that form (a) returns -inf (out of support) once
+// p rounds to 1.0 on a y = 0 row (z >= 36.74) and (b) loses accuracy through 1 - p for
+// badly misclassified rows.  With the sign-folded margin sg = (y ? z : -z) the exact value is
+//     min(sg, 0) - log1p(exp(-|sg|)).
+// For sg >= -12 the naive form agrees with it to < 1e-11 absolute per row, so the hot
+// path evaluates the exact form with lean fp64 kernels: the operand ranges are known, so
+// there is no overflow/denormal/NaN handling, no general division and no selects.  For
+// sg < -12 (or |sg| >= 700, or NaN) -- rare, and the only place where the reference's own
+// rounding and its -inf convention are visible -- the naive arithmetic is executed literally.
+// Coefficients live in constant memory so each one is a direct DFMA operand.
+__constant__ double kExpC[13] = {
+    2.08767569878680989792e-09, 2.50521083854417187751e-08, 2.75573192239858906526e-07,
+    2.75573192239858906526e-06, 2.48015873015873015873e-05, 1.98412698412698412698e-04,
+    1.38888888888888888889e-03, 8.33333333333333333333e-03, 4.16666666666666666667e-02,
+    1.66666666666666666667e-01, 0.5, 1.0, 1.0};
+__constant__ double kAtanhC[9] = {
+    5.26315789473684210526e-02, 5.88235294117647058824e-02, 6.66666666666666666667e-02,
+    7.69230769230769230769e-02, 9.09090909090909090909e-02, 1.11111111111111111111e-01,
+    1.42857142857142857143e-01, 2.00000000000000000000e-01, 3.33333333333333333333e-01};
+// {-log2(e), 1.5*2^52, -ln2_hi, -ln2_lo, 1 - C, 1 + C, log(C)} with C = fl(sqrt 2)
+__constant__ double kLogitK[7] = {
+    -1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
+    -0.41421356237309514547, 2.41421356237309514547, 0.34657359027997269783};
+
+BPT_D double exp_neg(double a) {   // exp(-a) for 0 <= a < 700
+  double kd = fma(a, kLogitK[0], kLogitK[1]);   // magic add: low word = round(-a*log2e)
+  const int k = __double2loint(kd);
+  kd -= kLogitK[1];
+  double r = fma(kd, kLogitK[2], -a);
+  r = fma(kd, kLogitK[3], r);
+  double p = kExpC[0];
+#pragma unroll
+  for (int i = 1; i < 13; i++) p = fma(p, r, kExpC[i]);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+BPT_D double log1p_unit(double t) {   // log(1+t), t in [0,1]: log C + 2 atanh(f), f = (1+t-C)/(1+t+C), |f| <= 0.1716
+  const double num = t + kLogitK[4];
+  const double den = t + kLogitK[5];
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+  double e = fma(-den, r, 1.0); r = fma(r, e, r);
+  e = fma(-den, r, 1.0); r = fma(r, e, r);
+  double f = num * r;
+  f = fma(fma(-den, f, num), r, f);
+  const double f2 = f * f;
+  double q = kAtanhC[0];
+#pragma unroll
+  for (int i = 1; i < 9; i++) q = fma(q, f2, kAtanhC[i]);
+  const double s1 = f + f;
+  return fma(s1 * f2, q, s1 + kLogitK[6]);
+}
+// zs = sign-folded margin (y ? z : -z); *yp is only read on the rare literal path
+BPT_D void logit_term(double zs, const uint8_t* yp, double& s, int& c, int* err) {
+  if (zs >= -12.0 && fabs(zs) < 700.0) {
+    const double l = log1p_unit(exp_neg(fabs(zs)));
+    s += fma(0.5, zs - fabs(zs), -l);          // min(zs,0) - log1p(exp(-|zs|))
+  } else {   // literal reference arithmetic (rounding + -inf convention); NaN lands here too
+    const int y = *yp;
+    const double z = y ? zs : -zs;
+    const double pr = 1.0 / (1.0 + exp(-z));
+    const double pick = y ? pr : 1.0 - pr;
+    acc_term(log(pick), s, c, err);
+  }
+}
+
 // Normal.bl:21-24 with constant mean/variance (a prior on x)
 BPT_D double normal_f2(double mean, double variance, double x) {
   if (variance <= 0.0) return BPT_NEG_INF;
@@ -128,18 +197,20 @@ struct NormalFam {
 
 // ===========================================================================
 // C2  Bayesian logistic regression.  P = w[0..p)
-//     per-chain cache eta_i = x_i . w in HBM; a move of w_k needs only
-//     column k of X:  eta_i(x) = eta_i + (x - w_k) * X[i][k]
+//     per-chain cache eta_i = s_i * (x_i . w) in HBM, s_i = +1 if y_i = 1 else -1 (the rows of
+//     the device copy of X are sign-folded once at set_model, which is exact); a move of w_k
+//     needs only column k of X:  eta_i(x) = eta_i + (x - w_k) * s_i X[i][k]
 // ===========================================================================
-struct LogisticFam {
+template <int THREADS>
+struct LogisticFamT {
   struct Data {
-    const double* xt;      // [p][npad] column-major copy of the design matrix
+    const double* xt;      // [p][npad] column-major, sign-folded copy of the design matrix
     const uint8_t* y;      // [npad]
     double* eta;           // [localSlots][npad]
     int n, npad, p;
     double v0;
   };
-  static constexpr int kThreads = 512;
+  static constexpr int kThreads = THREADS;
   Data d; double* P; double* eta; RowRange rr; int* err;
 
   BPT_D static int n_reals(const Data& d) { return d.p; }
@@ -152,25 +223,28 @@ struct LogisticFam {
   BPT_D int simplex_dim() const { return 0; }
   BPT_D double fixed(int, double x, int) const { return normal_f2(0.0, d.v0, x); }
 
-  // Bernoulli.bl:11-14 -> Categorical.bl:12-15 with p = logistic(eta): the reference's naive form
-  BPT_D void row_term(double z, int y, double& s, int& c) const {
-    const double pr = 1.0 / (1.0 + exp(-z));
-    const double pick = y ? pr : 1.0 - pr;
-    acc_term(log(pick), s, c, err);
-  }
+  // Bernoulli.bl:11-14 -> Categorical.bl:12-15 with p = logistic(eta).  See logit_term() above.
+  BPT_D void row_term(double zs, const uint8_t* yp, double& s, int& c) const { logit_term(zs, yp, s, c, err); }
+
+  // one pass over this CTA's rows: eta and column k of X streamed with 16-byte loads, the next
+  // pair prefetched before the current pair's ~110 fp64 instructions
   BPT_D void annealed(int k, double x, int, GroupReducer& red, double& s, int& c) const {
     const double delta = x - P[k];
     const double* col = d.xt + (size_t)k * d.npad;
     double acc = 0.0; int cnt = 0;
-    for (int i = rr.lo + 2 * threadIdx.x; i < rr.hi; i += 2 * blockDim.x) {
-      if (i + 1 < rr.hi) {
-        const double2 e = *reinterpret_cast<const double2*>(eta + i);
-        const double2 xv = *reinterpret_cast<const double2*>(col + i);
-        const uchar2 yy = *reinterpret_cast<const uchar2*>(d.y + i);
-        row_term(fma(delta, xv.x, e.x), yy.x, acc, cnt);
-        row_term(fma(delta, xv.y, e.y), yy.y, acc, cnt);
-      } else row_term(fma(delta, col[i], eta[i]), d.y[i], acc, cnt);
+    const int stride = 2 * THREADS;
+    int i = rr.lo + 2 * threadIdx.x;
+    double2 en = make_double2(0.0, 0.0), xn = en;
+    if (i + 1 < rr.hi) { en = *reinterpret_cast<const double2*>(eta + i); xn = *reinterpret_cast<const double2*>(col + i); }
+    while (i + 1 < rr.hi) {
+      const double2 e = en, xv = xn;
+      const int nx = i + stride;
+      if (nx + 1 < rr.hi) { en = *reinterpret_cast<const double2*>(eta + nx); xn = *reinterpret_cast<const double2*>(col + nx); }
+      row_term(fma(delta, xv.x, e.x), d.y + i, acc, cnt);
+      row_term(fma(delta, xv.y, e.y), d.y + i + 1, acc, cnt);
+      i = nx;
     }
+    if (i < rr.hi) row_term(fma(delta, col[i], eta[i]), d.y + i, acc, cnt);
     red.reduce(acc, cnt);
     s = acc; c = cnt;
   }
@@ -178,7 +252,7 @@ struct LogisticFam {
     const double delta = x - P[k];
     const double* col = d.xt + (size_t)k * d.npad;
     if (delta != 0.0)
-      for (int i = rr.lo + 2 * threadIdx.x; i < rr.hi; i += 2 * blockDim.x) {
+      for (int i = rr.lo + 2 * threadIdx.x; i < rr.hi; i += 2 * THREADS) {
         if (i + 1 < rr.hi) {
           double2 e = *reinterpret_cast<const double2*>(eta + i);
           const double2 xv = *reinterpret_cast<const double2*>(col + i);
@@ -191,7 +265,7 @@ struct LogisticFam {
   }
   // rebuild eta from scratch: sum_j w_j * X[i][j], j ascending from 0.0 (F/SpikedGLM.bl:29-33)
   BPT_D void refresh() {
-    for (int i = rr.lo + 2 * threadIdx.x; i < rr.hi; i += 2 * blockDim.x) {
+    for (int i = rr.lo + 2 * threadIdx.x; i < rr.hi; i += 2 * THREADS) {
       const bool two = i + 1 < rr.hi;
       double a = 0.0, b = 0.0;
       for (int j = 0; j < d.p; j++) {
@@ -206,9 +280,9 @@ struct LogisticFam {
   BPT_D void full(GroupReducer& red, double& loglik, int& noos, double& logprior) {
     refresh();
     double acc = 0.0; int cnt = 0;
-    for (int i = rr.lo + 2 * threadIdx.x; i < rr.hi; i += 2 * blockDim.x) {
-      row_term(eta[i], d.y[i], acc, cnt);
-      if (i + 1 < rr.hi) row_term(eta[i + 1], d.y[i + 1], acc, cnt);
+    for (int i = rr.lo + 2 * threadIdx.x; i < rr.hi; i += 2 * THREADS) {
+      row_term(eta[i], d.y + i, acc, cnt);
+      if (i + 1 < rr.hi) row_term(eta[i + 1], d.y + i + 1, acc, cnt);
     }
     red.reduce(acc, cnt);
     loglik = acc; noos = cnt;
@@ -221,6 +295,7 @@ struct LogisticFam {
     for (int j = 0; j < d.p; j++) { const double w = gen_normal(rng, 0.0, d.v0); P[j] = w; }
   }
 };
+using LogisticFam = LogisticFamT<512>;
 
 // ===========================================================================
 // C3  K-component Gaussian mixture, indicators marginalised.

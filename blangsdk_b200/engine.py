@@ -70,7 +70,7 @@ EXPORTS = [
     "blangpt_get_round_stats", "blangpt_adapt", "blangpt_reset_round", "blangpt_rounds",
     "blangpt_perform_inference", "blangpt_counters", "blangpt_set_stream", "blangpt_evaluate", "blangpt_prime",
     "blangpt_explore", "blangpt_table_ptr", "blangpt_local_chains", "blangpt_swap", "blangpt_synchronize",
-    "blangpt_microbench",
+    "blangpt_microbench", "blangpt_debug_logit_terms",
 ]
 
 _LIB = None
@@ -118,6 +118,7 @@ def load_library():
     L.blangpt_local_chains.restype = C.c_int64
     L.blangpt_swap.argtypes = [vp, C.POINTER(ScanOutputs)]
     L.blangpt_microbench.argtypes = [C.c_int32, C.c_int32, _dp]
+    L.blangpt_debug_logit_terms.argtypes = [C.c_int32, _dp, _ip, C.c_int64, _dp]
     _LIB = L
     return L
 
@@ -129,6 +130,17 @@ def microbench(which, device=0):
     if rc != 0:
         raise BlangPTError("microbench failed (no GPU?)")
     return out.value
+
+
+def debug_logit_terms(z, y, device=0):
+    """Per-row Bernoulli(logistic(z)) terms as the CUDA kernels compute them (accuracy tests)."""
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.int32)
+    out = np.zeros_like(z)
+    rc = load_library().blangpt_debug_logit_terms(device, _d(z), _i(y), z.size, _d(out))
+    if rc != 0:
+        raise BlangPTError("debug_logit_terms failed")
+    return out
 
 
 def rounds(nScans, adaptFraction):

@@ -208,6 +208,9 @@ int blangpt_synchronize(blangpt_handle* h);
  * which = 1 -> logistic-regression row terms per second with operands in registers (the
  * compute-only bound of the C2 likelihood kernel). */
 int blangpt_microbench(int32_t device, int32_t which, double* out_rate);
+/* Accuracy hook: the per-row Bernoulli(logistic(z)) log-likelihood term exactly as the C2 kernels
+ * evaluate it (F/SpikedGLM.bl:26-35 -> Bernoulli.bl:11-14 -> Categorical.bl:12-15); -inf = out of support. */
+int blangpt_debug_logit_terms(int32_t device, const double* z, const int32_t* y, int64_t n, double* out);
 
 #ifdef __cplusplus
 }

@@ -314,3 +314,26 @@ def test_error_paths(datasets):
     eng.close()
     with pytest.raises(BlangPTError):
         PT(targetAccept=0.5)
+
+
+def test_logit_term_accuracy_and_support():
+    """The lean fp64 row term of the C2 kernels: exact form within 1e-13 of a long-double evaluation on
+    sg >= -12, the reference's naive arithmetic (incl. -inf once p rounds to 1.0) beyond."""
+    from blangsdk_b200.engine import debug_logit_terms
+    rng = np.random.default_rng(5)
+    z = np.concatenate([rng.normal(0, 4, 20000), np.linspace(-45, 45, 9001), rng.normal(0, 30, 5000),
+                        [0.0, -0.0, 1e-300, -1e-300, 700.0, -700.0, 36.7, 36.8, -36.8, 12.0, -12.0, 11.999999, -12.000001]])
+    y = rng.integers(0, 2, z.size).astype(np.int32)
+    got = debug_logit_terms(z, y)
+    sg = np.where(y == 1, z, -z).astype(np.longdouble)
+    exact = (np.minimum(sg, 0) - np.log1p(np.exp(-np.abs(sg)))).astype(np.float64)
+    with np.errstate(divide="ignore", over="ignore"):
+        pr = 1.0 / (1.0 + np.exp(-z))
+        naive = np.log(np.where(y == 1, pr, 1.0 - pr))
+    lean = sg >= -12.0
+    assert np.max(np.abs(got[lean] - exact[lean])) < 1e-13
+    assert np.max(np.abs(got[lean] - naive[lean])) < 2e-11          # the two forms agree where the lean one is used
+    fin = ~lean & np.isfinite(naive)
+    assert np.array_equal(np.isinf(got[~lean]), np.isinf(naive[~lean]))   # same out-of-support rows
+    assert np.max(np.abs(got[fin] - naive[fin]) / np.abs(naive[fin])) < 1e-12
+    assert np.isinf(got[~lean]).sum() > 0
