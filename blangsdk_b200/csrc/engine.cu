@@ -31,7 +31,7 @@ struct blangpt_handle {
   int family = 0;
   int n_reals = 0, n_ints = 0, n_samplers = 0;
   int G = 1;                      // CTAs per chain
-  int logistic_threads = 1024;    // CTA size of the C2 kernel (BLANGPT_LOGISTIC_THREADS=512|1024)
+  int logistic_threads = 512;     // CTA size of the C2 kernel (BLANGPT_LOGISTIC_THREADS=512|1024)
   bool model_set = false, tables_valid = false;
   cudaStream_t stream = nullptr;  // nullptr = legacy default stream
   bool own_stream = false;
@@ -104,7 +104,7 @@ extern "C" int blangpt_create(const blangpt_config* cfg, blangpt_handle** out) {
   if (prop.major < 10) { set_error(nullptr, "device sm_%d%d is not Blackwell (kernels are built for sm_100a only)", prop.major, prop.minor); return BLANGPT_ECUDA; }
   blangpt_handle* h = new blangpt_handle();
   h->cfg = *cfg;
-  if (const char* t = getenv("BLANGPT_LOGISTIC_THREADS")) h->logistic_threads = atoi(t) == 512 ? 512 : 1024;
+  if (const char* t = getenv("BLANGPT_LOGISTIC_THREADS")) h->logistic_threads = atoi(t) == 1024 ? 1024 : 512;
   h->M_total = (int64_t)cfg->nReplicas * cfg->nChains;
   *out = h;
   return BLANGPT_OK;
@@ -808,9 +808,8 @@ __global__ void mb_logit_kernel(double* out, int iters) {
   __shared__ int serr;
   double z0 = -3.0 + 9.0 * threadIdx.x / blockDim.x, z1 = 1.0 - z0, acc = 0.0; int cnt = 0;
   __shared__ uint8_t sy[2];
-  LogisticFam fam; fam.err = &serr;
   for (int i = 0; i < iters; i++) {
-    fam.row_term(z0, sy, acc, cnt); fam.row_term(z1, sy + 1, acc, cnt);
+    logit_pair(z0, z1, sy, acc, cnt, &serr);
     z0 += 1e-6; z1 -= 1e-6;
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc + cnt;

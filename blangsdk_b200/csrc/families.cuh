@@ -22,6 +22,9 @@
 
 namespace bpt {
 
+#ifndef BPT_LOGIT_QUAD
+#define BPT_LOGIT_QUAD 0
+#endif
 constexpr int kMaxParams = 64;    // latent reals per chain held in shared memory
 constexpr int kMaxSamplers = 65;
 
@@ -57,13 +60,13 @@ BPT_D void acc_term(double t, double& s, int& c, int* err) {
 // sg < -12 (or |sg| >= 700, or NaN) -- rare, and the only place where the reference's own
 // rounding and its -inf convention are visible -- the naive arithmetic is executed literally.
 // Coefficients live in constant memory so each one is a direct DFMA operand.
-__constant__ double kExpC[13] = {
-    2.08767569878680989792e-09, 2.50521083854417187751e-08, 2.75573192239858906526e-07,
+__constant__ double kExpC[12] = {   // Taylor 1/11! .. 1/0!: |r| <= ln2/2 -> relative error < 7e-15
+    2.50521083854417187751e-08, 2.75573192239858906526e-07,
     2.75573192239858906526e-06, 2.48015873015873015873e-05, 1.98412698412698412698e-04,
     1.38888888888888888889e-03, 8.33333333333333333333e-03, 4.16666666666666666667e-02,
     1.66666666666666666667e-01, 0.5, 1.0, 1.0};
-__constant__ double kAtanhC[9] = {
-    5.26315789473684210526e-02, 5.88235294117647058824e-02, 6.66666666666666666667e-02,
+__constant__ double kAtanhC[8] = {  // 1/17 .. 1/3: |f| <= 0.1716 -> absolute error < 3e-16
+    5.88235294117647058824e-02, 6.66666666666666666667e-02,
     7.69230769230769230769e-02, 9.09090909090909090909e-02, 1.11111111111111111111e-01,
     1.42857142857142857143e-01, 2.00000000000000000000e-01, 3.33333333333333333333e-01};
 // {-log2(e), 1.5*2^52, -ln2_hi, -ln2_lo, 1 - C, 1 + C, log(C)} with C = fl(sqrt 2)
@@ -71,45 +74,70 @@ __constant__ double kLogitK[7] = {
     -1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
     -0.41421356237309514547, 2.41421356237309514547, 0.34657359027997269783};
 
-BPT_D double exp_neg(double a) {   // exp(-a) for 0 <= a < 700
-  double kd = fma(a, kLogitK[0], kLogitK[1]);   // magic add: low word = round(-a*log2e)
-  const int k = __double2loint(kd);
-  kd -= kLogitK[1];
-  double r = fma(kd, kLogitK[2], -a);
-  r = fma(kd, kLogitK[3], r);
-  double p = kExpC[0];
+// W independent lanes evaluated together: min(z,0) - log1p(exp(-|z|)) for -12 <= z, |z| < 700.
+// Straight-line code; the W Horner chains interleave (ILP) and share every coefficient load.
+template <int W>
+BPT_D void logit_fast(const double (&z)[W], double& s) {
+  double kd[W], r[W], p[W]; int k[W];
 #pragma unroll
-  for (int i = 1; i < 13; i++) p = fma(p, r, kExpC[i]);
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  for (int w = 0; w < W; w++) {
+    const double a = fabs(z[w]);
+    kd[w] = fma(a, kLogitK[0], kLogitK[1]);     // magic add: low word = round(-a*log2e)
+    k[w] = __double2loint(kd[w]);
+    kd[w] -= kLogitK[1];
+    r[w] = fma(kd[w], kLogitK[2], -a);
+    r[w] = fma(kd[w], kLogitK[3], r[w]);
+    p[w] = kExpC[0];
+  }
+#pragma unroll
+  for (int i = 1; i < 12; i++)
+#pragma unroll
+    for (int w = 0; w < W; w++) p[w] = fma(p[w], r[w], kExpC[i]);
+  double f[W], f2[W], q[W];
+#pragma unroll
+  for (int w = 0; w < W; w++) {
+    // t = exp(-|z|) = p * 2^k in (0, 1]
+    const double t = __hiloint2double(__double2hiint(p[w]) + (k[w] << 20), __double2loint(p[w]));
+    // log(1+t) = log C + 2 atanh(f), f = (1+t-C)/(1+t+C), |f| <= 0.1716
+    const double num = t + kLogitK[4];
+    const double den = t + kLogitK[5];
+    double rc;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(den));
+    double e = fma(-den, rc, 1.0); rc = fma(rc, e, rc);
+    e = fma(-den, rc, 1.0); rc = fma(rc, e, rc);
+    f[w] = num * rc;
+    f2[w] = f[w] * f[w];
+    q[w] = kAtanhC[0];
+  }
+#pragma unroll
+  for (int i = 1; i < 8; i++)
+#pragma unroll
+    for (int w = 0; w < W; w++) q[w] = fma(q[w], f2[w], kAtanhC[i]);
+#pragma unroll
+  for (int w = 0; w < W; w++) {
+    const double s1 = f[w] + f[w];
+    const double l = fma(s1 * f2[w], q[w], s1 + kLogitK[6]);
+    s += fma(0.5, z[w] - fabs(z[w]), -l);       // min(z,0) - log1p(exp(-|z|))
+  }
 }
-BPT_D double log1p_unit(double t) {   // log(1+t), t in [0,1]: log C + 2 atanh(f), f = (1+t-C)/(1+t+C), |f| <= 0.1716
-  const double num = t + kLogitK[4];
-  const double den = t + kLogitK[5];
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
-  double e = fma(-den, r, 1.0); r = fma(r, e, r);
-  e = fma(-den, r, 1.0); r = fma(r, e, r);
-  double f = num * r;
-  f = fma(fma(-den, f, num), r, f);
-  const double f2 = f * f;
-  double q = kAtanhC[0];
-#pragma unroll
-  for (int i = 1; i < 9; i++) q = fma(q, f2, kAtanhC[i]);
-  const double s1 = f + f;
-  return fma(s1 * f2, q, s1 + kLogitK[6]);
+BPT_D bool logit_is_fast(double zs) { return zs >= -12.0 && fabs(zs) < 700.0; }
+
+// the literal reference arithmetic (rounding + -inf convention); NaN lands here too
+BPT_D void logit_slow(double zs, const uint8_t* yp, double& s, int& c, int* err) {
+  const int y = *yp;
+  const double z = y ? zs : -zs;
+  const double pr = 1.0 / (1.0 + exp(-z));
+  const double pick = y ? pr : 1.0 - pr;
+  acc_term(log(pick), s, c, err);
 }
 // zs = sign-folded margin (y ? z : -z); *yp is only read on the rare literal path
 BPT_D void logit_term(double zs, const uint8_t* yp, double& s, int& c, int* err) {
-  if (zs >= -12.0 && fabs(zs) < 700.0) {
-    const double l = log1p_unit(exp_neg(fabs(zs)));
-    s += fma(0.5, zs - fabs(zs), -l);          // min(zs,0) - log1p(exp(-|zs|))
-  } else {   // literal reference arithmetic (rounding + -inf convention); NaN lands here too
-    const int y = *yp;
-    const double z = y ? zs : -zs;
-    const double pr = 1.0 / (1.0 + exp(-z));
-    const double pick = y ? pr : 1.0 - pr;
-    acc_term(log(pick), s, c, err);
-  }
+  if (logit_is_fast(zs)) { const double z[1] = {zs}; logit_fast<1>(z, s); }
+  else logit_slow(zs, yp, s, c, err);
+}
+BPT_D void logit_pair(double za, double zb, const uint8_t* yp, double& s, int& c, int* err) {
+  if (logit_is_fast(za) && logit_is_fast(zb)) { const double z[2] = {za, zb}; logit_fast<2>(z, s); }
+  else { logit_term(za, yp, s, c, err); logit_term(zb, yp + 1, s, c, err); }
 }
 
 // Normal.bl:21-24 with constant mean/variance (a prior on x)
@@ -226,25 +254,45 @@ struct LogisticFamT {
   // Bernoulli.bl:11-14 -> Categorical.bl:12-15 with p = logistic(eta).  See logit_term() above.
   BPT_D void row_term(double zs, const uint8_t* yp, double& s, int& c) const { logit_term(zs, yp, s, c, err); }
 
-  // one pass over this CTA's rows: eta and column k of X streamed with 16-byte loads, the next
-  // pair prefetched before the current pair's ~110 fp64 instructions
+  // one pass over this CTA's rows: eta and column k of X streamed as 16-byte pairs, the next pair
+  // prefetched before the current pair's ~90 fp64 instructions; both rows of a pair run interleaved
   BPT_D void annealed(int k, double x, int, GroupReducer& red, double& s, int& c) const {
     const double delta = x - P[k];
-    const double* col = d.xt + (size_t)k * d.npad;
     double acc = 0.0; int cnt = 0;
-    const int stride = 2 * THREADS;
-    int i = rr.lo + 2 * threadIdx.x;
-    double2 en = make_double2(0.0, 0.0), xn = en;
-    if (i + 1 < rr.hi) { en = *reinterpret_cast<const double2*>(eta + i); xn = *reinterpret_cast<const double2*>(col + i); }
-    while (i + 1 < rr.hi) {
-      const double2 e = en, xv = xn;
-      const int nx = i + stride;
-      if (nx + 1 < rr.hi) { en = *reinterpret_cast<const double2*>(eta + nx); xn = *reinterpret_cast<const double2*>(col + nx); }
-      row_term(fma(delta, xv.x, e.x), d.y + i, acc, cnt);
-      row_term(fma(delta, xv.y, e.y), d.y + i + 1, acc, cnt);
-      i = nx;
+    const int n_pairs = (rr.hi - rr.lo) >> 1;
+    const double2* pe = reinterpret_cast<const double2*>(eta + rr.lo) + threadIdx.x;
+    const double2* px = reinterpret_cast<const double2*>(d.xt + (size_t)k * d.npad + rr.lo) + threadIdx.x;
+    const uint8_t* py = d.y + rr.lo + 2 * threadIdx.x;
+    int left = n_pairs - (int)threadIdx.x;          // pairs this thread still has to do (stride THREADS)
+#if BPT_LOGIT_QUAD
+    // two pairs (4 rows) per iteration: 4 interleaved Horner chains per thread
+    while (left > THREADS) {
+      const double2 e0 = pe[0], x0 = px[0], e1 = pe[THREADS], x1 = px[THREADS];
+      const double z0 = fma(delta, x0.x, e0.x), z1 = fma(delta, x0.y, e0.y);
+      const double z2 = fma(delta, x1.x, e1.x), z3 = fma(delta, x1.y, e1.y);
+      if (logit_is_fast(z0) && logit_is_fast(z1) && logit_is_fast(z2) && logit_is_fast(z3)) {
+        const double z[4] = {z0, z1, z2, z3};
+        logit_fast<4>(z, acc);
+      } else {
+        logit_pair(z0, z1, py, acc, cnt, err);
+        logit_pair(z2, z3, py + 2 * THREADS, acc, cnt, err);
+      }
+      left -= 2 * THREADS; pe += 2 * THREADS; px += 2 * THREADS; py += 4 * THREADS;
     }
-    if (i < rr.hi) row_term(fma(delta, col[i], eta[i]), d.y + i, acc, cnt);
+#endif
+    double2 en = make_double2(0.0, 0.0), xn = en;
+    if (left > 0) { en = *pe; xn = *px; }
+    while (left > 0) {
+      const double2 e = en, xv = xn;
+      left -= THREADS; pe += THREADS; px += THREADS;
+      if (left > 0) { en = *pe; xn = *px; }
+      logit_pair(fma(delta, xv.x, e.x), fma(delta, xv.y, e.y), py, acc, cnt, err);
+      py += 2 * THREADS;
+    }
+    if (((rr.hi - rr.lo) & 1) && threadIdx.x == 0) {   // odd tail row of this CTA's range
+      const int i = rr.hi - 1;
+      row_term(fma(delta, d.xt[(size_t)k * d.npad + i], eta[i]), d.y + i, acc, cnt);
+    }
     red.reduce(acc, cnt);
     s = acc; c = cnt;
   }
