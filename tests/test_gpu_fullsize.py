@@ -1,0 +1,158 @@
+"""-m gpu tests at BASELINE.json's full sizes, where the oracle is too slow: size-independent properties
+(annealing linearity, additivity over data splits, permutation invariance, symmetry, DEO parity pattern,
+round trips replayed from the swap indicators) and an independent numpy evaluation of the likelihood."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _logit_loglik(x, y, w):
+    s = np.where(y == 1, 1.0, -1.0) * (x @ w)
+    return float(np.sum(np.minimum(s, 0.0) - np.log1p(np.exp(-np.abs(s)))))
+
+
+def test_c2_full_size_against_numpy(datasets):
+    """C2 (100k x 32, 64 chains): after real scans, every chain's reported log-likelihood equals a numpy
+    evaluation at the reported state; annealed density = fixed + beta * loglik."""
+    from blangsdk_b200.engine import Engine
+    spec = datasets.logistic_regression()
+    eng = Engine(nChains=64, random=3)
+    eng.set_model(spec)
+    eng.initialize("COPIES")
+    out = eng.run_scans(3, want=("energy", "logDensity", "nOutOfSupport", "swapIndicators"))
+    d = eng.log_density()                        # from-scratch evaluation of the current states
+    lad = eng.get_ladder()[0]
+    for p in range(0, 63, 7):                    # cold chains: no row anywhere near the literal (z < -12) path
+        w, _ = eng.get_state(p)
+        ref = _logit_loglik(spec["x"], spec["y"], w)
+        assert abs(d["loglik"][0, p] - ref) <= TOL * abs(ref)
+        assert d["noos"][0, p] == 0
+        prior = float(np.sum(-0.5 * math.log(2 * math.pi * 10.0) - 0.5 * w ** 2 / 10.0))
+        assert abs(d["fixed"][0, p] - prior) <= TOL * abs(prior)
+        assert abs(d["logdens"][0, p] - (prior + lad[p] * ref)) <= TOL * abs(prior + lad[p] * ref)
+    # DEO: scan t only attempts pairs i = (t mod 2) + 2k
+    ind = out["swapIndicators"][:, 0, :]
+    for t in range(ind.shape[0]):
+        assert np.all(ind[t, (1 - t % 2)::2] == 0)
+    eng.close()
+
+
+@pytest.mark.parametrize("fam", ["normal", "mixture", "logistic"])
+def test_additivity_and_permutation(datasets, fam):
+    """loglik(A u B) = loglik(A) + loglik(B), and shuffling the observations changes nothing (to rounding)"""
+    from blangsdk_b200.engine import Engine
+    rng = np.random.default_rng(0)
+    if fam == "normal":
+        spec = datasets.normal_meanvar(n=200_001)
+        split = lambda s, idx: dict(s, y=s["y"][idx])
+        state = [1.3, 3.7]
+    elif fam == "mixture":
+        spec = datasets.gaussian_mixture(n=300_001)
+        split = lambda s, idx: dict(s, y=s["y"][idx])
+        state = [-5.5, -2.2, 1.7, 6.3, 1.1, 0.3, 0.2, 0.9, 0.2, 0.3, 0.1, 0.4]
+    else:
+        spec = datasets.logistic_regression(150_001, 16)
+        split = lambda s, idx: dict(s, x=s["x"][idx], y=s["y"][idx])
+        state = rng.normal(0, 0.3, 16)
+    n = len(spec["y"])
+    perm = rng.permutation(n)
+
+    def loglik(sp):
+        e = Engine(nChains=2, random=1)
+        e.set_model(sp)
+        for p in range(2):
+            e.set_state(p, state)
+        v = e.log_density()["loglik"][0]
+        e.close()
+        assert v[0] == v[1]
+        return v[0]
+    full = loglik(spec)
+    a, b = loglik(split(spec, perm[: n // 3])), loglik(split(spec, perm[n // 3:]))
+    shuffled = loglik(split(spec, perm))
+    assert abs(full - (a + b)) <= 1e-11 * abs(full)
+    assert abs(full - shuffled) <= 1e-11 * abs(full)
+
+
+def test_c4_ising_symmetries(datasets):
+    """256 x 256 lattice: all-equal configuration has energy J * 2N^2 exactly; global flip symmetry at moment 0"""
+    from blangsdk_b200.engine import Engine
+    spec = datasets.ising(256)
+    J, N = spec["hyper"]["coupling"], 256
+    eng = Engine(nChains=4, random=1)
+    eng.set_model(spec)
+    rng = np.random.default_rng(1)
+    s = rng.integers(0, 2, N * N)
+    eng.set_state(0, None, np.ones(N * N, dtype=np.int32))
+    eng.set_state(1, None, np.zeros(N * N, dtype=np.int32))
+    eng.set_state(2, None, s)
+    eng.set_state(3, None, 1 - s)
+    d = eng.log_density()
+    assert d["loglik"][0, 0] == J * 2 * N * N and d["loglik"][0, 1] == J * 2 * N * N
+    assert d["loglik"][0, 2] == d["loglik"][0, 3]
+    g = s.reshape(N, N) * 2 - 1
+    ref = J * float(np.sum(g * np.roll(g, -1, 0)) + np.sum(g * np.roll(g, -1, 1)))
+    assert abs(d["loglik"][0, 2] - ref) <= 1e-12 * max(1.0, abs(ref))
+    assert np.allclose(d["fixed"][0], N * N * math.log(0.5), rtol=1e-13)
+    eng.close()
+
+
+def test_c5_round_trips_replayed_from_indicators(datasets):
+    """many replicas: the device-side index process (Paths.nRejuvenations) equals a host replay of the
+    recorded swap indicators, replica by replica"""
+    from blangsdk_b200.engine import Engine
+    R, N, S = 64, 8, 300
+    eng = Engine(nChains=N, nReplicas=R, random=4)
+    eng.set_model(datasets.beta_binomial_batch(R))
+    eng.initialize("FORWARD")
+    out = eng.run_scans(S, want=("swapIndicators",))
+    st = eng.round_stats()
+    ind = out["swapIndicators"]
+    for r in range(R):
+        pos = list(range(N))                       # pos[particle]
+        at = list(range(N))                        # particle at position
+        flag = [p == N - 1 for p in range(N)]
+        count = 0
+        for t in range(S):
+            assert np.all(ind[t, r, (1 - t % 2)::2] == 0)
+            for i in range(N - 1):
+                if ind[t, r, i]:
+                    a, b = at[i], at[i + 1]
+                    at[i], at[i + 1] = b, a
+            for p in range(N):
+                q = at[p]
+                if p == 0 and flag[q]:
+                    flag[q] = False; count += 1
+                elif p == N - 1:
+                    flag[q] = True
+        assert count == st["roundTrips"][r]
+    assert st["roundTrips"].sum() > 0
+    eng.close()
+
+
+def test_ising_gpu_statistics_against_enumeration(oracle, datasets):
+    """Checkerboard NRPT on a 4x4 lattice: stepping-stone log Z within 0.1 of exhaustive enumeration
+    (the reference's own bar, T/TestEndToEnd.xtend:139-167) and mean energy at beta=1 within MC error."""
+    from blangsdk_b200.engine import PT
+    spec = datasets.ising(4)
+    h = spec["hyper"]
+    exact = oracle.lib().orc_ising_exact_log_z(4, h["coupling"], h["moment"], 1.0)
+    pt = PT(nChains=8, nScans=4000, adaptFraction=0.5, random=5)
+    pt.setSampledModel(spec)
+    res = pt.performInference(want=("energy",))
+    st = res["finalStats"]
+    assert abs(st["logZSteppingStone"][0] - exact) < 0.1
+    assert abs(st["logZThermodynamic"][0] - exact) < 0.1
+    # d/dbeta log Z(beta) at 1 = E[loglik]: finite-difference the exact enumeration
+    eps = 1e-4
+    dlogz = (oracle.lib().orc_ising_exact_log_z(4, h["coupling"], h["moment"], 1.0 + eps) -
+             oracle.lib().orc_ising_exact_log_z(4, h["coupling"], h["moment"], 1.0 - eps)) / (2 * eps)
+    e = -res["energy"][-2000:, 0, 0]              # loglik of the beta = 1 chain in the final round
+    nb = 40
+    bm = e[: len(e) // nb * nb].reshape(nb, -1).mean(1)
+    se = bm.std(ddof=1) / math.sqrt(nb)
+    assert abs(e.mean() - dlogz) < 5 * se + 0.05
+    pt.engine.close()

@@ -1,0 +1,103 @@
+"""Exact-invariance tests of the oracle's samplers, after R/validation/ExactInvarianceTest.java:71-102,221-247
+(the reference's main correctness tool, T/TestSDKDistributions.xtend:12-18): a test function of the
+parameters has the same law under (a) the prior and (b) prior -> simulate data -> K posterior sampler steps.
+Two-sample KS, Bonferroni-corrected.  The CUDA engine reproduces the oracle draw for draw (-m gpu tests), so
+these laws carry over.  Plus the exhaustive 16-state check of T/TestDiscreteModels.xtend:17-30 for Ising N=2."""
+import math
+
+import numpy as np
+import pytest
+from scipy import stats
+
+N_REP = 600
+K_SCANS = 6
+ALPHA = 0.005
+
+
+def _eit(oracle, make_spec, draw_prior, simulate, n_reals, stat_fns, seed0):
+    rng = np.random.default_rng(seed0)
+    prior_vals, post_vals = [], []
+    for rep in range(N_REP):
+        theta = draw_prior(rng)
+        data = simulate(rng, theta)
+        m = oracle.Model(make_spec(data))
+        pt = oracle.PT(m, nChains=1, seed=1000 + rep)
+        pt.set_state(0, theta)
+        for _ in range(K_SCANS):
+            pt.scan()
+        post, _ = pt.get_state(0)
+        prior_vals.append([f(np.asarray(theta)) for f in stat_fns])
+        post_vals.append([f(post) for f in stat_fns])
+        assert pt.check_caches() < 1e-9
+    prior_vals, post_vals = np.array(prior_vals), np.array(post_vals)
+    for j in range(len(stat_fns)):
+        p = stats.ks_2samp(prior_vals[:, j], post_vals[:, j]).pvalue
+        assert p > ALPHA / len(stat_fns), "statistic %d: KS p = %.2e" % (j, p)
+
+
+def test_eit_normal(oracle):
+    def prior(rng):
+        return [rng.normal(0.0, 2.0), rng.exponential(1.0 / 0.7)]
+    def sim(rng, th):
+        return rng.normal(th[0], math.sqrt(th[1]), 4)
+    spec = lambda y: dict(family="normal", hyper=dict(m0=0.0, v0=4.0, rate=0.7), y=y)
+    _eit(oracle, spec, prior, sim, 2, [lambda t: t[0], lambda t: t[1], lambda t: t[0] * t[1]], 1)
+
+
+def test_eit_logistic(oracle):
+    x = np.column_stack([np.ones(6), np.linspace(-1.5, 1.5, 6)])
+    def prior(rng):
+        return rng.normal(0.0, math.sqrt(1.5), 2)
+    def sim(rng, th):
+        return (rng.random(6) < 1.0 / (1.0 + np.exp(-(x @ th)))).astype(np.int32)
+    spec = lambda y: dict(family="logistic", hyper=dict(v0=1.5), x=x, y=y)
+    _eit(oracle, spec, prior, sim, 2, [lambda t: t[0], lambda t: t[1], lambda t: t[0] ** 2 + t[1] ** 2], 2)
+
+
+def test_eit_beta_binomial(oracle):
+    nt = np.array([12, 7, 20], dtype=np.int32)
+    def prior(rng):
+        return [rng.exponential(1.0 / 0.8), rng.exponential(1.0 / 0.8)]
+    def sim(rng, th):
+        p = rng.beta(th[0], th[1], 3)
+        p = np.clip(p, 1e-300, 1 - 1e-16)
+        return rng.binomial(nt, p).astype(np.int32)
+    spec = lambda y: dict(family="betabinomial", hyper=dict(rate=0.8), y=y, ntrials=nt)
+    _eit(oracle, spec, prior, sim, 2, [lambda t: t[0], lambda t: t[1], lambda t: t[0] / (t[0] + t[1])], 3)
+
+
+def test_eit_mixture(oracle):
+    K = 2
+    def prior(rng):
+        return np.concatenate([rng.normal(0.0, 2.0, K), rng.gamma(2.0, 1.0 / 2.0, K), rng.dirichlet(np.ones(K))])
+    def sim(rng, th):
+        z = rng.random(5) < th[4]            # component 0 with probability pi_0
+        comp = np.where(z, 0, 1)
+        return rng.normal(th[comp], np.sqrt(th[2 + comp]))
+    spec = lambda y: dict(family="mixture", hyper=dict(K=K, m0=0.0, v0=4.0, gshape=2.0, grate=2.0, conc=1.0), y=y)
+    _eit(oracle, spec, prior, sim, 6,
+         [lambda t: t[0], lambda t: t[2], lambda t: t[4], lambda t: t[0] * t[4] + t[1] * t[5]], 4)
+
+
+@pytest.mark.parametrize("order", ["reference", "checkerboard"])
+def test_ising_16_states(oracle, datasets, order):
+    """Ising N=2 at beta = 1: state frequencies of a long single-chain run against exact enumeration."""
+    spec = datasets.ising(2)
+    m = oracle.Model(spec)
+    logp = np.array([m.log_density(ints=[(s >> k) & 1 for k in range(4)])["logdens"] for s in range(16)])
+    p = np.exp(logp - logp.max()); p /= p.sum()
+    pt = oracle.PT(m, nChains=1, seed=5, nPassesPerScan=1.0,
+                   sweepOrder=oracle.ORDER_CHECKERBOARD if order == "checkerboard" else oracle.ORDER_REFERENCE)
+    counts = np.zeros(16)
+    n, thin = 40000, 4
+    for t in range(n * thin):
+        pt.scan()
+        if t % thin == 0:
+            _, s = pt.get_state(0)
+            counts[int(s[0] + 2 * s[1] + 4 * s[2] + 8 * s[3])] += 1
+    # the two ordered states (all 0 / all 1, 42% each) exchange slowly: fold each state with its global
+    # flip (equal probability by symmetry at moment = 0) for the tight check, loose check unfolded
+    freq = counts / n
+    folded = freq + freq[::-1]
+    assert np.max(np.abs(folded - (p + p[::-1]))) < 0.01
+    assert np.max(np.abs(freq - p)) < 0.06

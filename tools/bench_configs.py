@@ -1,0 +1,56 @@
+"""Throughput of every BASELINE.json config shape on one GPU (C1..C5), a few scans each.
+Writes one JSON object per config to stdout; used for profiles/configs_r01.json."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from blangsdk_b200 import datasets as D  # noqa: E402
+from blangsdk_b200.engine import Engine  # noqa: E402
+
+
+def run(name, spec, nChains, nReplicas=1, init="FORWARD", warm=3, scans=10, algo_bytes=None):
+    eng = Engine(nChains=nChains, nReplicas=nReplicas, random=1)
+    eng.set_model(spec)
+    eng.initialize(init)
+    eng.run_scans(warm, want=())
+    c0 = eng.counters()
+    t0 = time.perf_counter()
+    eng.run_scans(scans, want=())
+    st_mid = eng.counters()
+    dt = time.perf_counter() - t0
+    ev = st_mid["evals"] - c0["evals"]
+    out = dict(config=name, nChains=nChains, nReplicas=nReplicas, scans=scans, ms_per_scan=1e3 * dt / scans,
+               evals_per_s=ev / dt, scans_per_s=scans / dt, evals_per_scan=ev / scans,
+               ctas_per_chain=eng.ctas_per_chain, launches=st_mid["launches"] - c0["launches"])
+    if algo_bytes:
+        out["algorithmic_GBps"] = ev / dt * algo_bytes / 1e9
+    # a short adaptive run for round trips / Lambda
+    eng.reset_round()
+    t0 = time.perf_counter()
+    n_rt = max(scans * 4, 40)
+    eng.run_scans(n_rt, want=())
+    dt2 = time.perf_counter() - t0
+    st = eng.round_stats()
+    out.update(round_trips=int(st["roundTrips"].sum()), round_trips_per_s=float(st["roundTrips"].sum()) / dt2,
+               Lambda=float(np.mean(st["Lambda"])))
+    eng.close()
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["C1", "C2", "C3", "C4", "C5"]
+    if "C1" in which:
+        run("C1 normal 1000 obs, 8 chains", D.normal_meanvar(), 8, scans=200, warm=20, algo_bytes=8000)
+    if "C2" in which:
+        run("C2 logistic 100k x 32, 64 chains", D.logistic_regression(), 64, init="COPIES", scans=10, algo_bytes=25_700_000)
+    if "C3" in which:
+        run("C3 mixture K=4 1M obs, 256 chains", D.gaussian_mixture(), 256, init="COPIES", scans=2, warm=1, algo_bytes=8_000_000)
+    if "C4" in which:
+        run("C4 ising 256x256, 128 chains (1 of 8 GPUs)", D.ising(256), 128, scans=20, warm=3, algo_bytes=None)
+    if "C5" in which:
+        run("C5 beta-binomial 4096 replicas x 8 chains", D.beta_binomial_batch(4096), 8, nReplicas=4096, scans=50, warm=5, algo_bytes=256)
