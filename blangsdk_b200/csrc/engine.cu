@@ -104,7 +104,7 @@ extern "C" int blangpt_create(const blangpt_config* cfg, blangpt_handle** out) {
   if (prop.major < 10) { set_error(nullptr, "device sm_%d%d is not Blackwell (kernels are built for sm_100a only)", prop.major, prop.minor); return BLANGPT_ECUDA; }
   blangpt_handle* h = new blangpt_handle();
   h->cfg = *cfg;
-  if (const char* t = getenv("BLANGPT_LOGISTIC_THREADS")) h->logistic_threads = atoi(t) == 1024 ? 1024 : 512;
+  if (const char* t = getenv("BLANGPT_LOGISTIC_THREADS")) h->logistic_threads = atoi(t) == 1024 ? 1024 : (atoi(t) == 768 ? 768 : 512);
   h->M_total = (int64_t)cfg->nReplicas * cfg->nChains;
   *out = h;
   return BLANGPT_OK;
@@ -150,6 +150,10 @@ static int launch_explore(blangpt_handle* h, int mode) {
       if (h->logistic_threads == 1024) {
         LogisticFamT<1024>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
         return launch_explore_t<LogisticFamT<1024>>(h, d2, mode);
+      }
+      if (h->logistic_threads == 768) {
+        LogisticFamT<768>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
+        return launch_explore_t<LogisticFamT<768>>(h, d2, mode);
       }
       return launch_explore_t<LogisticFam>(h, h->logistic, mode);
     case BLANGPT_FAM_MIXTURE:

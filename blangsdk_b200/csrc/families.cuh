@@ -22,9 +22,6 @@
 
 namespace bpt {
 
-#ifndef BPT_LOGIT_QUAD
-#define BPT_LOGIT_QUAD 0
-#endif
 constexpr int kMaxParams = 64;    // latent reals per chain held in shared memory
 constexpr int kMaxSamplers = 65;
 
@@ -264,22 +261,6 @@ struct LogisticFamT {
     const double2* px = reinterpret_cast<const double2*>(d.xt + (size_t)k * d.npad + rr.lo) + threadIdx.x;
     const uint8_t* py = d.y + rr.lo + 2 * threadIdx.x;
     int left = n_pairs - (int)threadIdx.x;          // pairs this thread still has to do (stride THREADS)
-#if BPT_LOGIT_QUAD
-    // two pairs (4 rows) per iteration: 4 interleaved Horner chains per thread
-    while (left > THREADS) {
-      const double2 e0 = pe[0], x0 = px[0], e1 = pe[THREADS], x1 = px[THREADS];
-      const double z0 = fma(delta, x0.x, e0.x), z1 = fma(delta, x0.y, e0.y);
-      const double z2 = fma(delta, x1.x, e1.x), z3 = fma(delta, x1.y, e1.y);
-      if (logit_is_fast(z0) && logit_is_fast(z1) && logit_is_fast(z2) && logit_is_fast(z3)) {
-        const double z[4] = {z0, z1, z2, z3};
-        logit_fast<4>(z, acc);
-      } else {
-        logit_pair(z0, z1, py, acc, cnt, err);
-        logit_pair(z2, z3, py + 2 * THREADS, acc, cnt, err);
-      }
-      left -= 2 * THREADS; pe += 2 * THREADS; px += 2 * THREADS; py += 4 * THREADS;
-    }
-#endif
     double2 en = make_double2(0.0, 0.0), xn = en;
     if (left > 0) { en = *pe; xn = *px; }
     while (left > 0) {

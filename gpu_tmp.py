@@ -4,7 +4,7 @@ from blangsdk_b200 import datasets as D
 from blangsdk_b200.engine import Engine, microbench
 spec = D.logistic_regression()
 print('terms/s', microbench(1))
-for thr in (512, 1024):
+for thr in (512, 768):
   os.environ['BLANGPT_LOGISTIC_THREADS'] = str(thr)
   for G in (2,):
     eng = Engine(nChains=64, random=1, ctasPerChain=G); eng.set_model(spec); eng.initialize("COPIES")
