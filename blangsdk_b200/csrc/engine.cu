@@ -293,14 +293,25 @@ static int alloc_engine(blangpt_handle* h) {
   return reset_round(h);
 }
 
+// Cluster size per chain: one wave when the chains fit (widest cluster that keeps >= 8k rows per CTA),
+// otherwise the smallest cluster whose last wave is >= 95 % full (chains are independent, so clusters of
+// different chains need not be co-resident).
 static int pick_ctas_per_chain(const blangpt_handle* h, int64_t rows) {
   if (h->cfg.ctasPerChain > 0) return h->cfg.ctasPerChain;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
   const int64_t local = h->M_total / h->cfg.worldSize;
   int G = 1;
-  // widest cluster that still fits one wave and leaves every CTA >= 8k rows
-  while (G < 8 && local * (G * 2) <= sms && rows / (G * 2) >= 8192) G *= 2;
+  if (local <= sms) {
+    while (G < 8 && local * (G * 2) <= sms && rows / (G * 2) >= 8192) G *= 2;
+    return G;
+  }
+  for (int g = 1; g <= 8; g *= 2) {
+    if (g > 1 && rows / g < 8192) break;
+    const double waves = (double)(local * g) / sms;
+    G = g;
+    if (std::ceil(waves) / waves <= 1.05) break;
+  }
   return G;
 }
 
@@ -818,11 +829,33 @@ __global__ void mb_logit_kernel(double* out, int iters) {
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc + cnt;
 }
-// which: 0 = fp64 FMA TFLOP/s, 1 = logistic row terms per second (compute-only ceiling of the C2 kernel)
+__global__ void mb_dfma_latency_kernel(double* out, int iters, int chains) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+  const double b = 0.999999, c = 1e-7;
+  if (chains == 1) for (int i = 0; i < iters; i++) { a0 = fma(a0, b, c); }
+  else if (chains == 2) for (int i = 0; i < iters; i++) { a0 = fma(a0, b, c); a1 = fma(a1, b, c); }
+  else for (int i = 0; i < iters; i++) { a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c); }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3;
+}
+// which: 0 = fp64 FMA TFLOP/s, 1 = logistic row terms per second (compute-only ceiling of the C2 kernel),
+// 10+c = cycles per dependent DFMA with c chains per thread, one warp per SM sub-partition (latency probe)
 extern "C" int blangpt_microbench(int32_t device, int32_t which, double* out_rate) {
   if (!out_rate) return BLANGPT_EINVAL;
   if (cudaSetDevice(device) != cudaSuccess) return BLANGPT_ECUDA;
   int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (which >= 10) {
+    const int chains = which - 10, iters = 200000;
+    double* d = nullptr;
+    if (cudaMalloc(&d, 128 * sizeof(double)) != cudaSuccess) return BLANGPT_ECUDA;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    mb_dfma_latency_kernel<<<1, 128>>>(d, 1000, chains);
+    cudaEventRecord(e0); mb_dfma_latency_kernel<<<1, 128>>>(d, iters, chains); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    *out_rate = (double)ms * 1e-3 * khz * 1e3 / ((double)iters * chains);   // cycles per DFMA issued per warp
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return cudaGetLastError() == cudaSuccess ? BLANGPT_OK : BLANGPT_ECUDA;
+  }
   const int threads = 512, blocks = sms * 2, iters = which == 0 ? 20000 : 2000;
   double* d = nullptr;
   if (cudaMalloc(&d, (size_t)threads * blocks * sizeof(double)) != cudaSuccess) return BLANGPT_ECUDA;

@@ -137,6 +137,40 @@ BPT_D void logit_pair(double za, double zb, const uint8_t* yp, double& s, int& c
   else { logit_term(za, yp, s, c, err); logit_term(zb, yp + 1, s, c, err); }
 }
 
+// ---------------------------------------------------------------------------
+// lean fp64 exp / log for the mixture kernel (operand ranges known, see MixtureFam::obs_fast)
+// ---------------------------------------------------------------------------
+BPT_D double exp_lean(double x) {   // exp(x) for -700 <= x <= 700 (caller clamps)
+  double kd = fma(x, -kLogitK[0], kLogitK[1]);
+  const int k = __double2loint(kd);
+  kd -= kLogitK[1];
+  double r = fma(kd, kLogitK[2], x);
+  r = fma(kd, kLogitK[3], r);
+  double p = kExpC[0];
+#pragma unroll
+  for (int i = 1; i < 12; i++) p = fma(p, r, kExpC[i]);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+BPT_D double log_lean(double a) {   // log(a) for normal positive a
+  const int hi = __double2hiint(a);
+  int mh = (hi & 0x000fffff) | 0x3ff00000;          // mantissa in [1, 2)
+  const int adj = mh >= 0x3ff6a09f ? 1 : 0;          // above sqrt(2): halve
+  mh -= adj << 20;
+  const int e = (hi >> 20) - 1023 + adj;
+  const double m = __hiloint2double(mh, __double2loint(a));   // [0.7071, 1.4142)
+  const double num = m - 1.0, den = m + 1.0;
+  double rc;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(den));
+  double t = fma(-den, rc, 1.0); rc = fma(rc, t, rc);
+  t = fma(-den, rc, 1.0); rc = fma(rc, t, rc);
+  const double f = num * rc, f2 = f * f;
+  double q = kAtanhC[0];
+#pragma unroll
+  for (int i = 1; i < 8; i++) q = fma(q, f2, kAtanhC[i]);
+  const double s1 = f + f;
+  return fma((double)e, 6.93147180559945309417e-01, fma(s1 * f2, q, s1));
+}
+
 // Normal.bl:21-24 with constant mean/variance (a prior on x)
 BPT_D double normal_f2(double mean, double variance, double x) {
   if (variance <= 0.0) return BPT_NEG_INF;
@@ -374,9 +408,10 @@ struct MixtureFam {
   }
   BPT_D void stage_constants(int k, double x, int aux) {
     __syncthreads();
-    if (threadIdx.x < d.K) {
+    if (threadIdx.x < KT) {
       const int c = threadIdx.x;
-      double mu, var, pi; substituted(k, x, aux, c, mu, var, pi);
+      double mu = 0.0, var = 1.0, pi = 0.0;      // padding components contribute exactly 0
+      if (c < d.K) substituted(k, x, aux, c, mu, var, pi);
       Cst[0 * KT + c] = mu;
       Cst[1 * KT + c] = var <= 0.0 ? BPT_NEG_INF : -0.5 * BPT_LOG_2PI + (-0.5 * log(var));
       Cst[2 * KT + c] = var <= 0.0 ? 0.0 : -0.5 / var;
@@ -384,24 +419,49 @@ struct MixtureFam {
     }
     __syncthreads();
   }
+  // literal form: log( sum_k pi_k * exp(logN_k(y)) ) with library exp/log (handles -inf, 0, NaN)
+  BPT_D void obs_slow(double yv, const double* mu, const double* a, const double* b, const double* pi, double& s,
+                      int& c) const {
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < KT; q++) { const double dd = mu[q] - yv; acc += pi[q] * exp(fma(b[q], dd * dd, a[q])); }
+    acc_term(log(acc), s, c, err);
+  }
+  // hot path: the KT exponentials run as KT interleaved chains; arguments are clamped to >= -700
+  // (a clamped term is < 1e-304, negligible next to the accepted range acc > 1e-250); anything
+  // outside that range -- every component underflowing, invalid variances, NaN -- is redone literally
   BPT_D void obs_term(double yv, const double* mu, const double* a, const double* b, const double* pi, double& s,
                       int& c) const {
     double acc = 0.0;
 #pragma unroll
-    for (int q = 0; q < KT; q++)
-      if (q < d.K) { const double dd = mu[q] - yv; acc += pi[q] * exp(fma(b[q], dd * dd, a[q])); }
-    acc_term(log(acc), s, c, err);
+    for (int q0 = 0; q0 < KT; q0 += 4) {     // four interleaved exp chains at a time
+      double arg[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const double dd = mu[q0 + q] - yv; arg[q] = fmax(fma(b[q0 + q], dd * dd, a[q0 + q]), -700.0); }
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc = fma(pi[q0 + q], exp_lean(arg[q]), acc);
+    }
+    if (acc > 1e-250 && acc < 1e250) s += log_lean(acc);
+    else obs_slow(yv, mu, a, b, pi, s, c);
   }
-  BPT_D void sum_obs(double& s, int& c) const {
+  // not inlined: the loop gets its own register allocation instead of competing with the sampler state
+  __device__ __noinline__ void sum_obs(double& s, int& c) const {
     double mu[KT], a[KT], b[KT], pi[KT];
 #pragma unroll
     for (int q = 0; q < KT; q++) { mu[q] = Cst[q]; a[q] = Cst[KT + q]; b[q] = Cst[2 * KT + q]; pi[q] = Cst[3 * KT + q]; }
-    for (int i = rr.lo + 2 * threadIdx.x; i < rr.hi; i += 2 * blockDim.x) {
-      if (i + 1 < rr.hi) {
-        const double2 v = *reinterpret_cast<const double2*>(d.y + i);
-        obs_term(v.x, mu, a, b, pi, s, c); obs_term(v.y, mu, a, b, pi, s, c);
-      } else obs_term(d.y[i], mu, a, b, pi, s, c);
+    const int n_pairs = (rr.hi - rr.lo) >> 1;
+    const double2* py = reinterpret_cast<const double2*>(d.y + rr.lo) + threadIdx.x;
+    int left = n_pairs - (int)threadIdx.x;
+    double2 vn = make_double2(0.0, 0.0);
+    if (left > 0) vn = *py;
+    while (left > 0) {
+      const double2 v = vn;
+      left -= blockDim.x; py += blockDim.x;
+      if (left > 0) vn = *py;
+      obs_term(v.x, mu, a, b, pi, s, c);
+      obs_term(v.y, mu, a, b, pi, s, c);
     }
+    if (((rr.hi - rr.lo) & 1) && threadIdx.x == 0) obs_term(d.y[rr.hi - 1], mu, a, b, pi, s, c);
   }
   BPT_D void annealed(int k, double x, int aux, GroupReducer& red, double& s, int& c) {
     stage_constants(k, x, aux);
