@@ -170,6 +170,17 @@ static int launch_explore(blangpt_handle* h, int mode) {
   FAIL(h, BLANGPT_ESTATE, "no model set");
 }
 
+// the fused replica kernel applies to warp-capable families with small data, <= 32 chains, one process
+static bool use_fused(const blangpt_handle* h) {
+  if (h->cfg.worldSize != 1 || h->cfg.nChains > 32) return false;
+  const char* env = getenv("BLANGPT_FUSED");
+  if (env && atoi(env) == 0) return false;
+  const bool forced = env && atoi(env) == 1;
+  if (h->family == BLANGPT_FAM_BETABINOMIAL) return forced || h->cfg.nReplicas >= 8;
+  if (h->family == BLANGPT_FAM_NORMAL) return h->normal.n <= 65536 && (forced || h->cfg.nReplicas >= 8);
+  return false;
+}
+
 static int launch_swap(blangpt_handle* h, const DevOut& O) {
   const int threads = std::min(256, std::max(32, ((h->cfg.nChains + 31) / 32) * 32));
   swap_kernel<<<h->cfg.nReplicas, threads, 0, h->stream>>>(h->E, h->St, O);
@@ -570,6 +581,13 @@ extern "C" int blangpt_run_scans(blangpt_handle* h, int32_t n_scans, const blang
     }
   }
   CUDA_OK(h, cudaMemsetAsync(h->E.batch_counter, 0, sizeof(uint32_t) * R, h->stream));
+  if (use_fused(h)) {   // many small replicas: the whole batch of scans in one launch, one warp per chain
+    const int threads = 32 * h->cfg.nChains;
+    if (h->family == BLANGPT_FAM_NORMAL) replica_kernel<NormalFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->normal, n_scans);
+    else replica_kernel<BetaBinomialFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->betabin, n_scans);
+    CUDA_OK(h, cudaGetLastError());
+    h->n_launches++;
+  } else
   for (int s = 0; s < n_scans; s++) {
     if ((rc = launch_explore(h, MODE_EXPLORE))) return rc;
     if (d_ising_samples) {

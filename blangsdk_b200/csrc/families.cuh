@@ -171,6 +171,33 @@ BPT_D double log_lean(double a) {   // log(a) for normal positive a
   return fma((double)e, 6.93147180559945309417e-01, fma(s1 * f2, q, s1));
 }
 
+// lean branch-free lnGamma for the beta-binomial kernel: shift by 8 and use Stirling's series at z = x + 8 >= 8
+//   lnGamma(x) = (z - 1/2) log z - z + log(2 pi)/2 + sum_j B_2j / (2j (2j-1) z^(2j-1)) - log( x (x+1) ... (x+7) )
+// (series truncated after z^-13: error < 1e-15).  All lanes execute the same instructions whatever their
+// argument, unlike the library lgamma whose range branches serialise inside a warp.  Valid for 1e-30 < x < 1e15;
+// outside, the library function is used.
+BPT_D double lgamma_lean(double x) {
+  if (!(x > 1e-30 && x < 1e15)) return lgamma(x);
+  double p = x;
+#pragma unroll
+  for (int j = 1; j < 8; j++) p *= x + (double)j;
+  const double z = x + 8.0;
+  double rz;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rz) : "d"(z));
+  double t = fma(-z, rz, 1.0); rz = fma(rz, t, rz);
+  t = fma(-z, rz, 1.0); rz = fma(rz, t, rz);
+  const double r2 = rz * rz;
+  double s = 6.41025641025641025641e-03;            //  1/156
+  s = fma(s, r2, -1.91752691752691752692e-03);      // -691/360360
+  s = fma(s, r2, 8.41750841750841750842e-04);       //  1/1188
+  s = fma(s, r2, -5.95238095238095238095e-04);      // -1/1680
+  s = fma(s, r2, 7.93650793650793650794e-04);       //  1/1260
+  s = fma(s, r2, -2.77777777777777777778e-03);      // -1/360
+  s = fma(s, r2, 8.33333333333333333333e-02);       //  1/12
+  const double body = fma(z - 0.5, log_lean(z), -z) + 9.18938533204672741780e-01;
+  return fma(s, rz, body) - log_lean(p);
+}
+
 // Normal.bl:21-24 with constant mean/variance (a prior on x)
 BPT_D double normal_f2(double mean, double variance, double x) {
   if (variance <= 0.0) return BPT_NEG_INF;
@@ -198,13 +225,16 @@ struct NormalFam {
     double m0, v0, rate;
   };
   static constexpr int kThreads = 128;
+  static constexpr bool kWarpCapable = true;   // may run one chain per warp in the fused replica kernel
   Data d; double* P; RowRange rr; int* err;
+  int t0, tn;   // this thread's index in the chain group and the group size
 
   BPT_D static int n_reals(const Data&) { return 2; }
   BPT_D static int n_samplers(const Data&) { return 2; }
   BPT_D void init(const Data& d_, int, double* P_, int G, int crank, int* err_) {
-    d = d_; P = P_; rr = group_rows(d.n, G, crank); err = err_;
+    d = d_; P = P_; rr = group_rows(d.n, G, crank); err = err_; t0 = threadIdx.x; tn = blockDim.x;
   }
+  BPT_D void set_lanes(int lane, int width) { t0 = lane; tn = width; }
   BPT_D int sampler_type(int) const { return S_REAL_SLICE; }
   BPT_D int sampler_var(int k) const { return k; }
   BPT_D int simplex_dim() const { return 0; }
@@ -213,7 +243,7 @@ struct NormalFam {
   }
   BPT_D double sum_sq(double mu) const {
     double s = 0.0;
-    for (int i = rr.lo + 2 * threadIdx.x; i < rr.hi; i += 2 * blockDim.x) {
+    for (int i = rr.lo + 2 * t0; i < rr.hi; i += 2 * tn) {
       if (i + 1 < rr.hi) {
         const double2 v = *reinterpret_cast<const double2*>(d.y + i);
         const double a = mu - v.x, b = mu - v.y;
@@ -270,6 +300,7 @@ struct LogisticFamT {
     double v0;
   };
   static constexpr int kThreads = THREADS;
+  static constexpr bool kWarpCapable = false;
   Data d; double* P; double* eta; RowRange rr; int* err;
 
   BPT_D static int n_reals(const Data& d) { return d.p; }
@@ -372,6 +403,7 @@ struct MixtureFam {
     double m0, v0, gshape, grate, conc;
   };
   static constexpr int kThreads = 512;
+  static constexpr bool kWarpCapable = false;
   Data d; double* P; double* Cst; RowRange rr; int* err;   // Cst: [4][KT] per-evaluation component constants
 
   BPT_D static int n_reals(const Data& d) { return 3 * d.K; }
@@ -537,7 +569,9 @@ struct BetaBinomialFam {
     double rate;
   };
   static constexpr int kThreads = 32;
+  static constexpr bool kWarpCapable = true;
   Data d; double* P; const int32_t* y; const int32_t* nt; const double* cst; RowRange rr; int* err;
+  int t0, tn;
 
   BPT_D static int n_reals(const Data&) { return 2; }
   BPT_D static int n_samplers(const Data&) { return 2; }
@@ -545,21 +579,25 @@ struct BetaBinomialFam {
     d = d_; P = P_; err = err_;
     const size_t rep = (size_t)(local_slot / d.chains_per_replica);
     y = d.y + rep * d.n; nt = d.nt + rep * d.n; cst = d.cst + rep * d.n;
-    rr = group_rows(d.n, G, crank);
+    rr = group_rows(d.n, G, crank); t0 = threadIdx.x; tn = blockDim.x;
   }
+  BPT_D void set_lanes(int lane, int width) { t0 = lane; tn = width; }
   BPT_D int sampler_type(int) const { return S_REAL_SLICE; }
   BPT_D int sampler_var(int k) const { return k; }
   BPT_D int simplex_dim() const { return 0; }
   BPT_D double fixed(int, double x, int) const { return gamma_ab(1.0, d.rate, x); }
   BPT_D void sum_groups(double a, double b, double& s, int& c) const {
     if (a <= 0.0 || b <= 0.0) {
-      for (int g = rr.lo + threadIdx.x; g < rr.hi; g += blockDim.x) c++;
+      for (int g = rr.lo + t0; g < rr.hi; g += tn) c++;
       return;
     }
-    const double ab = lgamma(a + b) - lgamma(a) - lgamma(b);
-    for (int g = rr.lo + threadIdx.x; g < rr.hi; g += blockDim.x) {
+#ifndef BPT_LGAMMA
+#define BPT_LGAMMA lgamma
+#endif
+    const double ab = BPT_LGAMMA(a + b) - BPT_LGAMMA(a) - BPT_LGAMMA(b);
+    for (int g = rr.lo + t0; g < rr.hi; g += tn) {
       const double yy = (double)y[g], n = (double)nt[g];
-      const double t = cst[g] + lgamma(yy + a) + lgamma(n - yy + b) + ab - lgamma(n + a + b);
+      const double t = cst[g] + BPT_LGAMMA(yy + a) + BPT_LGAMMA(n - yy + b) + ab - BPT_LGAMMA(n + a + b);
       acc_term(t, s, c, err);
     }
   }

@@ -63,6 +63,112 @@ struct DevOut {       // per-scan outputs of the current batch (nullable)
   int reversible;
 };
 
+// how the threads that share one chain synchronise and index themselves
+template <class Fam> struct LogDensityInline;
+template <class Fam> struct LogDensityCall;
+struct CtaSync {    // a chain owns whole CTAs (a cluster of G of them)
+  template <class Fam> using LogDensityOf = LogDensityInline<Fam>;
+  BPT_D static void sync() { __syncthreads(); }
+  BPT_D static int tid() { return threadIdx.x; }
+  BPT_D static int nthr() { return blockDim.x; }
+};
+struct WarpSync {   // a chain owns one warp (fused replica kernel)
+  template <class Fam> using LogDensityOf = LogDensityCall<Fam>;
+  BPT_D static void sync() { __syncwarp(); }
+  BPT_D static int tid() { return threadIdx.x & 31; }
+  BPT_D static int nthr() { return 32; }
+};
+
+// RealSliceSampler.logDensity :156-161 over ExponentiatedFactor.logDensity :70-80: the sampler's view of the
+// annealed density with its variable set to x.  Deliberately NOT inlined: the slice sampler calls it from
+// seven places; one shared copy keeps the kernel's code (and instruction-cache footprint, which dominated the
+// many-small-replicas kernel: ncu stall_no_instruction) small and gives the row loop its own registers.
+template <class Fam>
+struct LogDensityBase {
+  const DevEngine& E; Fam& fam; GroupReducer& red;
+  int k, aux; double beta;
+  unsigned long long& evals; int& err;
+  BPT_D double eval(double x) {
+    evals++;
+    const double fx = fam.fixed(k, x, aux);
+    if (beta == 0.0 || fx == BPT_NEG_INF) return fx;
+    double s; int c;
+    fam.annealed(k, x, aux, red, s, c);
+    double a = beta * s;
+    if (c) a += E.anneal_support ? c * annealed_minus_infinity(beta) : BPT_NEG_INF;
+    const double r = fx + a;
+    if (r != r) err |= ERR_NAN;   // ExponentiatedFactor.java:26-29
+    return r;
+  }
+};
+// inlined at every call site: best for the big-data kernels (the row loop keeps its operands in registers)
+template <class Fam>
+struct LogDensityInline : LogDensityBase<Fam> {
+  BPT_D double operator()(double x) { return this->eval(x); }
+};
+// one shared copy: best for the fused replica kernel, whose 8-32 warps run different parts of the sampler
+// at the same time (inlined: ncu stall_no_instruction = 12 warps per issue; outlined: 2x faster)
+template <class Fam>
+struct LogDensityCall : LogDensityBase<Fam> {
+  __device__ __noinline__ double operator()(double x) { return this->eval(x); }
+};
+
+// One chain's share of ParallelTempering.moveKernel for one scan: forward sample at beta = 0, else
+// floor(nPasses * S) sampler executions in the persistent shuffled order.  P / order are the chain's
+// parameter and sampler-order arrays (shared memory); every thread of the chain group runs this.
+template <class Fam, class Sync>
+BPT_D void explore_chain(const DevEngine& E, Fam& fam, GroupReducer& red, double* P, int* order, int& curpos, int S,
+                         int pos, double beta, uint32_t scan, uint32_t key1, int mode, unsigned long long& evals,
+                         unsigned long long& execs, int& err) {
+  const int tid = Sync::tid();
+  if (mode == MODE_FORWARD_INIT) {
+    Rng rng(E.key0, key1, P_INIT, (uint32_t)pos, 0u, 0u);
+    fam.forward(rng);
+  } else if (mode == MODE_EXPLORE) {
+    if (beta == 0.0 && E.use_prior) {
+      Rng rng(E.key0, key1, P_FORWARD, (uint32_t)pos, scan, 0u);
+      fam.forward(rng);
+    } else {
+      const int n_steps = (int)floor(E.n_passes * S);
+      for (int t = 0; t < n_steps; t++) {
+        Sync::sync();
+        if (curpos == -1) {   // Collections.shuffle(order, rnd); SampledModel.java:267-272
+          if (tid == 0) {
+            Rng sh(E.key0, key1, P_SHUFFLE, (uint32_t)pos, scan, (uint32_t)t);
+            for (int i = S; i > 1; i--) {
+              const int j = sh.next_int(i);
+              const int tmp = order[i - 1]; order[i - 1] = order[j]; order[j] = tmp;
+            }
+          }
+          Sync::sync();
+          curpos = S - 1;
+        }
+        const int k = order[curpos--];
+        Rng rng(E.key0, key1, P_MOVE, (uint32_t)pos, scan, (uint32_t)t);
+        int aux = 0;
+        typename Sync::template LogDensityOf<Fam> lp{{E, fam, red, k, aux, beta, evals, err}};
+        execs++;
+        if (fam.sampler_type(k) == S_REAL_SLICE) {
+          const double x0 = P[fam.sampler_var(k)];
+          const double xn = real_slice(lp, rng, x0, false, 0.0, 0.0, err);
+          fam.commit(k, xn, 0);
+        } else {   // SimplexSampler.xtend:21-28
+          const int K = fam.simplex_dim();
+          aux = rng.next_int(K);
+          lp.aux = aux;
+          const int base = fam.sampler_var(k);
+          const int nx = aux == K - 1 ? 0 : aux + 1;
+          const double x0 = P[base + aux];
+          const double sum = P[base + aux] + P[base + nx];
+          const double xn = real_slice(lp, rng, x0, true, 0.0, sum, err);
+          fam.commit(k, xn, aux);
+        }
+      }
+    }
+  }
+  Sync::sync();
+}
+
 template <class Fam>
 __global__ void __launch_bounds__(Fam::kThreads)
 explore_kernel(DevEngine E, typename Fam::Data D, int G, int mode) {
@@ -92,64 +198,7 @@ explore_kernel(DevEngine E, typename Fam::Data D, int G, int mode) {
   red.init(&rs, G, crank);
   unsigned long long evals = 0, execs = 0;
   int err = 0;
-
-  if (mode == MODE_FORWARD_INIT) {
-    Rng rng(E.key0, key1, P_INIT, (uint32_t)pos, 0u, 0u);
-    fam.forward(rng);
-  } else if (mode == MODE_EXPLORE) {
-    if (beta == 0.0 && E.use_prior) {
-      Rng rng(E.key0, key1, P_FORWARD, (uint32_t)pos, scan, 0u);
-      fam.forward(rng);
-    } else {
-      const int n_steps = (int)floor(E.n_passes * S);
-      for (int t = 0; t < n_steps; t++) {
-        __syncthreads();
-        if (curpos == -1) {   // Collections.shuffle(order, rnd); SampledModel.java:267-272
-          if (tid == 0) {
-            Rng sh(E.key0, key1, P_SHUFFLE, (uint32_t)pos, scan, (uint32_t)t);
-            for (int i = S; i > 1; i--) {
-              const int j = sh.next_int(i);
-              const int tmp = order[i - 1]; order[i - 1] = order[j]; order[j] = tmp;
-            }
-          }
-          __syncthreads();
-          curpos = S - 1;
-        }
-        const int k = order[curpos--];
-        Rng rng(E.key0, key1, P_MOVE, (uint32_t)pos, scan, (uint32_t)t);
-        int aux = 0;
-        // RealSliceSampler.logDensity :156-161 over ExponentiatedFactor.logDensity :70-80
-        auto lp = [&](double x) -> double {
-          evals++;
-          const double fx = fam.fixed(k, x, aux);
-          if (beta == 0.0 || fx == BPT_NEG_INF) return fx;
-          double s; int c;
-          fam.annealed(k, x, aux, red, s, c);
-          double a = beta * s;
-          if (c) a += E.anneal_support ? c * annealed_minus_infinity(beta) : BPT_NEG_INF;
-          const double r = fx + a;
-          if (r != r) err |= ERR_NAN;   // ExponentiatedFactor.java:26-29
-          return r;
-        };
-        execs++;
-        if (fam.sampler_type(k) == S_REAL_SLICE) {
-          const double x0 = P[fam.sampler_var(k)];
-          const double xn = real_slice(lp, rng, x0, false, 0.0, 0.0, err);
-          fam.commit(k, xn, 0);
-        } else {   // SimplexSampler.xtend:21-28
-          const int K = fam.simplex_dim();
-          aux = rng.next_int(K);
-          const int base = fam.sampler_var(k);
-          const int nx = aux == K - 1 ? 0 : aux + 1;
-          const double x0 = P[base + aux];
-          const double sum = P[base + aux] + P[base + nx];
-          const double xn = real_slice(lp, rng, x0, true, 0.0, sum, err);
-          fam.commit(k, xn, aux);
-        }
-      }
-    }
-  }
-  __syncthreads();
+  explore_chain<Fam, CtaSync>(E, fam, red, P, order, curpos, S, pos, beta, scan, key1, mode, evals, execs, err);
 
   double loglik, logprior; int noos;
   fam.full(red, loglik, noos, logprior);
@@ -180,8 +229,9 @@ BPT_D void summary_add(long long& n, double& m1, double& m2, double x) {
   m2 += ((double)n - 1.0) * dev * ndev;
 }
 
-__global__ void swap_kernel(DevEngine E, DevStats St, DevOut O) {
-  const int rep = blockIdx.x, N = E.N, tid = threadIdx.x;
+// energy accumulators + DEO swap pass + index process of one replica; called by every thread of a CTA
+BPT_D void swap_replica(const DevEngine& E, const DevStats& St, const DevOut& O, int rep) {
+  const int N = E.N, tid = threadIdx.x;
   const size_t base = (size_t)rep * N;
   const double* ladder = E.ladder + base;
   int* sop = E.slot_of_pos + base;
@@ -272,6 +322,61 @@ __global__ void swap_kernel(DevEngine E, DevStats St, DevOut O) {
     E.scan_counter[rep] = scan + 1;
     if (N > 1) E.swap_counter[rep] = swap_index + 1;
     E.batch_counter[rep] = b + 1;
+  }
+}
+
+__global__ void swap_kernel(DevEngine E, DevStats St, DevOut O) { swap_replica(E, St, O, blockIdx.x); }
+
+// Fused kernel for many small models (config C5: thousands of independent replicas, a few chains each):
+// one CTA per replica, one WARP per chain (reductions are shuffles only), and the whole scan loop --
+// explore, record, DEO swap, index process -- runs inside the kernel, so n_scans scans cost one launch and
+// the swap pass costs two block barriers instead of two kernel launches.
+template <class Fam>
+__global__ void __launch_bounds__(1024) replica_kernel(DevEngine E, DevStats St, DevOut O, typename Fam::Data D, int n_scans) {
+  __shared__ double Pall[32][8];
+  __shared__ int order_all[32][8];
+  const int rep = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int l = rep * E.N + warp;              // local slot == global slot (single-process path)
+  double* P = Pall[warp];
+  int* order = order_all[warp];
+  const int nR = Fam::n_reals(D), S = Fam::n_samplers(D);
+  const uint32_t key1 = E.key1 ^ (E.replica_offset + (uint32_t)rep);
+  Fam fam;
+  fam.init(D, l, P, 1, 0, E.err);
+  fam.set_lanes(lane, 32);
+  for (int v = lane; v < nR; v += 32) P[v] = E.reals[(size_t)v * E.M_local + l];
+  for (int k = lane; k < S; k += 32) order[k] = E.order[(size_t)l * E.s_max + k];
+  int curpos = E.curpos[l];
+  __syncwarp();
+  GroupReducer red;
+  red.init_warp();
+  unsigned long long evals_total = 0, execs = 0;
+  int err = 0;
+  for (int it = 0; it < n_scans; it++) {
+    const int pos = E.pos_of_slot[l];
+    const double beta = E.ladder[rep * E.N + pos];
+    const uint32_t scan = E.scan_counter[rep];
+    unsigned long long evals = 0;
+    explore_chain<Fam, WarpSync>(E, fam, red, P, order, curpos, S, pos, beta, scan, key1, MODE_EXPLORE, evals, execs, err);
+    double loglik, logprior; int noos;
+    fam.full(red, loglik, noos, logprior);
+    if (loglik != loglik || logprior != logprior) err |= ERR_NAN;
+    for (int v = lane; v < nR; v += 32) E.reals[(size_t)v * E.M_local + l] = P[v];
+    if (lane == 0) {
+      double* t = E.table + (size_t)l * 4;
+      t[0] = loglik; t[1] = (double)noos; t[2] = logprior; t[3] = (double)evals;
+    }
+    evals_total += evals;
+    __syncthreads();
+    swap_replica(E, St, O, rep);
+    __syncthreads();
+  }
+  for (int k = lane; k < S; k += 32) E.order[(size_t)l * E.s_max + k] = order[k];
+  if (lane == 0) {
+    E.curpos[l] = curpos;
+    E.evals[l] += evals_total;
+    E.execs[l] += execs;
+    if (err) atomicOr(E.err, err);
   }
 }
 

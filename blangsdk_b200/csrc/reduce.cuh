@@ -36,6 +36,8 @@ struct GroupReducer {
   BPT_D void init(ReduceSmem* s, int G_, int crank_) {
     sm = s; parity = 0; G = G_; crank = crank_; nwarps = (blockDim.x + 31) >> 5;
   }
+  // one chain per warp (fused small-model kernel): shuffles only, no shared memory, no barrier
+  BPT_D void init_warp() { sm = nullptr; parity = 0; G = 1; crank = 0; nwarps = 1; }
 
   // all threads of the group call this; on return s / c hold the group totals
   BPT_D void reduce(double& s, int& c) {

@@ -337,3 +337,50 @@ def test_logit_term_accuracy_and_support():
     assert np.array_equal(np.isinf(got[~lean]), np.isinf(naive[~lean]))   # same out-of-support rows
     assert np.max(np.abs(got[fin] - naive[fin]) / np.abs(naive[fin])) < 1e-12
     assert np.isinf(got[~lean]).sum() > 0
+
+
+@pytest.mark.parametrize("fam", ["betabinomial", "normal"])
+def test_fused_replica_kernel(oracle, datasets, fam, monkeypatch):
+    """many small replicas run in the fused kernel (one warp per chain, scan loop + swaps inside one launch)
+    and must still reproduce the oracle replica by replica; the unfused path must give the same bits"""
+    from blangsdk_b200.engine import Engine
+    R, N, S = 12, 6, 25
+    if fam == "betabinomial":
+        spec = datasets.beta_binomial_batch(R)
+        one = lambda r: datasets.beta_binomial(r)
+    else:
+        spec = datasets.normal_meanvar(n=333)
+        one = lambda r: spec
+    outs = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("BLANGPT_FUSED", fused)
+        eng = Engine(nChains=N, nReplicas=R, random=19)
+        eng.set_model(spec)
+        eng.initialize("FORWARD")
+        launches0 = eng.counters()["launches"]
+        outs[fused] = eng.run_scans(S, want=("energy", "swapIndicators", "samples", "logDensity"))
+        outs[fused]["launches"] = eng.counters()["launches"] - launches0
+        outs[fused]["evals"] = eng.counters()["evals"]
+        outs[fused]["stats"] = eng.round_stats()
+        eng.close()
+    assert outs["1"]["launches"] == 1 and outs["0"]["launches"] == 2 * S
+    for k in ("energy", "swapIndicators", "samples", "logDensity"):
+        if fam == "betabinomial":     # same 32-lane reduction tree in both kernels: identical bits
+            assert np.array_equal(outs["1"][k], outs["0"][k]), k
+        else:                          # 32 lanes vs 128 threads: summation order differs
+            assert rel(outs["1"][k], outs["0"][k]) < TOL, k
+    assert np.array_equal(outs["1"]["swapIndicators"], outs["0"]["swapIndicators"])
+    assert outs["1"]["evals"] == outs["0"]["evals"]
+    assert np.array_equal(outs["1"]["stats"]["roundTrips"], outs["0"]["stats"]["roundTrips"])
+    out = outs["1"]
+    total = 0
+    for r in range(R):
+        ref = oracle.PT(oracle.Model(one(r)), nChains=N, seed=19, replica=r)
+        ref.initialize()
+        for s in range(S):
+            e, ind = ref.scan()
+            assert np.array_equal(out["swapIndicators"][s, r], ind)
+            assert rel(out["energy"][s, r], e) < TOL
+        total += ref.n_evals()
+        assert rel(out["stats"]["swapAcceptMean"][r], ref.round_stats()["swap_accept_mean"]) < TOL
+    assert total == out["evals"]
