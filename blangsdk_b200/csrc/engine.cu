@@ -440,7 +440,9 @@ extern "C" int blangpt_set_ladder(blangpt_handle* h, const double* betas, int64_
     const double* src = betas + (n == N ? 0 : (size_t)r * N);
     std::vector<double> v(src, src + N);
     std::sort(v.begin(), v.end(), [](double a, double b) { return a > b; });
-    if (v[0] != 1.0) FAIL(h, BLANGPT_EINVAL, "the ladder must start at exactly 1.0 (ParallelTempering.java:191-192)");
+    // a lone chain may sit at any exponent (SampledModel.setExponent, as factories/Pigeons.java:56-64 uses it)
+    if (v[0] != 1.0 && N > 1) FAIL(h, BLANGPT_EINVAL, "the ladder must start at exactly 1.0 (ParallelTempering.java:191-192)");
+    if (N == 1 && !(v[0] >= 0.0 && v[0] <= 1.0)) FAIL(h, BLANGPT_EINVAL, "the exponent must be in [0,1]");
     std::copy(v.begin(), v.end(), h->ladder.begin() + (size_t)r * N);
   }
   CUDA_OK(h, cudaMemcpyAsync((void*)h->E.ladder, h->ladder.data(), h->ladder.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -703,6 +705,67 @@ extern "C" int blangpt_rounds(int32_t nScans, double f, int32_t* rn, int32_t* ra
   if (r.size() > 64) return -1;
   for (size_t i = 0; i < r.size(); i++) { rn[i] = r[i].n_scans; ra[i] = r[i].is_adapt ? 1 : 0; }
   return (int)r.size();
+}
+
+extern "C" int blangpt_make_ladder(int32_t kind, int32_t nChains, double param, const double* user, int32_t n_user,
+                                   int32_t allowSplineGeneralization, double* out) {
+  if (!out) return BLANGPT_EINVAL;
+  std::vector<double> l = make_ladder(kind, nChains, param, user, n_user, allowSplineGeneralization != 0);
+  if ((int)l.size() != nChains) return BLANGPT_EINVAL;
+  std::copy(l.begin(), l.end(), out);
+  return BLANGPT_OK;
+}
+
+// PT.reportParallelTemperingDiagnostics (PT.java:387-505) + reportLambdaFunctions (:192-210) for one replica
+extern "C" int blangpt_get_diagnostics(blangpt_handle* h, int64_t replica, blangpt_diagnostics* d) {
+  if (!h || !d) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  const int N = h->cfg.nChains, R = h->cfg.nReplicas; const int64_t M = h->M_total;
+  if (replica < 0 || replica >= R) FAIL(h, BLANGPT_EINVAL, "replica out of range");
+  if (N < 2) FAIL(h, BLANGPT_EINVAL, "PT diagnostics need at least two chains (PT.java:102)");
+  std::vector<double> acc(M), emean(M), evar(M), ecov(M), Lam(R), lz(R), lzt(R); std::vector<int64_t> rt(R);
+  blangpt_round_stats st{};
+  st.swapAcceptMean = acc.data(); st.energyVariance = evar.data(); st.energyCovariance = ecov.data(); st.energyMean = emean.data();
+  st.Lambda = Lam.data(); st.logZSteppingStone = lz.data(); st.logZThermodynamic = lzt.data(); st.roundTrips = rt.data();
+  int rc = blangpt_get_round_stats(h, &st);
+  if (rc) return rc;
+  const size_t base = (size_t)replica * N;
+  double lowest = INFINITY, sum = 0.0, ineff = 0.0;
+  for (int i = 0; i < N - 1; i++) { const double a = acc[base + i]; lowest = std::min(lowest, a); sum += a; ineff += (1.0 - a) / a; }
+  d->nScansInRound = st.nScansInRound;
+  d->swapLowest = lowest; d->swapAverage = sum / (N - 1);
+  double csum = 0.0, cmax = -INFINITY;
+  for (int c = 0; c < N; c++) {   // :400-417 energy before/after correlation, clamped to [-1,1]
+    double corr = ecov[base + c] / evar[base + c];
+    if (corr < -1) corr = -1;
+    if (corr > 1) corr = 1;
+    csum += corr; if (corr > cmax || cmax != cmax) cmax = corr;
+  }
+  d->energyCorrelationAverage = csum / N; d->energyCorrelationHighest = cmax;
+  d->Lambda = Lam[replica];
+  d->inefficiency = ineff;
+  d->timeToFirstRestart = 2.0 * N * (1.0 + ineff);
+  d->effectiveNScans = std::max(0.0, (double)st.nScansInRound - d->timeToFirstRestart);
+  const double corrected = d->effectiveNScans == 0 ? (double)st.nScansInRound : d->effectiveNScans;
+  d->temperedRestarts = rt[replica];
+  d->temperedRestartRate = (double)rt[replica] / corrected;
+  d->asymptoticRoundTripRate = 1.0 / (2.0 + 2.0 * d->Lambda);
+  d->asymptoticRoundTripCount = d->asymptoticRoundTripRate * corrected;
+  d->nonAsymptoticRoundTripRate = 1.0 / (2.0 + 2.0 * ineff);
+  d->nonAsymptoticRoundTripCount = d->nonAsymptoticRoundTripRate * corrected;
+  d->logNormalizationSteppingStone = lz[replica];
+  d->logNormalizationThermodynamic = lzt[replica];
+  // cumulative Lambda(beta) and its derivative on the 99-point grid of reportLambdaFunctions
+  std::vector<double> desc(h->ladder.begin() + base, h->ladder.begin() + base + N);
+  std::vector<double> asc(desc.rbegin(), desc.rend());
+  std::vector<double> accv(acc.begin() + base, acc.begin() + base + N - 1);
+  MonotoneSpline cum = cumulative_lambda_spline(asc, intensities_ascending(accv));
+  for (int i = 1; i < 100; i++) {
+    const double beta = (double)i / 100.0;
+    d->cumulativeLambda[i - 1] = cum(beta);
+    d->lambdaInstantaneous[i - 1] = cum.derivative(beta);
+  }
+  return BLANGPT_OK;
 }
 
 extern "C" int blangpt_perform_inference(blangpt_handle* h, int32_t nScans, double adaptFraction, int32_t thinning,

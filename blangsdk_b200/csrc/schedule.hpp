@@ -67,31 +67,59 @@ struct MonotoneSpline {
     return (y[i] * (1 + 2 * t) + h * m[i] * t) * (1 - t) * (1 - t) +
            (y[i + 1] * (3 - 2 * t) + h * m[i + 1] * (t - 1)) * t * t;
   }
+  // d/dx of the interpolant (R/engines/internals/SplineDerivatives.xtend:10-32): 0 outside the knots
+  double derivative(double at) const {
+    const int n = (int)x.size();
+    if (std::isnan(at)) return at;
+    if (at <= x[0] || at >= x[n - 1]) return 0.0;
+    int i = 0;
+    while (at >= x[i + 1]) i += 1;
+    const double h = x[i + 1] - x[i];
+    const double t = (at - x[i]) / h, dt = 1.0 / h;
+    // y_i (1+2t)(1-t)^2 + h m_i t (1-t)^2 + y_{i+1} (3-2t) t^2 + h m_{i+1} (t-1) t^2
+    const double a = y[i] * (2 * (1 - t) * (1 - t) - 2 * (1 + 2 * t) * (1 - t));
+    const double b = h * m[i] * ((1 - t) * (1 - t) - 2 * t * (1 - t));
+    const double c = y[i + 1] * (-2 * t * t + 2 * t * (3 - 2 * t));
+    const double d = h * m[i + 1] * (t * t + 2 * t * (t - 1));
+    return (a + b + c + d) * dt;
+  }
 };
 
-// betas_desc[n] (position order) and mean swap acceptance per pair [n-1] (position order)
-// -> new descending ladder; cum_x / cum_y receive the cumulative-Lambda knots (ascending beta).
-inline std::vector<double> adapt_ladder(const std::vector<double>& betas_desc, const std::vector<double>& accept,
-                                        std::vector<double>* cum_x, std::vector<double>* cum_y) {
-  const int n = (int)betas_desc.size();
-  std::vector<double> asc(betas_desc.rbegin(), betas_desc.rend());
-  std::vector<double> intens(n - 1);
-  for (int i = 0; i < n - 1; i++) {
-    double a = accept[i];
-    if (a == 1.0) a = 0.99999; else if (!std::isfinite(a)) a = 0.0;   // PT.java:152
-    intens[n - 2 - i] = 1.0 - a;                                       // reversed to ascending beta
+// EngineStaticUtils.acceptProbabilitiesToIntensities :95-105 with PT.adapt's clamps (PT.java:152), reversed
+// to ascending beta
+inline std::vector<double> intensities_ascending(const std::vector<double>& accept_by_position) {
+  const int m = (int)accept_by_position.size();
+  std::vector<double> out(m);
+  for (int i = 0; i < m; i++) {
+    double a = accept_by_position[i];
+    if (a == 1.0) a = 0.99999; else if (!std::isfinite(a)) a = 0.0;
+    out[m - 1 - i] = 1.0 - a;
   }
-  auto cumulative = [&](double nudge) {
-    std::vector<double> ys(n, 0.0);
-    for (int i = 1; i < n; i++) ys[i] = ys[i - 1] + intens[i - 1] + nudge;
-    return ys;
-  };
-  if (cum_x) *cum_x = asc;
-  if (cum_y) *cum_y = cumulative(0.0);
+  return out;
+}
+
+// paddedCumulative :86-93
+inline std::vector<double> padded_cumulative(const std::vector<double>& intens, double nudge) {
+  std::vector<double> ys(intens.size() + 1, 0.0);
+  for (size_t i = 1; i < ys.size(); i++) ys[i] = ys[i - 1] + intens[i - 1] + nudge;
+  return ys;
+}
+
+// estimateCumulativeLambdaFromIntensities :112-117: spline through (beta_k, Lambda_k)
+inline MonotoneSpline cumulative_lambda_spline(const std::vector<double>& betas_asc, const std::vector<double>& intens) {
+  return MonotoneSpline(betas_asc, padded_cumulative(intens, 0.0));
+}
+
+// estimateScheduleGeneratorFromIntensities :119-155 + fixedSizeOptimalPartitionFromScheduleGenerator :157-168:
+// spline through (Lambda_k / Lambda_N, beta_k), evaluated at n_out equally spaced points, ends pinned to 0 and 1.
+// Zero-width steps: retry once with a 1e-6 nudge (:144-151).  Returns the ladder in ASCENDING order.
+inline std::vector<double> partition_from_intensities(const std::vector<double>& betas_asc, const std::vector<double>& intens,
+                                                      int n_out) {
+  const int n = (int)betas_asc.size();
   std::vector<double> ys;
   double nudge = 0.0;
-  for (int attempt = 0; attempt < 2; attempt++) {   // zero-width steps: retry once with a 1e-6 nudge (:144-151)
-    ys = cumulative(nudge);
+  for (int attempt = 0; attempt < 2; attempt++) {
+    ys = padded_cumulative(intens, nudge);
     const double norm = ys[n - 1];
     bool retry = false;
     for (int i = 0; i < n; i++) {
@@ -101,14 +129,66 @@ inline std::vector<double> adapt_ladder(const std::vector<double>& betas_desc, c
     if (!retry) break;
     nudge = 1e-6;
   }
-  MonotoneSpline generator(ys, asc);   // schedule generator: normalised cumulative Lambda -> beta
-  std::vector<double> out_asc(n);
-  out_asc[0] = 0.0;
-  for (int i = 1; i < n - 1; i++) out_asc[i] = generator(i / (n - 1.0));
-  out_asc[n - 1] = 1.0;
+  MonotoneSpline generator(ys, betas_asc);
+  std::vector<double> out(n_out);
+  out[0] = 0.0;
+  for (int i = 1; i < n_out - 1; i++) out[i] = generator(i / (n_out - 1.0));
+  out[n_out - 1] = 1.0;
+  return out;
+}
+
+// PT.adapt (PT.java:148-171, non-targetAccept branch): betas_desc[n] (position order) and mean swap acceptance per
+// pair [n-1] (position order) -> new descending ladder; cum_x / cum_y receive the cumulative-Lambda knots.
+inline std::vector<double> adapt_ladder(const std::vector<double>& betas_desc, const std::vector<double>& accept,
+                                        std::vector<double>* cum_x, std::vector<double>* cum_y) {
+  const int n = (int)betas_desc.size();
+  std::vector<double> asc(betas_desc.rbegin(), betas_desc.rend());
+  const std::vector<double> intens = intensities_ascending(accept);
+  if (cum_x) *cum_x = asc;
+  if (cum_y) *cum_y = padded_cumulative(intens, 0.0);
+  std::vector<double> out_asc = partition_from_intensities(asc, intens, n);
   std::vector<double> desc(out_asc.rbegin(), out_asc.rend());
   std::sort(desc.begin(), desc.end(), [](double a, double b) { return a > b; });
   return desc;
+}
+
+// ---- initial ladders (R/engines/internals/ladders/*.java) --------------------------------------------------
+enum LadderKind { LADDER_EQUALLY_SPACED = 0, LADDER_GEOMETRIC = 1, LADDER_POLYNOMIAL = 2, LADDER_USER_SPECIFIED = 3 };
+
+// returns an empty vector on the conditions under which the reference throws
+inline std::vector<double> make_ladder(int kind, int n_chains, double param, const double* user, int n_user,
+                                       bool allow_spline_generalization) {
+  std::vector<double> out;
+  if (n_chains < 1) return out;
+  switch (kind) {
+    case LADDER_EQUALLY_SPACED: return equally_spaced(n_chains);
+    case LADDER_GEOMETRIC:                                   // Geometric.java:17-33, annealingScaling default 0.8
+      if (param < 0.0 || param >= 1.0) return out;
+      if (n_chains == 1) { out.push_back(1.0); return out; }
+      for (int i = 0; i < n_chains - 1; i++) out.push_back(std::pow(param, i));
+      out.push_back(0.0);
+      return out;
+    case LADDER_POLYNOMIAL:                                  // Polynomial.java:17-31, power default 3
+      if (param < 1.0) return out;
+      if (n_chains == 1) { out.push_back(1.0); return out; }
+      for (int i = 0; i < n_chains; i++) out.push_back(std::pow(1.0 - (double)i / ((double)n_chains - 1.0), param));
+      return out;
+    case LADDER_USER_SPECIFIED: {                            // UserSpecified.java:24-83
+      if (!user || n_user < 1) return out;
+      std::vector<double> sorted(user, user + n_user);
+      std::sort(sorted.begin(), sorted.end(), [](double a, double b) { return a > b; });
+      if (n_user == n_chains) { if (sorted[0] != 1.0) return std::vector<double>(); return sorted; }
+      if (!allow_spline_generalization) return out;
+      if (n_chains == 1) { out.push_back(1.0); return out; }
+      if (sorted[0] != 1.0 || sorted[n_user - 1] != 0.0 || n_user < 2) return out;
+      std::vector<double> asc(sorted.rbegin(), sorted.rend());
+      std::vector<double> uniform(n_user - 1, 0.5);
+      std::vector<double> res = partition_from_intensities(asc, uniform, n_chains);
+      std::sort(res.begin(), res.end(), [](double a, double b) { return a > b; });
+      return res;
+    }
+  }
+  return out;
 }
 
 }  // namespace bpt

@@ -57,6 +57,17 @@ class RoundStats(C.Structure):
                 ("roundTrips", _lp), ("Lambda", _dp), ("logZSteppingStone", _dp), ("logZThermodynamic", _dp)]
 
 
+class Diagnostics(C.Structure):
+    _fields_ = [("nScansInRound", C.c_int64), ("swapLowest", C.c_double), ("swapAverage", C.c_double),
+                ("energyCorrelationAverage", C.c_double), ("energyCorrelationHighest", C.c_double),
+                ("Lambda", C.c_double), ("inefficiency", C.c_double), ("timeToFirstRestart", C.c_double),
+                ("effectiveNScans", C.c_double), ("temperedRestarts", C.c_int64), ("temperedRestartRate", C.c_double),
+                ("asymptoticRoundTripCount", C.c_double), ("asymptoticRoundTripRate", C.c_double),
+                ("nonAsymptoticRoundTripCount", C.c_double), ("nonAsymptoticRoundTripRate", C.c_double),
+                ("logNormalizationSteppingStone", C.c_double), ("logNormalizationThermodynamic", C.c_double),
+                ("cumulativeLambda", C.c_double * 99), ("lambdaInstantaneous", C.c_double * 99)]
+
+
 class InferenceSummary(C.Structure):
     _fields_ = [("nRounds", C.c_int32), ("roundNScans", C.c_int32 * 64), ("roundIsAdapt", C.c_int32 * 64),
                 ("Lambda", _dp), ("logZ", _dp), ("roundTrips", _lp), ("minAccept", _dp), ("meanAccept", _dp),
@@ -70,7 +81,7 @@ EXPORTS = [
     "blangpt_get_round_stats", "blangpt_adapt", "blangpt_reset_round", "blangpt_rounds",
     "blangpt_perform_inference", "blangpt_counters", "blangpt_set_stream", "blangpt_evaluate", "blangpt_prime",
     "blangpt_explore", "blangpt_table_ptr", "blangpt_local_chains", "blangpt_swap", "blangpt_synchronize",
-    "blangpt_microbench", "blangpt_debug_logit_terms",
+    "blangpt_microbench", "blangpt_debug_logit_terms", "blangpt_make_ladder", "blangpt_get_diagnostics",
 ]
 
 _LIB = None
@@ -119,6 +130,8 @@ def load_library():
     L.blangpt_swap.argtypes = [vp, C.POINTER(ScanOutputs)]
     L.blangpt_microbench.argtypes = [C.c_int32, C.c_int32, _dp]
     L.blangpt_debug_logit_terms.argtypes = [C.c_int32, _dp, _ip, C.c_int64, _dp]
+    L.blangpt_make_ladder.argtypes = [C.c_int32, C.c_int32, C.c_double, _dp, C.c_int32, C.c_int32, _dp]
+    L.blangpt_get_diagnostics.argtypes = [vp, C.c_int64, C.POINTER(Diagnostics)]
     _LIB = L
     return L
 
@@ -130,6 +143,35 @@ def microbench(which, device=0):
     if rc != 0:
         raise BlangPTError("microbench failed (no GPU?)")
     return out.value
+
+
+LADDERS = {"EquallySpaced": 0, "Geometric": 1, "Polynomial": 2, "UserSpecified": 3}
+
+
+def make_ladder(kind, nChains, param=None, annealingParameters=None, allowSplineGeneralization=False):
+    """Initial ladders of R/engines/internals/ladders (EquallySpaced, Geometric(annealingScaling=0.8),
+    Polynomial(power=3), UserSpecified(annealingParameters, allowSplineGeneralization)); descending."""
+    if param is None:
+        param = {"Geometric": 0.8, "Polynomial": 3.0}.get(kind, 0.0)
+    user = None if annealingParameters is None else np.ascontiguousarray(annealingParameters, dtype=np.float64)
+    out = np.zeros(max(1, nChains))
+    rc = load_library().blangpt_make_ladder(LADDERS[kind], nChains, float(param), _d(user),
+                                            0 if user is None else user.size, int(allowSplineGeneralization), _d(out))
+    if rc != 0:
+        raise BlangPTError("invalid ladder specification (%s, nChains=%d)" % (kind, nChains))
+    return out[:nChains]
+
+
+def ladder_from_another_exec(annealing_parameters_csv, nChains, allowSplineGeneralization=False):
+    """ladders/FromAnotherExec.java:27-40: the final (isAdapt == false) round's schedule of an earlier run."""
+    import csv
+    parsed = [0.0]
+    with open(annealing_parameters_csv) as f:
+        for row in csv.DictReader(f):
+            if row["isAdapt"] == "false":
+                parsed.append(float(row["value"]))
+    return make_ladder("UserSpecified", nChains, annealingParameters=parsed,
+                       allowSplineGeneralization=allowSplineGeneralization)
 
 
 def debug_logit_terms(z, y, device=0):
@@ -307,6 +349,15 @@ class Engine:
         out.update(per, logSumN=lsn[:, :N - 1], roundTrips=rt, nScansInRound=int(st.nScansInRound))
         return out
 
+    def diagnostics(self, replica=0):
+        """PT.reportParallelTemperingDiagnostics + reportLambdaFunctions for the current round."""
+        d = Diagnostics()
+        self._check(self.L.blangpt_get_diagnostics(self.h, replica, C.byref(d)))
+        out = {k: getattr(d, k) for k, _ in Diagnostics._fields_ if k not in ("cumulativeLambda", "lambdaInstantaneous")}
+        out["cumulativeLambda"] = np.array(d.cumulativeLambda)
+        out["lambdaInstantaneous"] = np.array(d.lambdaInstantaneous)
+        return out
+
     def adapt(self):
         knots = np.zeros((self.R, 2, self.N))
         self._check(self.L.blangpt_adapt(self.h, _d(knots)))
@@ -368,16 +419,44 @@ class PT:
 
     def setSampledModel(self, spec):
         """PT.setSampledModel (PT.java:270-281): lower the model, ladder, informed initialisation."""
+        self._spec = spec
         self.engine.set_model(spec)
         if not isinstance(self.ladder, str):
             self.engine.set_ladder(self.ladder)
         elif self.ladder != "EquallySpaced":
-            raise BlangPTError("only the EquallySpaced ladder or an explicit list is built in")
+            self.engine.set_ladder(make_ladder(self.ladder, self.nChains))
         self.engine.initialize(self.initialization)
 
-    def performInference(self, want=("energy", "swapIndicators", "samples")):
-        res = self.engine.perform_inference(self.nScans, self.adaptFraction, self.thinning, want)
-        res["finalStats"] = self.engine.round_stats()
-        res["ladder"] = self.engine.get_ladder()
-        res["counters"] = self.engine.counters()
-        return res
+    def performInference(self, want=("energy", "swapIndicators", "samples"), results=None):
+        """PT.performInference (PT.java:85-113).  With `results` (a folder) the reference's samples/ and
+        monitoring/ tables are written there, one batched write per round (blangsdk_b200/results.py)."""
+        if results is None:
+            res = self.engine.perform_inference(self.nScans, self.adaptFraction, self.thinning, want)
+            res["finalStats"] = self.engine.round_stats()
+            res["ladder"] = self.engine.get_ladder()
+            res["counters"] = self.engine.counters()
+            return res
+        import time
+        from .results import PTResultsWriter
+        eng = self.engine
+        if eng.R != 1:
+            raise BlangPTError("result tables are written for one replica at a time")
+        w = PTResultsWriter(results, eng.family, eng.N, self._spec["hyper"], thinning=self.thinning,
+                            logNormalizationEstimator=self.logNormalizationEstimator)
+        rs = rounds(self.nScans, self.adaptFraction if eng.N > 1 else 0.0)
+        scan, summary = 0, []
+        full = ("energy", "logDensity", "nOutOfSupport", "swapIndicators", "samples")
+        for r, (n, is_adapt) in enumerate(rs):
+            t0 = time.perf_counter()
+            out = eng.run_scans(n, want=full)
+            w.write_scans(scan, out)
+            scan += n
+            millis = 1e3 * (time.perf_counter() - t0)
+            if eng.N > 1:
+                stats, diag = eng.round_stats(), eng.diagnostics()
+                w.write_round(r, is_adapt, n, eng.get_ladder()[0], stats, diag, eng.n_samplers, self.nPassesPerScan, millis)
+                summary.append(dict(nScans=n, isAdapt=is_adapt, **{k: v for k, v in diag.items() if np.isscalar(v)}))
+                if r + 1 < len(rs):
+                    eng.adapt()
+        w.close()
+        return dict(rounds=summary, ladder=eng.get_ladder(), counters=eng.counters(), finalStats=eng.round_stats())

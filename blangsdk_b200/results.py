@@ -1,0 +1,249 @@
+"""Output tables in the reference's on-disk format.
+
+The reference's PT engine writes tidy CSV tables every scan through `ExperimentResults.getTabularWriter`
+(R/engines/internals/factories/PT.java:116-143,173-229,360-385,387-505,517-537; format:
+R/runtime/internals/doc/contents/InputOutput.xtend:185-240).  Here they are written once per ROUND from the
+batched device->host outputs of `blangpt_run_scans`, same folders, file names and columns, so that the
+reference's consumers (DefaultPostProcessor, ptanalysis/Paths, ladders/FromAnotherExec, user scripts) read them
+unchanged:
+
+  samples/     energy, allLogDensities, nOutOfSupport (sample,chain,value); logDensity (sample,value);
+               one table per latent variable of the family (index_0,sample,value / sample,value)
+  monitoring/  swapIndicators (sample,chain,value); swapStatistics, annealingParameters (isAdapt,round,chain,value);
+               swapSummaries (round,lowest,average); energyExplCorrelation (round,chain,beta,isAdapt,value);
+               energyExplCorrelationSummaries (round,average,highest); globalLambda (round,value);
+               timeToFirstRestart (round,time,effectiveNScans); actualTemperedRestarts, asymptoticRoundTripBound,
+               nonAsymptoticRountTrip [sic] (round,count,rate); logNormalizationConstantProgress (round,value);
+               cumulativeLambda, lambdaInstantaneous (round,isAdapt,beta,value);
+               roundTimings (round,isAdapt,nExplorationSteps,value); runningTimeSummary.tsv
+  logNormalizationEstimate.csv (estimator,value)
+"""
+import os
+
+import numpy as np
+
+# latent variables of each catalogue family as a Blang model would name and shape them
+VARIABLES = {
+    "normal": [("mu", None, 0, 1), ("sigma2", None, 1, 1)],
+    "logistic": [("coefficients", "index_0", 0, None)],
+    "mixture": [("means", "index_0", 0, "K"), ("variances", "index_0", "K", "K"), ("pi", "entry", "2K", "K")],
+    "betabinomial": [("alpha", None, 0, 1), ("beta", None, 1, 1)],
+    "ising": [("vertices", "index_0", 0, None)],
+}
+
+
+def _fmt(v):
+    if isinstance(v, (bool, np.bool_)):
+        return "true" if v else "false"
+    if isinstance(v, (int, np.integer)):
+        return str(int(v))
+    if isinstance(v, (float, np.floating)):
+        if np.isnan(v):
+            return "NaN"
+        if np.isinf(v):
+            return "Infinity" if v > 0 else "-Infinity"
+        return repr(float(v))
+    return str(v)
+
+
+class TabularWriter:
+    """One tidy CSV: the header is fixed by the first write (blang.inits TabularWriter behaviour)."""
+
+    def __init__(self, path):
+        self.path = path
+        self.columns = None
+        self.f = None
+
+    def write(self, *pairs):
+        cols = [k for k, _ in pairs]
+        if self.f is None:
+            os.makedirs(os.path.dirname(self.path), exist_ok=True)
+            self.f = open(self.path, "w")
+            self.columns = cols
+            self.f.write(",".join(cols) + "\n")
+        elif cols != self.columns:
+            raise ValueError("columns changed in %s: %s vs %s" % (self.path, cols, self.columns))
+        self.f.write(",".join(_fmt(v) for _, v in pairs) + "\n")
+
+    def write_block(self, columns, arrays):
+        """vectorised: arrays are equally long 1-D arrays, one per column"""
+        if self.f is None:
+            os.makedirs(os.path.dirname(self.path), exist_ok=True)
+            self.f = open(self.path, "w")
+            self.columns = list(columns)
+            self.f.write(",".join(columns) + "\n")
+        elif list(columns) != self.columns:
+            raise ValueError("columns changed in %s" % self.path)
+        rows = zip(*[[_fmt(x) for x in a] for a in arrays])
+        self.f.write("".join(",".join(r) + "\n" for r in rows))
+
+    def close(self):
+        if self.f is not None:
+            self.f.close()
+            self.f = None
+
+
+class ExperimentResults:
+    """results folder with lazily created tabular writers (blang.inits ExperimentResults)."""
+
+    def __init__(self, folder):
+        self.folder = folder
+        os.makedirs(folder, exist_ok=True)
+        self.writers = {}
+
+    def writer(self, sub, name):
+        key = (sub, name)
+        if key not in self.writers:
+            base = os.path.join(self.folder, sub) if sub else self.folder
+            self.writers[key] = TabularWriter(os.path.join(base, name + ".csv"))
+        return self.writers[key]
+
+    def flush_all(self):
+        for w in self.writers.values():
+            if w.f is not None:
+                w.f.flush()
+
+    def close_all(self):
+        for w in self.writers.values():
+            w.close()
+
+
+class PTResultsWriter:
+    """Writes what PT.performInference writes, one round at a time."""
+
+    def __init__(self, folder, family, n_chains, hyper=None, statisticRecordedMaxChainIndex=100, thinning=1,
+                 logNormalizationEstimator="steppingStone"):
+        self.results = ExperimentResults(folder)
+        self.family, self.N = family, n_chains
+        self.max_idx = statisticRecordedMaxChainIndex
+        self.thinning = thinning
+        self.estimator = logNormalizationEstimator
+        self.K = int(hyper["K"]) if hyper and "K" in hyper else None
+
+    def _resolve(self, v, n_reals):
+        if v is None:
+            return n_reals
+        if isinstance(v, str):
+            return {"K": self.K, "2K": 2 * self.K}[v]
+        return v
+
+    # ---- per-scan tables (PT.java:116-143, 360-385), written per round from the batched outputs ----
+    def write_scans(self, first_scan, out):
+        n = out["energy"].shape[0]
+        N = self.N
+        m = min(N, self.max_idx)
+        scans = np.arange(first_scan, first_scan + n)
+        samp = np.repeat(scans, m)
+        chain = np.tile(np.arange(m), n)
+        S = self.results.writer
+        if "logDensity" in out:
+            S("samples", "allLogDensities").write_block(["sample", "chain", "value"], [samp, chain, out["logDensity"][:, 0, :m].ravel()])
+        S("samples", "energy").write_block(["sample", "chain", "value"], [samp, chain, out["energy"][:, 0, :m].ravel()])
+        if "nOutOfSupport" in out:
+            S("samples", "nOutOfSupport").write_block(["sample", "chain", "value"], [samp, chain, out["nOutOfSupport"][:, 0, :m].ravel()])
+        if "logDensity" in out and self.max_idx >= 0:
+            S("samples", "logDensity").write_block(["sample", "value"], [scans, out["logDensity"][:, 0, 0]])
+        keep = (scans % self.thinning) == 0
+        if "samples" in out or "intSamples" in out:
+            vals = out["samples"][:, 0, :] if "samples" in out else out["intSamples"][:, 0, :]
+            n_reals = vals.shape[1]
+            for name, index_col, start, count in VARIABLES[self.family]:
+                a = self._resolve(start, n_reals)
+                c = self._resolve(count, n_reals) if count is not None else n_reals - a
+                block = vals[keep, a:a + c]
+                ks = scans[keep]
+                if index_col is None:
+                    S("samples", name).write_block(["sample", "value"], [ks, block[:, 0]])
+                else:
+                    S("samples", name).write_block([index_col, "sample", "value"],
+                                                   [np.tile(np.arange(c), len(ks)), np.repeat(ks, c), block.ravel()])
+        if N > 1 and "swapIndicators" in out:
+            S("monitoring", "swapIndicators").write_block(
+                ["sample", "chain", "value"], [np.repeat(scans, N), np.tile(np.arange(N), n), out["swapIndicators"][:, 0, :].ravel()])
+
+    # ---- per-round tables (PT.java:173-229, 387-505) ----
+    def write_round(self, round_index, is_adapt, n_scans, ladder_desc, stats, diag, n_samplers, n_passes, millis):
+        W = lambda name: self.results.writer("monitoring", name)
+        N = self.N
+        acc = stats["swapAcceptMean"][0]
+        for i in range(N - 1):   # reportAcceptanceRatios :173-190
+            W("swapStatistics").write(("isAdapt", is_adapt), ("round", round_index), ("chain", i), ("value", acc[i]))
+            W("annealingParameters").write(("isAdapt", is_adapt), ("round", round_index), ("chain", i), ("value", ladder_desc[i]))
+        W("swapSummaries").write(("round", round_index), ("lowest", diag["swapLowest"]), ("average", diag["swapAverage"]))
+        var, cov = stats["energyVariance"][0], stats["energyCovariance"][0]
+        for c in range(N):       # :400-417
+            with np.errstate(divide="ignore", invalid="ignore"):
+                corr = float(np.clip(cov[c] / var[c], -1.0, 1.0)) if var[c] == var[c] else float("nan")
+            W("energyExplCorrelation").write(("round", round_index), ("chain", c), ("beta", ladder_desc[c]),
+                                             ("isAdapt", is_adapt), ("value", corr))
+        W("energyExplCorrelationSummaries").write(("round", round_index), ("average", diag["energyCorrelationAverage"]),
+                                                  ("highest", diag["energyCorrelationHighest"]))
+        W("globalLambda").write(("round", round_index), ("value", diag["Lambda"]))
+        W("timeToFirstRestart").write(("round", round_index), ("time", diag["timeToFirstRestart"]),
+                                      ("effectiveNScans", diag["effectiveNScans"]))
+        W("actualTemperedRestarts").write(("round", round_index), ("count", diag["temperedRestarts"]),
+                                          ("rate", diag["temperedRestartRate"]))
+        W("asymptoticRoundTripBound").write(("round", round_index), ("count", diag["asymptoticRoundTripCount"]),
+                                            ("rate", diag["asymptoticRoundTripRate"]))
+        W("nonAsymptoticRountTrip").write(("round", round_index), ("count", diag["nonAsymptoticRoundTripCount"]),
+                                          ("rate", diag["nonAsymptoticRoundTripRate"]))
+        logz = diag["logNormalizationSteppingStone"] if self.estimator == "steppingStone" else diag["logNormalizationThermodynamic"]
+        if logz == logz:
+            W("logNormalizationConstantProgress").write(("round", round_index), ("value", logz))
+            if not is_adapt:     # :497-504 final estimate in the SCM format
+                w = self.results.writer("", "logNormalizationEstimate")
+                w.write(("estimator", self.estimator), ("value", logz))
+        for i in range(1, 100):  # reportLambdaFunctions :192-210
+            beta = i / 100.0
+            W("cumulativeLambda").write(("round", round_index), ("isAdapt", is_adapt), ("beta", beta),
+                                        ("value", diag["cumulativeLambda"][i - 1]))
+            W("lambdaInstantaneous").write(("round", round_index), ("isAdapt", is_adapt), ("beta", beta),
+                                           ("value", diag["lambdaInstantaneous"][i - 1]))
+        n_expl = n_scans * int(np.floor(n_passes * n_samplers)) * N      # reportRoundTiming :212-229
+        W("roundTimings").write(("round", round_index), ("isAdapt", is_adapt), ("nExplorationSteps", n_expl),
+                                ("value", int(round(millis))))
+        if not is_adapt:
+            os.makedirs(os.path.join(self.results.folder, "monitoring"), exist_ok=True)
+            with open(os.path.join(self.results.folder, "monitoring", "runningTimeSummary.tsv"), "a") as f:
+                f.write("postAdaptTime_ms\t%d\n" % int(round(millis)))
+        self.results.flush_all()
+
+    def close(self):
+        self.results.close_all()
+
+
+def replay_round_trips(swap_indicators_csv, start_scan, end_scan):
+    """ptanalysis/Paths.xtend:83-117 + nRejuvenations :26-50 replayed from swapIndicators.csv"""
+    import csv
+    rows = {}
+    n_chains = 0
+    with open(swap_indicators_csv) as f:
+        for r in csv.DictReader(f):
+            s, c, v = int(r["sample"]), int(r["chain"]), int(r["value"])
+            n_chains = max(n_chains, c + 1)
+            if start_scan <= s < end_scan:
+                rows.setdefault(s, {})[c] = v
+    paths = [[c] for c in range(n_chains)]
+    for s in sorted(rows):
+        just = False
+        for c in range(n_chains):
+            if just:
+                just = False
+                continue
+            if rows[s][c] == 1:
+                paths[c], paths[c + 1] = paths[c + 1], paths[c]
+                paths[c].append(c)
+                paths[c + 1].append(c + 1)
+                just = True
+            else:
+                paths[c].append(c)
+    count = 0
+    for p in paths:
+        new = False
+        for st in p:
+            if st == 0 and new:
+                new = False
+                count += 1
+            elif st == n_chains - 1:
+                new = True
+    return count

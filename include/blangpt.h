@@ -163,6 +163,31 @@ int blangpt_adapt(blangpt_handle* h, double* cum_lambda_xy);
 /* reset accumulators without changing the ladder */
 int blangpt_reset_round(blangpt_handle* h);
 
+/* Initial ladders (R/engines/internals/ladders/): kind 0 EquallySpaced (:9-18), 1 Geometric (param =
+ * annealingScaling, default 0.8), 2 Polynomial (param = power, default 3), 3 UserSpecified (user list, optional
+ * spline generalisation to another nChains; FromAnotherExec = UserSpecified on the parsed annealingParameters.csv).
+ * Pure host function.  out[nChains] descending.  EINVAL where the reference throws. */
+int blangpt_make_ladder(int32_t kind, int32_t nChains, double param, const double* user, int32_t n_user,
+                        int32_t allowSplineGeneralization, double* out);
+
+/* Per-round ptanalysis outputs of PT.reportParallelTemperingDiagnostics (PT.java:387-505) and
+ * reportLambdaFunctions (:192-210), computed from the current round's accumulators of one replica. */
+typedef struct {
+  int64_t nScansInRound;
+  double swapLowest, swapAverage;                       /* swapSummaries                               */
+  double energyCorrelationAverage, energyCorrelationHighest; /* energyExplCorrelationSummaries          */
+  double Lambda;                                        /* globalLambda = sum_i (1 - mean accept_i)    */
+  double inefficiency;                                  /* sum_i (1 - a_i) / a_i                       */
+  double timeToFirstRestart, effectiveNScans;           /* timeToFirstRestart                          */
+  int64_t temperedRestarts; double temperedRestartRate; /* actualTemperedRestarts (round trips)        */
+  double asymptoticRoundTripCount, asymptoticRoundTripRate;       /* 1 / (2 + 2 Lambda)                */
+  double nonAsymptoticRoundTripCount, nonAsymptoticRoundTripRate; /* 1 / (2 + 2 inefficiency)          */
+  double logNormalizationSteppingStone, logNormalizationThermodynamic;
+  double cumulativeLambda[99];                          /* Lambda(beta), beta = 0.01 .. 0.99           */
+  double lambdaInstantaneous[99];                       /* lambda(beta) = dLambda/dbeta                */
+} blangpt_diagnostics;
+int blangpt_get_diagnostics(blangpt_handle* h, int64_t replica, blangpt_diagnostics* out);
+
 /* PT.rounds (PT.java:239-265).  Arrays sized >= 64.  Returns the number of rounds. */
 int blangpt_rounds(int32_t nScans, double adaptFraction, int32_t* round_nscans, int32_t* round_is_adapt);
 
