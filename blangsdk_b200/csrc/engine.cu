@@ -49,6 +49,9 @@ struct blangpt_handle {
   uint64_t n_scans = 0, n_launches = 0;
   int64_t scans_in_round = 0;
   int64_t M_total = 0;
+  // SCM initialisation (PT.scmInit defaults, PT.java:68-72,507-515)
+  int scm_particles = 100; double scm_threshold = 0.9, scm_resampling_ess = 0.5;
+  double scm_log_norm = std::nan(""); int scm_n_temperatures = 0, scm_n_resamplings = 0;
 };
 
 #define FAIL(h, code, ...) do { set_error((h), __VA_ARGS__); return (code); } while (0)
@@ -259,6 +262,7 @@ static int alloc_engine(blangpt_handle* h) {
   E.key0 = (uint32_t)c.random; E.key1 = (uint32_t)(c.random >> 32);
   E.replica_offset = (uint32_t)c.replicaOffset;
   E.n_passes = c.nPassesPerScan; E.use_prior = c.usePriorSamples; E.anneal_support = c.annealSupport;
+  E.beta_override = std::nan(""); E.steps_override = 0;
   E.s_max = h->family == BLANGPT_FAM_ISING ? 1 : std::max(1, h->n_samplers);
   double* ladder; int rc;
   if ((rc = dev_alloc(h, &ladder, M))) return rc;
@@ -506,10 +510,224 @@ extern "C" int blangpt_get_state(blangpt_handle* h, int64_t replica, int32_t pos
   return BLANGPT_OK;
 }
 
+// ---------------------------------------------------------------------------
+// SCM initialisation: PT's default `initialization` (PT.java:300-329).  An annealed SMC
+// (AdaptiveJarzynski.getApproximation, R/engines/AdaptiveJarzynski.java:91-137) with nParticles particles
+// walks the temperature up; at each ladder point one particle, drawn by weight, becomes that chain's state.
+// Particles are the chain slots of a child engine that shares the parent's device data; every particle runs
+// at the same exponent (beta_override) and makes ONE sampler step per temperature (steps_override = 1,
+// AdaptiveJarzynski.sampleNext :224-233).  The control logic -- adaptive temperature by a Pegasus search on
+// the relative conditional ESS (schedules/AdaptiveTemperatureSchedule.java:48-78, EngineStaticUtils.java:21-47),
+// stratified resampling below ESS 0.5, weight bookkeeping -- is O(nParticles) host arithmetic on the
+// (loglik, nOOS, fixed) table, as it is host code in the reference.
+// ---------------------------------------------------------------------------
+namespace {
+enum { P_MASTER = 6 };
+struct ScmParticle { double loglik, noos, fixed; };
+
+double scm_density(const ScmParticle& p, double beta, int anneal_support) {
+  return annealed_log_density(p.fixed, p.loglik, p.noos, beta, anneal_support);
+}
+// SampledModel.logDensityRatio :199-206
+bool scm_ratio(const ScmParticle& p, double t, double next, int as, double* out) {
+  const double num = scm_density(p, next, as), den = scm_density(p, t, as);
+  if (num == -INFINITY && den == -INFINITY) return false;
+  *out = num - den;
+  return true;
+}
+// EngineStaticUtils.relativeCESS :27-47
+double scm_relative_cess(const std::vector<ScmParticle>& ps, const std::vector<double>& w, double t, double next, int as, bool* ok) {
+  double lnum = -INFINITY, lden = -INFINITY;
+  for (size_t i = 0; i < ps.size(); i++) {
+    double r;
+    if (!scm_ratio(ps[i], t, next, as, &r)) { *ok = false; return std::nan(""); }
+    lnum = log_add(lnum, log(w[i]) + 1.0 * r);
+    lden = log_add(lden, log(w[i]) + 2.0 * r);
+  }
+  return exp(2.0 * lnum - lden);
+}
+// commons-math3 PegasusSolver (BaseSecantSolver.doSolve, ANY_SIDE), restated from its published algorithm
+template <class F>
+double pegasus_solve(F f, double x0, double x1, double atol, int max_eval) {
+  const double ftol = 1e-15, rtol = 1e-14;
+  double f0 = f(x0), f1 = f(x1);
+  int evals = 2;
+  if (f0 == 0.0) return x0;
+  if (f1 == 0.0) return x1;
+  for (;;) {
+    const double x = x1 - ((f1 * (x1 - x0)) / (f1 - f0));
+    const double fx = f(x);
+    if (++evals > max_eval) return x;
+    if (fx == 0.0) return x;
+    if (f1 * fx < 0) { x0 = x1; f0 = f1; }
+    else f0 *= f1 / (f1 + fx);
+    x1 = x; f1 = fx;
+    if (std::fabs(f1) <= ftol) return x1;
+    if (std::fabs(x1 - x0) < std::max(rtol * std::fabs(x1), atol)) return x1;
+  }
+}
+}  // namespace
+
+static int scm_read_table(blangpt_handle* c, std::vector<ScmParticle>& ps) {
+  const int P = c->cfg.nChains;
+  std::vector<double> tab((size_t)P * 4);
+  CUDA_OK(c, cudaMemcpyAsync(tab.data(), c->E.table, tab.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  int rc = check_device_errors(c);
+  if (rc) return rc;
+  ps.resize(P);
+  for (int i = 0; i < P; i++) ps[i] = {tab[i * 4 + 0], tab[i * 4 + 1], tab[i * 4 + 2]};
+  return 0;
+}
+
+// new particle i = old particle ancestors[i] (ParticlePopulation.resample + deepCopyParticles :149-170)
+static int scm_permute(blangpt_handle* c, const std::vector<int>& anc) {
+  const int P = c->cfg.nChains;
+  if (c->n_reals) {
+    std::vector<double> a((size_t)c->n_reals * P), b(a.size());
+    CUDA_OK(c, cudaMemcpy(a.data(), c->E.reals, a.size() * 8, cudaMemcpyDeviceToHost));
+    for (int v = 0; v < c->n_reals; v++) for (int i = 0; i < P; i++) b[(size_t)v * P + i] = a[(size_t)v * P + anc[i]];
+    CUDA_OK(c, cudaMemcpy(c->E.reals, b.data(), b.size() * 8, cudaMemcpyHostToDevice));
+  }
+  if (c->n_ints) {
+    const size_t S = c->n_ints;
+    std::vector<uint8_t> a(S * P), b(S * P);
+    CUDA_OK(c, cudaMemcpy(a.data(), c->ising.spins, a.size(), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < P; i++) memcpy(&b[S * i], &a[S * anc[i]], S);
+    CUDA_OK(c, cudaMemcpy(c->ising.spins, b.data(), b.size(), cudaMemcpyHostToDevice));
+  }
+  {   // the sampler order travels with the state (SampledModel.currentSamplingOrder is deep-cloned)
+    const size_t sm = c->E.s_max;
+    std::vector<int> o(sm * P), o2(sm * P), cp(P), cp2(P);
+    CUDA_OK(c, cudaMemcpy(o.data(), c->E.order, o.size() * 4, cudaMemcpyDeviceToHost));
+    CUDA_OK(c, cudaMemcpy(cp.data(), c->E.curpos, cp.size() * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < P; i++) { memcpy(&o2[sm * i], &o[sm * anc[i]], sm * 4); cp2[i] = cp[anc[i]]; }
+    CUDA_OK(c, cudaMemcpy(c->E.order, o2.data(), o2.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_OK(c, cudaMemcpy(c->E.curpos, cp2.data(), cp2.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return launch_explore(c, MODE_EVAL);   // rebuild per-particle caches and the table
+}
+
+static int scm_initialize(blangpt_handle* h) {
+  if (h->cfg.worldSize != 1 || h->cfg.nReplicas != 1) FAIL(h, BLANGPT_EUNSUPPORTED, "SCM initialisation is implemented for one replica on one GPU");
+  const int N = h->cfg.nChains, P = h->scm_particles, as = h->cfg.annealSupport;
+  // chains at beta == 0 (and every chain before it is overwritten) start from the prior, PT.java:311-315
+  int rc = blangpt_initialize(h, BLANGPT_INIT_FORWARD);
+  if (rc) return rc;
+  // ---- child engine: P particles sharing the parent's device data ----
+  blangpt_handle* c = new blangpt_handle();
+  c->cfg = h->cfg; c->cfg.nChains = P; c->cfg.nReplicas = 1; c->cfg.usePriorSamples = 0;
+  c->cfg.random = h->cfg.random ^ 0x53434D2D696E6974ULL;   // its own Philox key ("SCM-init")
+  c->M_total = P; c->family = h->family; c->stream = h->stream; c->logistic_threads = h->logistic_threads;
+  c->n_reals = h->n_reals; c->n_ints = h->n_ints; c->n_samplers = h->n_samplers;
+  c->normal = h->normal; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising;
+  c->betabin.chains_per_replica = P;
+  auto fail = [&](int code) { for (void* p : c->allocs) cudaFree(p); if (code) h->error = c->error; delete c; return code; };
+  if (h->family == BLANGPT_FAM_LOGISTIC && (rc = dev_alloc(c, &c->logistic.eta, (size_t)c->logistic.npad * P))) return fail(rc);
+  if (h->family == BLANGPT_FAM_ISING && (rc = dev_alloc(c, &c->ising.spins, (size_t)P * h->n_ints))) return fail(rc);
+  int64_t rows = h->family == BLANGPT_FAM_NORMAL ? h->normal.n : h->family == BLANGPT_FAM_LOGISTIC ? h->logistic.n
+               : h->family == BLANGPT_FAM_MIXTURE ? h->mixture.n : 1;
+  c->G = h->family == BLANGPT_FAM_ISING || h->family == BLANGPT_FAM_BETABINOMIAL ? 1 : pick_ctas_per_chain(c, rows);
+  if ((rc = alloc_engine(c))) return fail(rc);
+  c->model_set = true;
+  if ((rc = launch_explore(c, MODE_FORWARD_INIT))) return fail(rc);   // AdaptiveJarzynski.sampleInitial :214-222
+  std::vector<ScmParticle> ps;
+  if ((rc = scm_read_table(c, ps))) return fail(rc);
+  std::vector<double> w(P, 1.0 / P);
+  double log_scaling = 0.0, temperature = 0.0;
+  uint32_t iter = 0, master = 0;
+  const uint32_t k0 = (uint32_t)c->cfg.random, k1 = (uint32_t)(c->cfg.random >> 32);
+  auto master_double = [&]() { Rng r(k0, k1, P_MASTER, 0u, master++, 0u); return r.next_double(); };
+  h->scm_n_temperatures = 0; h->scm_n_resamplings = 0;
+  c->E.steps_override = 1;
+
+  for (int li = N - 1; li >= 0; li--) {            // ladder ascending; position li
+    const double target = h->ladder[li];
+    if (target == 0.0) continue;
+    while (temperature < target) {
+      // --- AdaptiveTemperatureSchedule.nextTemperature :48-70 ---
+      bool ok = true;
+      auto objective = [&](double x) { return scm_relative_cess(ps, w, temperature, x, as, &ok) - h->scm_threshold; };
+      double next;
+      const double at_one = objective(1.0);
+      if (!ok) return fail((set_error(c, "Invalid logDensity ratio (0/0): this could be caused by a generate(rand){..} block not faithful with its laws{..} block."), BLANGPT_ENUMERIC));
+      if (at_one != at_one) next = std::max(temperature, 1e-10);
+      else next = objective(target) >= 0 ? target : pegasus_solve(objective, temperature, target, 1e-16, 100);
+      if (!(next > temperature)) next = target;     // guard against a stalled search (never reached in the tests)
+      // --- resamplingNeeded :139-147 / resample :149-154 (stratified) ---
+      bool need = false;
+      double ess_den = 0.0;
+      for (int i = 0; i < P; i++) { if (w[i] == 0.0) need = true; ess_den += w[i] * w[i]; }
+      const double rel_ess = 1.0 / (ess_den * P);
+      if (need || (rel_ess < h->scm_resampling_ess && next < target)) {
+        std::vector<int> anc(P);
+        double cum = w[0]; int j = 0;
+        for (int i = 0; i < P; i++) {
+          const double u = (i + master_double()) / P;
+          while (u > cum && j < P - 1) cum += w[++j];
+          anc[i] = j;
+        }
+        if ((rc = scm_permute(c, anc))) return fail(rc);
+        if ((rc = scm_read_table(c, ps))) return fail(rc);
+        std::fill(w.begin(), w.end(), 1.0 / P);
+        h->scm_n_resamplings++;
+      }
+      // --- propose :171-212: weights from the CURRENT states, then one sampler step at the next temperature ---
+      std::vector<double> lw(P);
+      double lsum = -INFINITY;
+      for (int i = 0; i < P; i++) {
+        double r;
+        if (!scm_ratio(ps[i], temperature, next, as, &r)) return fail((set_error(c, "Invalid logDensity ratio (0/0)"), BLANGPT_ENUMERIC));
+        lw[i] = r + log(w[i]);
+        lsum = log_add(lsum, lw[i]);
+      }
+      c->E.beta_override = next;
+      CUDA_OK(c, cudaMemcpyAsync(c->E.scan_counter, &iter, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      if ((rc = launch_explore(c, MODE_EXPLORE))) return fail(rc);
+      if ((rc = scm_read_table(c, ps))) return fail(rc);
+      for (int i = 0; i < P; i++) w[i] = exp(lw[i] - lsum);   // ParticlePopulation.buildDestructivelyFromLogWeights
+      log_scaling += lsum;
+      temperature = next;
+      iter++; h->scm_n_temperatures++;
+    }
+    // --- population.sample(random).duplicate() becomes the chain at this ladder point, PT.java:318-320 ---
+    const double u = master_double();
+    double cum = 0.0; int pick = P - 1;
+    for (int i = 0; i < P; i++) { cum += w[i]; if (u < cum) { pick = i; break; } }
+    std::vector<double> reals(std::max(1, h->n_reals)); std::vector<int32_t> ints(std::max(1, h->n_ints));
+    if (h->n_reals) CUDA_OK(c, cudaMemcpy2D(reals.data(), 8, c->E.reals + pick, (size_t)P * 8, 8, h->n_reals, cudaMemcpyDeviceToHost));
+    if (h->n_ints) {
+      std::vector<uint8_t> b(h->n_ints);
+      CUDA_OK(c, cudaMemcpy(b.data(), c->ising.spins + (size_t)pick * h->n_ints, b.size(), cudaMemcpyDeviceToHost));
+      for (int q = 0; q < h->n_ints; q++) ints[q] = b[q];
+    }
+    if ((rc = blangpt_set_state(h, 0, li, h->n_reals ? reals.data() : nullptr, h->n_ints ? ints.data() : nullptr))) return fail(rc);
+  }
+  h->scm_log_norm = log_scaling;
+  h->n_launches += c->n_launches;
+  fail(0);
+  h->tables_valid = false;
+  return ensure_tables(h);
+}
+
+extern "C" int blangpt_set_scm_options(blangpt_handle* h, int32_t nParticles, double threshold, double resamplingESSThreshold) {
+  if (!h) return BLANGPT_EINVAL;
+  if (nParticles < 2 || !(threshold > 0.0 && threshold < 1.0)) FAIL(h, BLANGPT_EINVAL, "The adaptive tempering threshold should be between 0 and 1 (exclusive)");
+  h->scm_particles = nParticles; h->scm_threshold = threshold; h->scm_resampling_ess = resamplingESSThreshold;
+  return BLANGPT_OK;
+}
+extern "C" int blangpt_scm_summary(const blangpt_handle* h, double* logNormEstimate, int32_t* nTemperatures, int32_t* nResamplings) {
+  if (!h) return BLANGPT_EINVAL;
+  if (logNormEstimate) *logNormEstimate = h->scm_log_norm;
+  if (nTemperatures) *nTemperatures = h->scm_n_temperatures;
+  if (nResamplings) *nResamplings = h->scm_n_resamplings;
+  return BLANGPT_OK;
+}
+
 extern "C" int blangpt_initialize(blangpt_handle* h, int32_t init_type) {
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
-  if (init_type == BLANGPT_INIT_SCM) FAIL(h, BLANGPT_EUNSUPPORTED, "initialization SCM is not implemented on the GPU engine; use FORWARD or COPIES");
+  if (init_type == BLANGPT_INIT_SCM) return scm_initialize(h);
   if (init_type == BLANGPT_INIT_COPIES) { h->tables_valid = false; return ensure_tables(h); }
   if (init_type != BLANGPT_INIT_FORWARD) FAIL(h, BLANGPT_EINVAL, "unknown initialization");
   int rc = launch_explore(h, MODE_FORWARD_INIT);

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kIsingThreads) ising_kernel(DevEngine E, Ising
   const int g = E.slot_lo + l;
   const int rep = g / E.N, s_in_rep = g - rep * E.N;
   const int pos = E.pos_of_slot[rep * E.N + s_in_rep];
-  const double beta = E.ladder[rep * E.N + pos];
+  const double beta = E.beta_override == E.beta_override ? E.beta_override : E.ladder[rep * E.N + pos];
   const uint32_t scan = E.scan_counter[rep];
   const uint32_t key1 = E.key1 ^ (E.replica_offset + (uint32_t)rep);
   uint8_t* gs = D.spins + (size_t)l * S;
@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(kIsingThreads) ising_kernel(DevEngine E, Ising
     }
     __syncthreads();
   } else if (mode == MODE_EXPLORE) {
-    const int n_pass = (int)floor(E.n_passes);
+    // steps_override (SCM: "one sampler step per temperature") is served by one full checkerboard pass
+    const int n_pass = E.steps_override > 0 ? 1 : (int)floor(E.n_passes);
     const double bj = beta * D.coupling;
     const int half = S / 2;
     for (int pass = 0; pass < n_pass; pass++)

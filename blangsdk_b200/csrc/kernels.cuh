@@ -28,6 +28,8 @@ struct DevEngine {
   uint32_t key0, key1;      // Philox key: (seed lo, seed hi); replica folded into key1
   uint32_t replica_offset;
   double n_passes;
+  double beta_override;     // NaN = use the ladder; otherwise every chain runs at this exponent (SCM particles)
+  int steps_override;       // 0 = floor(n_passes * S) sampler executions per scan; > 0 = exactly that many
   int use_prior, anneal_support;
   int s_max;                // stride of the order array
   const double* ladder;     // [R][N] descending
@@ -129,7 +131,7 @@ BPT_D void explore_chain(const DevEngine& E, Fam& fam, GroupReducer& red, double
       Rng rng(E.key0, key1, P_FORWARD, (uint32_t)pos, scan, 0u);
       fam.forward(rng);
     } else {
-      const int n_steps = (int)floor(E.n_passes * S);
+      const int n_steps = E.steps_override > 0 ? E.steps_override : (int)floor(E.n_passes * S);
       for (int t = 0; t < n_steps; t++) {
         Sync::sync();
         if (curpos == -1) {   // Collections.shuffle(order, rnd); SampledModel.java:267-272
@@ -182,7 +184,7 @@ explore_kernel(DevEngine E, typename Fam::Data D, int G, int mode) {
   const int g = E.slot_lo + l;
   const int rep = g / E.N, s_in_rep = g - rep * E.N;
   const int pos = E.pos_of_slot[rep * E.N + s_in_rep];
-  const double beta = E.ladder[rep * E.N + pos];
+  const double beta = E.beta_override == E.beta_override ? E.beta_override : E.ladder[rep * E.N + pos];
   const uint32_t scan = E.scan_counter[rep];
   const uint32_t key1 = E.key1 ^ (E.replica_offset + (uint32_t)rep);
 

@@ -4,7 +4,7 @@
 (R/engines/internals/factories/PT.java:47-82) and blang.engines.ParallelTempering
 (R/engines/ParallelTempering.java:25-40) so a test reads like the reference's own:
 
-    pt = PT(nChains=8, nScans=1000, adaptFraction=0.5, random=1, initialization="FORWARD")
+    pt = PT(nChains=8, nScans=1000, adaptFraction=0.5, random=1)          # initialization="SCM" like the reference
     pt.setSampledModel(datasets.normal_meanvar())
     result = pt.performInference()
 
@@ -82,6 +82,7 @@ EXPORTS = [
     "blangpt_perform_inference", "blangpt_counters", "blangpt_set_stream", "blangpt_evaluate", "blangpt_prime",
     "blangpt_explore", "blangpt_table_ptr", "blangpt_local_chains", "blangpt_swap", "blangpt_synchronize",
     "blangpt_microbench", "blangpt_debug_logit_terms", "blangpt_make_ladder", "blangpt_get_diagnostics",
+    "blangpt_set_scm_options", "blangpt_scm_summary",
 ]
 
 _LIB = None
@@ -132,6 +133,8 @@ def load_library():
     L.blangpt_debug_logit_terms.argtypes = [C.c_int32, _dp, _ip, C.c_int64, _dp]
     L.blangpt_make_ladder.argtypes = [C.c_int32, C.c_int32, C.c_double, _dp, C.c_int32, C.c_int32, _dp]
     L.blangpt_get_diagnostics.argtypes = [vp, C.c_int64, C.POINTER(Diagnostics)]
+    L.blangpt_set_scm_options.argtypes = [vp, C.c_int32, C.c_double, C.c_double]
+    L.blangpt_scm_summary.argtypes = [vp, _dp, _ip, _ip]
     _LIB = L
     return L
 
@@ -295,8 +298,15 @@ class Engine:
         self._check(self.L.blangpt_get_state(self.h, replica, position, _d(re), _i(it)))
         return re[:self.n_reals], it[:self.n_ints]
 
-    def initialize(self, initialization="FORWARD"):
+    def initialize(self, initialization="FORWARD", nParticles=None, threshold=0.9, resamplingESSThreshold=0.5):
+        if nParticles is not None:
+            self._check(self.L.blangpt_set_scm_options(self.h, nParticles, threshold, resamplingESSThreshold))
         self._check(self.L.blangpt_initialize(self.h, INIT[initialization]))
+
+    def scm_summary(self):
+        ln, nt, nr = C.c_double(), C.c_int32(), C.c_int32()
+        self._check(self.L.blangpt_scm_summary(self.h, C.byref(ln), C.byref(nt), C.byref(nr)))
+        return dict(logNormEstimate=ln.value, nTemperatures=nt.value, nResamplings=nr.value)
 
     def log_density(self):
         M = self.R * self.N
@@ -396,12 +406,11 @@ class Engine:
 class PT:
     """Python mirror of blang.engines.internals.factories.PT (option names and defaults kept).
 
-    Differences, all loud: `initialization` defaults to FORWARD because SCM initialisation is a
-    "next" row and is rejected; `targetAccept` is rejected; `nThreads` is ignored.
+    Differences, all loud: `targetAccept` is rejected; `nThreads` is ignored.
     """
 
     def __init__(self, nChains=8, nScans=1000, adaptFraction=0.5, nPassesPerScan=3.0, thinning=1, random=1,
-                 usePriorSamples=True, reversible=False, initialization="FORWARD", targetAccept=None,
+                 usePriorSamples=True, reversible=False, initialization="SCM", targetAccept=None,
                  logNormalizationEstimator="steppingStone", nThreads=None, ladder="EquallySpaced",
                  annealSupport=True, treatNaNAsNegativeInfinity=False, nReplicas=1, device=0, ctasPerChain=0):
         if targetAccept is not None:

@@ -50,7 +50,7 @@ enum {
 };
 
 /* PT.InitType (R/engines/internals/factories/PT.java:267) */
-enum { BLANGPT_INIT_COPIES = 0, BLANGPT_INIT_FORWARD = 1, BLANGPT_INIT_SCM = 2 /* rejected: EUNSUPPORTED */ };
+enum { BLANGPT_INIT_COPIES = 0, BLANGPT_INIT_FORWARD = 1, BLANGPT_INIT_SCM = 2 };
 
 enum { BLANGPT_F64 = 0, BLANGPT_I32 = 1 };
 
@@ -112,9 +112,15 @@ int blangpt_get_ladder(const blangpt_handle* h, double* out, int64_t n);
  * written/read when worldSize > 1 (others return EINVAL). */
 int blangpt_set_state(blangpt_handle* h, int64_t replica, int32_t position, const double* reals, const int32_t* ints);
 int blangpt_get_state(blangpt_handle* h, int64_t replica, int32_t position, double* reals, int32_t* ints);
-/* PT.informedInitialization :284-329 (COPIES keeps the states as set; FORWARD draws
- * every chain from the prior) */
+/* PT.informedInitialization :284-329.  COPIES keeps the states as set; FORWARD draws every chain from the
+ * prior; SCM (the reference's default) runs an annealed SMC (R/engines/AdaptiveJarzynski.java:91-233,
+ * schedules/AdaptiveTemperatureSchedule.java:48-78) with nParticles particles and hands one particle, drawn
+ * by weight, to each ladder point. */
 int blangpt_initialize(blangpt_handle* h, int32_t init_type);
+/* PT.scmInit options (PT.java:68-72: nParticles 100, temperatureSchedule.threshold 0.9; resamplingESSThreshold 0.5) */
+int blangpt_set_scm_options(blangpt_handle* h, int32_t nParticles, double threshold, double resamplingESSThreshold);
+/* after an SCM initialisation: population.logNormEstimate() (PT.java:322-327), temperatures visited, resamplings */
+int blangpt_scm_summary(const blangpt_handle* h, double* logNormEstimate, int32_t* nTemperatures, int32_t* nResamplings);
 
 /* Parity hook: annealed log-densities of the CURRENT states, per position:
  * out_logdens = SampledModel.logDensity() at the chain's own beta (:161-176),

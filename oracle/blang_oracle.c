@@ -1243,6 +1243,149 @@ int orc_pt_perform_inference(orc_pt* pt, int n_scans, double adapt_fraction,
   return scan;
 }
 
+/* ------------------------------------------------------------------ */
+/* SCM initialisation of PT (PT.informedInitialization, PT.java:300-329;  */
+/* AdaptiveJarzynski.java:91-233; AdaptiveTemperatureSchedule.java:48-78; */
+/* EngineStaticUtils.relativeCESS :27-47).  bayonet's ParticlePopulation  */
+/* and commons-math3's PegasusSolver are restated from their published    */
+/* algorithms (neither is in the tree).                                   */
+/* ------------------------------------------------------------------ */
+enum { P_MASTER = 6 };
+
+typedef struct { SampledModel** p; double* w; int n; double t; int as; double thr; int err; } ScmPop;
+
+static int scm_ratio(SampledModel* s, double t, double next, double* out) {   /* SampledModel.logDensityRatio :199-206 */
+  double num = sm_log_density_at(s, next), den = sm_log_density_at(s, t);
+  if (num == NEG_INF && den == NEG_INF) return 0;
+  *out = num - den;
+  return 1;
+}
+static double scm_objective(ScmPop* q, double x) {
+  double lnum = NEG_INF, lden = NEG_INF;
+  for (int i = 0; i < q->n; i++) {
+    double r;
+    if (!scm_ratio(q->p[i], q->t, x, &r)) { q->err = 1; return NAN; }
+    lnum = orc_log_add(lnum, log(q->w[i]) + 1.0 * r);
+    lden = orc_log_add(lden, log(q->w[i]) + 2.0 * r);
+  }
+  return exp(2.0 * lnum - lden) - q->thr;
+}
+static double scm_pegasus(ScmPop* q, double x0, double x1, double atol, int max_eval) {
+  const double ftol = 1e-15, rtol = 1e-14;
+  double f0 = scm_objective(q, x0), f1 = scm_objective(q, x1);
+  int evals = 2;
+  if (f0 == 0.0) return x0;
+  if (f1 == 0.0) return x1;
+  for (;;) {
+    double x = x1 - ((f1 * (x1 - x0)) / (f1 - f0));
+    double fx = scm_objective(q, x);
+    if (++evals > max_eval) return x;
+    if (fx == 0.0) return x;
+    if (f1 * fx < 0) { x0 = x1; f0 = f1; }
+    else f0 *= f1 / (f1 + fx);
+    x1 = x; f1 = fx;
+    if (fabs(f1) <= ftol) return x1;
+    if (fabs(x1 - x0) < fmax(rtol * fabs(x1), atol)) return x1;
+  }
+}
+static void sm_copy(SampledModel* dst, const SampledModel* src) {   /* SampledModel.duplicate (deep clone) */
+  const orc_model* m = src->m;
+  memcpy(dst->reals, src->reals, sizeof(double) * m->n_reals);
+  memcpy(dst->ints, src->ints, sizeof(int32_t) * m->n_ints);
+  memcpy(dst->caches, src->caches, sizeof(double) * m->n_factors);
+  memcpy(dst->order, src->order, sizeof(int32_t) * m->n_samplers);
+  dst->cur_pos = src->cur_pos; dst->cumulative_n_scans = src->cumulative_n_scans;
+  dst->sum_pre = src->sum_pre; dst->sum_fixed = src->sum_fixed; dst->n_oos = src->n_oos;
+  dst->oos_detected = src->oos_detected; dst->exponent = src->exponent;
+}
+
+int orc_pt_initialize_scm(orc_pt* pt, int n_particles, double threshold, double ess_threshold,
+                          double* log_norm_out, int32_t* n_temps_out, int32_t* n_resample_out) {
+  const orc_model* m = pt->m;
+  const int P = n_particles, N = pt->n;
+  const uint64_t seed = pt->cfg.seed ^ 0x53434D2D696E6974ULL;
+  orc_pt_initialize(pt, ORC_INIT_FORWARD);
+  SampledModel** ps = (SampledModel**)calloc(P, sizeof(SampledModel*));
+  SampledModel** tmp = (SampledModel**)calloc(P, sizeof(SampledModel*));
+  double* w = (double*)malloc(sizeof(double) * P);
+  double* lw = (double*)malloc(sizeof(double) * P);
+  int* anc = (int*)malloc(sizeof(int) * P);
+  for (int i = 0; i < P; i++) {                       /* AdaptiveJarzynski.sampleInitial :214-222 */
+    ps[i] = sm_new(m, pt->cfg.anneal_support); tmp[i] = sm_new(m, pt->cfg.anneal_support);
+    ps[i]->exponent = 0.0;
+    Rng r = rng_make(seed, 0, P_INIT, (uint32_t)i, 0, 0);
+    sm_forward_sample(ps[i], &r);
+    w[i] = 1.0 / P;
+  }
+  ScmPop q; q.p = ps; q.w = w; q.n = P; q.t = 0.0; q.as = pt->cfg.anneal_support; q.thr = threshold; q.err = 0;
+  double log_scaling = 0.0;
+  uint32_t iter = 0, master = 0;
+  int n_temps = 0, n_res = 0, status = 0;
+  for (int li = N - 1; li >= 0 && !status; li--) {
+    const double target = pt->betas[li];
+    if (target == 0.0) continue;
+    while (q.t < target) {
+      double next;
+      double at_one = scm_objective(&q, 1.0);
+      if (q.err) { status = 1; break; }
+      if (isnan(at_one)) next = fmax(q.t, 1e-10);
+      else next = scm_objective(&q, target) >= 0 ? target : scm_pegasus(&q, q.t, target, 1e-16, 100);
+      if (!(next > q.t)) next = target;
+      int need = 0; double den = 0.0;
+      for (int i = 0; i < P; i++) { if (w[i] == 0.0) need = 1; den += w[i] * w[i]; }
+      double rel_ess = 1.0 / (den * P);
+      if (need || (rel_ess < ess_threshold && next < target)) {     /* stratified resampling */
+        double cum = w[0]; int j = 0;
+        for (int i = 0; i < P; i++) {
+          Rng r = rng_make(seed, 0, P_MASTER, 0, master++, 0);
+          double u = (i + rng_double(&r)) / P;
+          while (u > cum && j < P - 1) cum += w[++j];
+          anc[i] = j;
+        }
+        for (int i = 0; i < P; i++) sm_copy(tmp[i], ps[anc[i]]);
+        for (int i = 0; i < P; i++) { SampledModel* t = ps[i]; ps[i] = tmp[i]; tmp[i] = t; w[i] = 1.0 / P; }
+        n_res++;
+      }
+      double lsum = NEG_INF;
+      for (int i = 0; i < P; i++) {                                 /* propose :171-212 */
+        double r;
+        if (!scm_ratio(ps[i], q.t, next, &r)) { status = 1; break; }
+        lw[i] = r + log(w[i]);
+        lsum = orc_log_add(lsum, lw[i]);
+      }
+      if (status) break;
+      for (int i = 0; i < P; i++) {                                 /* sampleNext :224-233: one sampler step */
+        SampledModel* s = ps[i];
+        s->exponent = next;
+        if (pt->cfg.sweep_order == ORC_ORDER_CHECKERBOARD && m->family == ORC_FAM_ISING) {
+          int Nn = m->N, S = Nn * Nn;
+          for (int colour = 0; colour < 2; colour++)
+            for (int v = 0; v < S; v++) {
+              if ((((v / Nn) + (v % Nn)) & 1) != colour) continue;
+              Rng r = rng_make(seed, 0, P_MOVE, (uint32_t)i, iter, (uint32_t)v);
+              sampler_execute(s, v, &r);
+              sm_update(s, v);
+            }
+        } else sm_posterior_sampling_step(s, seed, 0, (uint32_t)i, iter, 0);
+      }
+      for (int i = 0; i < P; i++) w[i] = exp(lw[i] - lsum);
+      log_scaling += lsum;
+      q.t = next; iter++; n_temps++;
+    }
+    if (status) break;
+    Rng r = rng_make(seed, 0, P_MASTER, 0, master++, 0);
+    double u = rng_double(&r), cum = 0.0; int pick = P - 1;
+    for (int i = 0; i < P; i++) { cum += w[i]; if (u < cum) { pick = i; break; } }
+    orc_pt_set_state(pt, li, ps[pick]->reals, ps[pick]->ints);
+  }
+  if (log_norm_out) *log_norm_out = log_scaling;
+  if (n_temps_out) *n_temps_out = n_temps;
+  if (n_resample_out) *n_resample_out = n_res;
+  for (int i = 0; i < P; i++) { sm_free(ps[i]); sm_free(tmp[i]); }
+  free(ps); free(tmp); free(w); free(lw); free(anc);
+  return status;
+}
+
 /* one-shot from-scratch density */
 void orc_model_log_density(const orc_model* m, const double* reals, const int32_t* ints,
                            double beta, int anneal_support, double out[4]) {

@@ -101,6 +101,9 @@ void orc_pt_get_ladder(const orc_pt*, double* out_desc);
 void orc_pt_set_state(orc_pt*, int position, const double* reals, const int32_t* ints);
 void orc_pt_get_state(const orc_pt*, int position, double* reals, int32_t* ints);
 void orc_pt_initialize(orc_pt*, int init_type);
+/* PT's default SCM initialisation (PT.java:300-329).  Returns 0, or 1 on the reference's "0/0 ratio" error. */
+int orc_pt_initialize_scm(orc_pt*, int n_particles, double threshold, double ess_threshold,
+                          double* log_norm_out, int32_t* n_temps_out, int32_t* n_resample_out);
 /* per-position: logDensity at own beta, preAnnealedLogLikelihood, nOutOfSupport, sumFixed */
 void orc_pt_densities(const orc_pt*, double* logdens, double* loglik, int32_t* noos, double* fixed);
 /* from-scratch check of the caches: max abs difference cache vs recomputed (SampledModel.check) */

@@ -92,6 +92,8 @@ def lib():
     L.orc_pt_set_state.argtypes = [vp, C.c_int, _dp, _ip]
     L.orc_pt_get_state.argtypes = [vp, C.c_int, _dp, _ip]
     L.orc_pt_initialize.argtypes = [vp, C.c_int]
+    L.orc_pt_initialize_scm.restype = C.c_int
+    L.orc_pt_initialize_scm.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp, _ip, _ip]
     L.orc_pt_densities.argtypes = [vp, _dp, _dp, _ip, _dp]
     L.orc_pt_check_caches.restype = C.c_double
     L.orc_pt_check_caches.argtypes = [vp]
@@ -248,6 +250,13 @@ class PT:
 
     def initialize(self, init_type=INIT_FORWARD):
         lib().orc_pt_initialize(self.h, init_type)
+
+    def initialize_scm(self, nParticles=100, threshold=0.9, resamplingESSThreshold=0.5):
+        ln, nt, nr = C.c_double(), C.c_int32(), C.c_int32()
+        rc = lib().orc_pt_initialize_scm(self.h, nParticles, threshold, resamplingESSThreshold, C.byref(ln), C.byref(nt), C.byref(nr))
+        if rc != 0:
+            raise RuntimeError("Invalid logDensity ratio (0/0)")
+        return dict(logNormEstimate=ln.value, nTemperatures=nt.value, nResamplings=nr.value)
 
     def densities(self):
         ld, ll, fx = np.zeros(self.n), np.zeros(self.n), np.zeros(self.n)

@@ -65,7 +65,7 @@ def test_cuda_reproduces_golden(case):
         assert _close(got["logdens"][0, p], d["logdens"])
     eng.close()
     r = case["run"]
-    pt = PT(nChains=r["nChains"], nScans=r["nScans"], adaptFraction=r["adaptFraction"], random=r["seed"])
+    pt = PT(nChains=r["nChains"], nScans=r["nScans"], adaptFraction=r["adaptFraction"], random=r["seed"], initialization="FORWARD")
     pt.setSampledModel(spec)
     res = pt.performInference()
     assert np.array_equal(res["swapIndicators"][:, 0, :], np.array(r["indicators"]))

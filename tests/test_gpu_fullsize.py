@@ -140,7 +140,7 @@ def test_ising_gpu_statistics_against_enumeration(oracle, datasets):
     spec = datasets.ising(4)
     h = spec["hyper"]
     exact = oracle.lib().orc_ising_exact_log_z(4, h["coupling"], h["moment"], 1.0)
-    pt = PT(nChains=8, nScans=4000, adaptFraction=0.5, random=5)
+    pt = PT(nChains=8, nScans=4000, adaptFraction=0.5, random=5, initialization="FORWARD")
     pt.setSampledModel(spec)
     res = pt.performInference(want=("energy",))
     st = res["finalStats"]

@@ -173,7 +173,7 @@ def test_rounds_adaptation_and_diagnostics(oracle, datasets):
     (PT.java:85-171,387-505) against the oracle's restatement."""
     from blangsdk_b200.engine import PT
     for spec in (datasets.normal_meanvar(n=150), datasets.logistic_regression(300, 4)):
-        pt = PT(nChains=6, nScans=200, adaptFraction=0.5, random=13)
+        pt = PT(nChains=6, nScans=200, adaptFraction=0.5, random=13, initialization="FORWARD")
         pt.setSampledModel(spec)
         res = pt.performInference()
         ref = oracle.PT(oracle.Model(spec), nChains=6, seed=13)
@@ -384,3 +384,37 @@ def test_fused_replica_kernel(oracle, datasets, fam, monkeypatch):
         total += ref.n_evals()
         assert rel(out["stats"]["swapAcceptMean"][r], ref.round_stats()["swap_accept_mean"]) < TOL
     assert total == out["evals"]
+
+
+@pytest.mark.parametrize("fam", ["normal", "logistic", "mixture", "betabinomial", "ising"])
+def test_scm_initialisation(oracle, datasets, fam):
+    """PT's default initialisation (PT.java:300-329): annealed SMC with adaptive temperatures, stratified
+    resampling and one sampler step per temperature, then one particle per ladder point.  Same temperatures,
+    same resampling rounds, same chain states as the oracle's restatement; then the scans agree too."""
+    from blangsdk_b200.engine import Engine
+    spec = {"normal": datasets.normal_meanvar(n=150), "logistic": datasets.logistic_regression(400, 4),
+            "mixture": datasets.gaussian_mixture(300), "betabinomial": datasets.beta_binomial(2),
+            "ising": datasets.ising(6)}[fam]
+    N = 5
+    eng = Engine(nChains=N, random=41)
+    eng.set_model(spec)
+    eng.initialize("SCM", nParticles=40, threshold=0.9)
+    ref = oracle.PT(oracle.Model(spec), nChains=N, seed=41,
+                    sweepOrder=oracle.ORDER_CHECKERBOARD if fam == "ising" else oracle.ORDER_REFERENCE)
+    rs = ref.initialize_scm(nParticles=40, threshold=0.9)
+    gs = eng.scm_summary()
+    assert gs["nTemperatures"] == rs["nTemperatures"] and gs["nResamplings"] == rs["nResamplings"]
+    assert gs["nTemperatures"] > 3
+    assert abs(gs["logNormEstimate"] - rs["logNormEstimate"]) <= 1e-8 * max(1.0, abs(rs["logNormEstimate"]))
+    for p in range(N):
+        re, it = eng.get_state(p)
+        rr, ri = ref.get_state(p)
+        assert rel(re, rr) < 1e-8 and np.array_equal(it, ri)
+    d, r = eng.log_density(), ref.densities()
+    assert rel(d["loglik"][0], r["loglik"]) < 1e-8
+    # informed start: the cold chains are near their target, far better than a prior draw
+    assert d["loglik"][0, 0] > d["loglik"][0, N - 1] or fam == "ising"
+    out, e_ref, i_ref = run_both(eng, ref, 5)
+    assert np.array_equal(out["swapIndicators"][:, 0, :], i_ref)
+    assert rel(out["energy"][:, 0, :], e_ref) < 1e-8
+    eng.close()

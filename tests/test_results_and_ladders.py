@@ -95,7 +95,7 @@ def test_results_writer_format(tmp_path):
 def test_run_to_disk_and_read_back(tmp_path, datasets):
     from blangsdk_b200.engine import PT, ladder_from_another_exec
     from blangsdk_b200.results import replay_round_trips
-    pt = PT(nChains=6, nScans=300, adaptFraction=0.5, random=8)
+    pt = PT(nChains=6, nScans=300, adaptFraction=0.5, random=8, initialization="FORWARD")
     pt.setSampledModel(datasets.normal_meanvar(n=60))
     res = pt.performInference(results=str(tmp_path))
     rs = res["rounds"]
