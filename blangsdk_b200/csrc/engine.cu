@@ -546,26 +546,6 @@ double scm_relative_cess(const std::vector<ScmParticle>& ps, const std::vector<d
   }
   return exp(2.0 * lnum - lden);
 }
-// commons-math3 PegasusSolver (BaseSecantSolver.doSolve, ANY_SIDE), restated from its published algorithm
-template <class F>
-double pegasus_solve(F f, double x0, double x1, double atol, int max_eval) {
-  const double ftol = 1e-15, rtol = 1e-14;
-  double f0 = f(x0), f1 = f(x1);
-  int evals = 2;
-  if (f0 == 0.0) return x0;
-  if (f1 == 0.0) return x1;
-  for (;;) {
-    const double x = x1 - ((f1 * (x1 - x0)) / (f1 - f0));
-    const double fx = f(x);
-    if (++evals > max_eval) return x;
-    if (fx == 0.0) return x;
-    if (f1 * fx < 0) { x0 = x1; f0 = f1; }
-    else f0 *= f1 / (f1 + fx);
-    x1 = x; f1 = fx;
-    if (std::fabs(f1) <= ftol) return x1;
-    if (std::fabs(x1 - x0) < std::max(rtol * std::fabs(x1), atol)) return x1;
-  }
-}
 }  // namespace
 
 static int scm_read_table(blangpt_handle* c, std::vector<ScmParticle>& ps) {
@@ -923,6 +903,35 @@ extern "C" int blangpt_rounds(int32_t nScans, double f, int32_t* rn, int32_t* ra
   if (r.size() > 64) return -1;
   for (size_t i = 0; i < r.size(); i++) { rn[i] = r[i].n_scans; ra[i] = r[i].is_adapt ? 1 : 0; }
   return (int)r.size();
+}
+
+// PT.adapt's targetAccept branch (PT.java:156-163): the resized ladder for the current round's acceptance rates.
+// The caller re-creates the engine with *n_out chains, all copies of the beta = 1 state (`initialize(states[0], random)`).
+extern "C" int blangpt_target_accept_ladder(blangpt_handle* h, int64_t replica, double targetAccept, double* out_desc,
+                                            int32_t capacity, int32_t* n_out) {
+  if (!h || !out_desc || !n_out) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  const int N = h->cfg.nChains;
+  if (N < 2 || replica < 0 || replica >= h->cfg.nReplicas) FAIL(h, BLANGPT_EINVAL, "bad replica / single chain");
+  if (!(targetAccept >= 0.0 && targetAccept < 1.0)) FAIL(h, BLANGPT_EINVAL, "targetAccept must be in [0,1)");
+  const int64_t M = h->M_total;
+  std::vector<long long> acc_n(M); std::vector<double> acc_m1(M);
+  CUDA_OK(h, cudaMemcpyAsync(acc_n.data(), h->St.acc_n, M * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaMemcpyAsync(acc_m1.data(), h->St.acc_m1, M * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  const size_t base = (size_t)replica * N;
+  std::vector<double> accv(N - 1);
+  for (int i = 0; i < N - 1; i++) accv[i] = acc_n[base + i] ? acc_m1[base + i] : std::nan("");
+  std::vector<double> desc(h->ladder.begin() + base, h->ladder.begin() + base + N);
+  std::vector<double> asc(desc.rbegin(), desc.rend());
+  MonotoneSpline cum = cumulative_lambda_spline(asc, intensities_ascending(accv));
+  std::vector<double> part = target_acceptance_partition(cum, targetAccept);
+  if (part.empty()) FAIL(h, BLANGPT_EINVAL, "invalid targetAccept");
+  *n_out = (int32_t)part.size();
+  if ((int)part.size() > capacity) FAIL(h, BLANGPT_EINVAL, "output buffer too small for %d chains", (int)part.size());
+  for (size_t i = 0; i < part.size(); i++) out_desc[i] = part[part.size() - 1 - i];
+  out_desc[0] = 1.0;
+  return BLANGPT_OK;
 }
 
 extern "C" int blangpt_make_ladder(int32_t kind, int32_t nChains, double param, const double* user, int32_t n_user,

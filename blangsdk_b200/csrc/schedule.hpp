@@ -152,6 +152,48 @@ inline std::vector<double> adapt_ladder(const std::vector<double>& betas_desc, c
   return desc;
 }
 
+// commons-math3 PegasusSolver (BaseSecantSolver.doSolve, ANY_SIDE), restated from its published algorithm:
+// a bracketing secant method; `atol` is the solver's absolute accuracy, relative 1e-14, function value 1e-15
+template <class F>
+inline double pegasus_solve(F f, double x0, double x1, double atol, int max_eval) {
+  const double ftol = 1e-15, rtol = 1e-14;
+  double f0 = f(x0), f1 = f(x1);
+  int evals = 2;
+  if (f0 == 0.0) return x0;
+  if (f1 == 0.0) return x1;
+  for (;;) {
+    const double x = x1 - ((f1 * (x1 - x0)) / (f1 - f0));
+    const double fx = f(x);
+    if (++evals > max_eval) return x;
+    if (fx == 0.0) return x;
+    if (f1 * fx < 0) { x0 = x1; f0 = f1; }
+    else f0 *= f1 / (f1 + fx);
+    x1 = x; f1 = fx;
+    if (std::fabs(f1) <= ftol) return x1;
+    if (std::fabs(x1 - x0) < std::max(rtol * std::fabs(x1), atol)) return x1;
+  }
+}
+
+// EngineStaticUtils.targetAcceptancePartition :75-83 + fixedSizeOptimalPartition :176-198: resize the ladder so
+// that every pair rejects with probability about 1 - targetAccept.  Returns the new ladder ASCENDING.
+inline std::vector<double> target_acceptance_partition(const MonotoneSpline& cumulative_lambda, double target_accept) {
+  std::vector<double> result;
+  if (!(target_accept >= 0.0 && target_accept <= 1.0)) return result;
+  const double Lambda = cumulative_lambda(1.0);
+  const int n_grids = std::max(2, (int)(Lambda / (1.0 - target_accept)));
+  double left = 0.0;
+  for (int i = 0; i < n_grids - 1; i++) {
+    const double y = Lambda * i / (n_grids - 1.0);
+    const double lo = std::max(0.0, left - 0.1);     // relaxed bracket, :188-190
+    const double point = pegasus_solve([&](double x) { return cumulative_lambda(x) - y; }, lo, 1.0, 1e-16, 10000);
+    result.push_back(point);
+    left = point;
+  }
+  result.push_back(1.0);
+  std::sort(result.begin(), result.end());
+  return result;
+}
+
 // ---- initial ladders (R/engines/internals/ladders/*.java) --------------------------------------------------
 enum LadderKind { LADDER_EQUALLY_SPACED = 0, LADDER_GEOMETRIC = 1, LADDER_POLYNOMIAL = 2, LADDER_USER_SPECIFIED = 3 };
 

@@ -82,7 +82,7 @@ EXPORTS = [
     "blangpt_perform_inference", "blangpt_counters", "blangpt_set_stream", "blangpt_evaluate", "blangpt_prime",
     "blangpt_explore", "blangpt_table_ptr", "blangpt_local_chains", "blangpt_swap", "blangpt_synchronize",
     "blangpt_microbench", "blangpt_debug_logit_terms", "blangpt_make_ladder", "blangpt_get_diagnostics",
-    "blangpt_set_scm_options", "blangpt_scm_summary",
+    "blangpt_set_scm_options", "blangpt_scm_summary", "blangpt_target_accept_ladder",
 ]
 
 _LIB = None
@@ -135,6 +135,7 @@ def load_library():
     L.blangpt_get_diagnostics.argtypes = [vp, C.c_int64, C.POINTER(Diagnostics)]
     L.blangpt_set_scm_options.argtypes = [vp, C.c_int32, C.c_double, C.c_double]
     L.blangpt_scm_summary.argtypes = [vp, _dp, _ip, _ip]
+    L.blangpt_target_accept_ladder.argtypes = [vp, C.c_int64, C.c_double, _dp, C.c_int32, _ip]
     _LIB = L
     return L
 
@@ -368,6 +369,13 @@ class Engine:
         out["lambdaInstantaneous"] = np.array(d.lambdaInstantaneous)
         return out
 
+    def target_accept_ladder(self, targetAccept, replica=0, capacity=65536):
+        """resized ladder of PT.adapt's targetAccept branch (PT.java:156-163), descending"""
+        out = np.zeros(capacity)
+        n = C.c_int32()
+        self._check(self.L.blangpt_target_accept_ladder(self.h, replica, float(targetAccept), _d(out), capacity, C.byref(n)))
+        return out[:n.value].copy()
+
     def adapt(self):
         knots = np.zeros((self.R, 2, self.N))
         self._check(self.L.blangpt_adapt(self.h, _d(knots)))
@@ -406,15 +414,20 @@ class Engine:
 class PT:
     """Python mirror of blang.engines.internals.factories.PT (option names and defaults kept).
 
-    Differences, all loud: `targetAccept` is rejected; `nThreads` is ignored.
+    `nThreads` is ignored.  `targetAccept` resizes the ladder at the last adaptive round (PT.java:156-163) by
+    re-creating the engine with the new number of chains, all started from the beta = 1 state.
     """
 
     def __init__(self, nChains=8, nScans=1000, adaptFraction=0.5, nPassesPerScan=3.0, thinning=1, random=1,
                  usePriorSamples=True, reversible=False, initialization="SCM", targetAccept=None,
                  logNormalizationEstimator="steppingStone", nThreads=None, ladder="EquallySpaced",
                  annealSupport=True, treatNaNAsNegativeInfinity=False, nReplicas=1, device=0, ctasPerChain=0):
-        if targetAccept is not None:
-            raise BlangPTError("targetAccept (PT.java:156-163) is not supported by the GPU engine yet")
+        if targetAccept is not None and not (0.0 <= targetAccept < 1.0):
+            raise BlangPTError("targetAccept must be in [0,1)")
+        self.targetAccept = targetAccept
+        self._engine_kw = dict(random=random, nPassesPerScan=nPassesPerScan, usePriorSamples=usePriorSamples,
+                               reversible=reversible, annealSupport=annealSupport,
+                               treatNaNAsNegativeInfinity=treatNaNAsNegativeInfinity, device=device, ctasPerChain=ctasPerChain)
         if logNormalizationEstimator not in ("steppingStone", "thermodynamicIntegration"):
             raise BlangPTError("unknown logNormalizationEstimator")
         self.nChains, self.nScans, self.adaptFraction = nChains, nScans, adaptFraction
@@ -439,12 +452,14 @@ class PT:
     def performInference(self, want=("energy", "swapIndicators", "samples"), results=None):
         """PT.performInference (PT.java:85-113).  With `results` (a folder) the reference's samples/ and
         monitoring/ tables are written there, one batched write per round (blangsdk_b200/results.py)."""
-        if results is None:
+        if results is None and self.targetAccept is None:
             res = self.engine.perform_inference(self.nScans, self.adaptFraction, self.thinning, want)
             res["finalStats"] = self.engine.round_stats()
             res["ladder"] = self.engine.get_ladder()
             res["counters"] = self.engine.counters()
             return res
+        if results is None:
+            return self._perform_with_target_accept(want)
         import time
         from .results import PTResultsWriter
         eng = self.engine
@@ -469,3 +484,35 @@ class PT:
                     eng.adapt()
         w.close()
         return dict(rounds=summary, ladder=eng.get_ladder(), counters=eng.counters(), finalStats=eng.round_stats())
+
+    def _resize_to_target_accept(self):
+        """PT.adapt's targetAccept branch (PT.java:156-163): new ladder size from Lambda / (1 - targetAccept),
+        every chain re-initialised as a copy of the beta = 1 state."""
+        old = self.engine
+        ladder = old.target_accept_ladder(self.targetAccept)
+        reals, ints = old.get_state(0)
+        old.close()
+        self.nChains = len(ladder)
+        self.engine = Engine(nChains=self.nChains, nReplicas=1, **self._engine_kw)
+        self.engine.set_model(self._spec)
+        for c in range(self.nChains):
+            self.engine.set_state(c, reals if len(reals) else None, ints if len(ints) else None)
+        self.engine.set_ladder(ladder)
+        self.engine.initialize("COPIES")
+
+    def _perform_with_target_accept(self, want):
+        rs = rounds(self.nScans, self.adaptFraction if self.engine.N > 1 else 0.0)
+        outs, summary = [], []
+        for r, (n, is_adapt) in enumerate(rs):
+            out = self.engine.run_scans(n, want=want)
+            outs.append(out)
+            if self.engine.N > 1:
+                d = self.engine.diagnostics()
+                summary.append(dict(nScans=n, isAdapt=is_adapt, nChains=self.engine.N,
+                                    **{k: v for k, v in d.items() if np.isscalar(v)}))
+                if r == len(rs) - 2:
+                    self._resize_to_target_accept()
+                elif r + 1 < len(rs):
+                    self.engine.adapt()
+        return dict(rounds=summary, outputs=outs, ladder=self.engine.get_ladder(), counters=self.engine.counters(),
+                    finalStats=self.engine.round_stats())

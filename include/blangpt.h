@@ -194,6 +194,13 @@ typedef struct {
 } blangpt_diagnostics;
 int blangpt_get_diagnostics(blangpt_handle* h, int64_t replica, blangpt_diagnostics* out);
 
+/* PT.adapt with --engine.targetAccept (PT.java:156-163; EngineStaticUtils.targetAcceptancePartition :75-83,
+ * fixedSizeOptimalPartition :176-198): the ladder, RESIZED to max(2, int(Lambda / (1 - targetAccept))) points by
+ * Pegasus root finding on the cumulative-Lambda spline of the current round.  The caller then re-creates the
+ * engine with *n_out chains, every chain a copy of the beta = 1 state, as the reference does. */
+int blangpt_target_accept_ladder(blangpt_handle* h, int64_t replica, double targetAccept, double* out_desc,
+                                 int32_t capacity, int32_t* n_out);
+
 /* PT.rounds (PT.java:239-265).  Arrays sized >= 64.  Returns the number of rounds. */
 int blangpt_rounds(int32_t nScans, double adaptFraction, int32_t* round_nscans, int32_t* round_is_adapt);
 

@@ -302,8 +302,6 @@ def test_error_paths(datasets):
         eng.set_model(dict(family="poisson", hyper={}))
     eng.set_model(datasets.normal_meanvar(n=20))
     with pytest.raises(BlangPTError):
-        eng.initialize("SCM")
-    with pytest.raises(BlangPTError):
         eng.set_ladder([0.9, 0.5, 0.2, 0.0])   # must start at exactly 1.0
     with pytest.raises(BlangPTError):
         eng.set_state(9, [0.0, 1.0])
@@ -313,7 +311,25 @@ def test_error_paths(datasets):
     assert "NaN" in str(ei.value)
     eng.close()
     with pytest.raises(BlangPTError):
-        PT(targetAccept=0.5)
+        PT(targetAccept=1.5)
+
+
+def test_target_accept_resizes_the_ladder(datasets):
+    """--engine.targetAccept (PT.java:156-163): after the last adaptive round the ladder has
+    max(2, int(Lambda / (1 - target))) points, every chain restarts from the beta = 1 state, and the final
+    round's swap acceptance sits near the target."""
+    from blangsdk_b200.engine import PT
+    pt = PT(nChains=12, nScans=600, adaptFraction=0.5, random=6, initialization="FORWARD", targetAccept=0.6)
+    pt.setSampledModel(datasets.normal_meanvar(n=300))
+    res = pt.performInference(want=("energy",))
+    rs = res["rounds"]
+    lam = rs[-2]["Lambda"]
+    assert rs[-1]["nChains"] == max(2, int(lam / (1 - 0.6))) == pt.engine.N
+    lad = res["ladder"][0]
+    assert lad[0] == 1.0 and lad[-1] == 0.0 and np.all(np.diff(lad) < 0)
+    acc = res["finalStats"]["swapAcceptMean"][0]
+    assert abs(acc.mean() - 0.6) < 0.15
+    pt.engine.close()
 
 
 def test_logit_term_accuracy_and_support():
