@@ -380,7 +380,13 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
       if (K < 2 || K > 8) FAIL(h, BLANGPT_EUNSUPPORTED, "mixture: 2 <= K <= 8");
       double* y; if ((rc = dev_alloc(h, &y, n + 2))) return rc;
       CUDA_OK(h, cudaMemcpyAsync(y, a[0].data, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      h->mixture = {y, n, K, hyper[1], hyper[2], hyper[3], hyper[4], hyper[5]};
+      const int npad = (n + 1) & ~1;
+      const int64_t local = h->M_total / c.worldSize;
+      double *rest, *e1, *e2;
+      if ((rc = dev_alloc(h, &rest, (size_t)npad * local, false))) return rc;
+      if ((rc = dev_alloc(h, &e1, (size_t)npad * local, false))) return rc;
+      if ((rc = dev_alloc(h, &e2, (size_t)npad * local, false))) return rc;
+      h->mixture = {y, n, K, hyper[1], hyper[2], hyper[3], hyper[4], hyper[5], rest, e1, e2, npad};
       h->n_reals = 3 * K; h->n_samplers = 2 * K + 1; rows = n;
     } break;
     case BLANGPT_FAM_BETABINOMIAL: {
@@ -604,6 +610,11 @@ static int scm_initialize(blangpt_handle* h) {
   auto fail = [&](int code) { for (void* p : c->allocs) cudaFree(p); if (code) h->error = c->error; delete c; return code; };
   if (h->family == BLANGPT_FAM_LOGISTIC && (rc = dev_alloc(c, &c->logistic.eta, (size_t)c->logistic.npad * P))) return fail(rc);
   if (h->family == BLANGPT_FAM_ISING && (rc = dev_alloc(c, &c->ising.spins, (size_t)P * h->n_ints))) return fail(rc);
+  if (h->family == BLANGPT_FAM_MIXTURE) {
+    const size_t sz = (size_t)c->mixture.npad * P;
+    if ((rc = dev_alloc(c, &c->mixture.rest, sz, false)) || (rc = dev_alloc(c, &c->mixture.e1, sz, false)) ||
+        (rc = dev_alloc(c, &c->mixture.e2, sz, false))) return fail(rc);
+  }
   int64_t rows = h->family == BLANGPT_FAM_NORMAL ? h->normal.n : h->family == BLANGPT_FAM_LOGISTIC ? h->logistic.n
                : h->family == BLANGPT_FAM_MIXTURE ? h->mixture.n : 1;
   c->G = h->family == BLANGPT_FAM_ISING || h->family == BLANGPT_FAM_BETABINOMIAL ? 1 : pick_ctas_per_chain(c, rows);

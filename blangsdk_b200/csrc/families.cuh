@@ -238,6 +238,7 @@ struct NormalFam {
   BPT_D int sampler_type(int) const { return S_REAL_SLICE; }
   BPT_D int sampler_var(int k) const { return k; }
   BPT_D int simplex_dim() const { return 0; }
+  BPT_D void begin_execution() {}
   BPT_D double fixed(int k, double x, int) const {
     return k == 0 ? normal_f2(d.m0, d.v0, x) : gamma_ab(1.0, d.rate, x);   // Exponential.bl:11 -> Gamma(1.0, rate)
   }
@@ -311,6 +312,7 @@ struct LogisticFamT {
   BPT_D int sampler_type(int) const { return S_REAL_SLICE; }
   BPT_D int sampler_var(int k) const { return k; }
   BPT_D int simplex_dim() const { return 0; }
+  BPT_D void begin_execution() {}
   BPT_D double fixed(int, double x, int) const { return normal_f2(0.0, d.v0, x); }
 
   // Bernoulli.bl:11-14 -> Categorical.bl:12-15 with p = logistic(eta).  See logit_term() above.
@@ -401,16 +403,25 @@ struct MixtureFam {
   struct Data {
     const double* y; int n; int K;
     double m0, v0, gshape, grate, conc;
+    // per-chain scratch in HBM, [localSlots][npad] each: within one sampler execution only one component
+    // (or the two simplex entries) changes, so the first evaluation stores the sum of the OTHER components'
+    // terms per observation and the remaining ~8 evaluations need one exp (or none) + one log per row
+    double* rest; double* e1; double* e2; int npad;
   };
   static constexpr int kThreads = 512;
   static constexpr bool kWarpCapable = false;
   Data d; double* P; double* Cst; RowRange rr; int* err;   // Cst: [4][KT] per-evaluation component constants
+  double *rest, *e1, *e2;
+  bool first;   // next annealed() call is the first of a sampler execution
 
   BPT_D static int n_reals(const Data& d) { return 3 * d.K; }
   BPT_D static int n_samplers(const Data& d) { return 2 * d.K + 1; }
-  BPT_D void init(const Data& d_, int, double* P_, int G, int crank, int* err_) {
+  BPT_D void init(const Data& d_, int local_slot, double* P_, int G, int crank, int* err_) {
     d = d_; P = P_; Cst = P_ + kMaxParams; rr = group_rows(d.n, G, crank); err = err_;
+    rest = d.rest + (size_t)local_slot * d.npad; e1 = d.e1 + (size_t)local_slot * d.npad;
+    e2 = d.e2 + (size_t)local_slot * d.npad; first = true;
   }
+  BPT_D void begin_execution() { first = true; }
   BPT_D int sampler_type(int k) const { return k == 2 * d.K ? S_SIMPLEX : S_REAL_SLICE; }
   BPT_D int sampler_var(int k) const { return k; }
   BPT_D int simplex_dim() const { return d.K; }
@@ -495,10 +506,119 @@ struct MixtureFam {
     }
     if (((rr.hi - rr.lo) & 1) && threadIdx.x == 0) obs_term(d.y[rr.hi - 1], mu, a, b, pi, s, c);
   }
+  // First evaluation of a sampler execution (always at the current state): every component is evaluated, and
+  // per observation the sum R of the components the sampler does NOT move is stored (plus, for the simplex
+  // sampler, the two moved components' unweighted densities).  j0 / j1 = moved components (j1 = -1 if one).
+  __device__ __noinline__ void pass_first(int j0, int j1, double& s, int& c) const {
+    double mu[KT], a[KT], b[KT], pi[KT];
+#pragma unroll
+    for (int q = 0; q < KT; q++) { mu[q] = Cst[q]; a[q] = Cst[KT + q]; b[q] = Cst[2 * KT + q]; pi[q] = Cst[3 * KT + q]; }
+    auto one = [&](double yv, double& r_out, double& e1_out, double& e2_out) {
+      double R = 0.0, M = 0.0, E1 = 0.0, E2 = 0.0;
+#pragma unroll
+      for (int q0 = 0; q0 < KT; q0 += 4) {
+        double arg[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const double dd = mu[q0 + q] - yv; arg[q] = fmax(fma(b[q0 + q], dd * dd, a[q0 + q]), -700.0); }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const double e = exp_lean(arg[q]);
+          const bool moved = (q0 + q == j0) || (q0 + q == j1);
+          if (q0 + q == j0) E1 = e;
+          if (q0 + q == j1) E2 = e;
+          if (moved) M = fma(pi[q0 + q], e, M); else R = fma(pi[q0 + q], e, R);
+        }
+      }
+      const double S = R + M;
+      if (S > 1e-250 && S < 1e250) { s += log_lean(S); r_out = R; }
+      else { obs_slow(yv, mu, a, b, pi, s, c); r_out = CUDART_NAN; }   // NaN marks a row the cached passes redo literally
+      e1_out = E1; e2_out = E2;
+    };
+    const int n_pairs = (rr.hi - rr.lo) >> 1;
+    for (int p = threadIdx.x; p < n_pairs; p += blockDim.x) {
+      const int i = rr.lo + 2 * p;
+      const double2 v = *reinterpret_cast<const double2*>(d.y + i);
+      double2 r, x1, x2;
+      one(v.x, r.x, x1.x, x2.x); one(v.y, r.y, x1.y, x2.y);
+      *reinterpret_cast<double2*>(rest + i) = r;
+      if (j1 >= 0) { *reinterpret_cast<double2*>(e1 + i) = x1; *reinterpret_cast<double2*>(e2 + i) = x2; }
+    }
+    if (((rr.hi - rr.lo) & 1) && threadIdx.x == 0) {
+      const int i = rr.hi - 1;
+      double r, x1, x2;
+      one(d.y[i], r, x1, x2);
+      rest[i] = r; if (j1 >= 0) { e1[i] = x1; e2[i] = x2; }
+    }
+  }
+  // Remaining evaluations of the execution: S_i = R_i + (moved terms at the candidate).  One exp + one log per
+  // row for a mean/variance move (SIMPLEX = false), no exp at all for a simplex move; 16 (or 32) bytes per row
+  // streamed from HBM with no reuse inside an evaluation, so kB pairs per thread are in flight and the next kB
+  // already requested while the current ones are evaluated (the pass is latency-, not bandwidth-bound).
+  template <bool SIMPLEX, int kB>
+  __device__ __noinline__ void pass_cached(int j0, int j1, double& s, int& c) const {
+    const double mu0 = Cst[j0], a0 = Cst[KT + j0], b0 = Cst[2 * KT + j0], pi0 = Cst[3 * KT + j0];
+    const double pi1 = SIMPLEX ? Cst[3 * KT + j1] : 0.0;
+    auto slow = [&](double yv) {
+      double mu[KT], a[KT], b[KT], pi[KT];
+#pragma unroll
+      for (int q = 0; q < KT; q++) { mu[q] = Cst[q]; a[q] = Cst[KT + q]; b[q] = Cst[2 * KT + q]; pi[q] = Cst[3 * KT + q]; }
+      obs_slow(yv, mu, a, b, pi, s, c);
+    };
+    auto one = [&](double yv, double R, double E1, double E2) {
+      double S;
+      if (!SIMPLEX) { const double dd = mu0 - yv; S = fma(pi0, exp_lean(fmax(fma(b0, dd * dd, a0), -700.0)), R); }
+      else S = fma(pi0, E1, fma(pi1, E2, R));
+      if (S > 1e-250 && S < 1e250) s += log_lean(S);
+      else slow(yv);
+    };
+    const int n_pairs = (rr.hi - rr.lo) >> 1;
+    const int stride = blockDim.x;
+    int p = threadIdx.x;
+    double2 vn[kB], rn[kB], an[SIMPLEX ? kB : 1], bn[SIMPLEX ? kB : 1];
+    auto load = [&](int pp) {
+#pragma unroll
+      for (int u = 0; u < kB; u++) {
+        const int q = pp + u * stride;
+        if (q < n_pairs) {
+          const int i = rr.lo + 2 * q;
+          vn[u] = *reinterpret_cast<const double2*>(d.y + i); rn[u] = __ldcs(reinterpret_cast<const double2*>(rest + i));
+          if (SIMPLEX) { an[u] = __ldcs(reinterpret_cast<const double2*>(e1 + i)); bn[u] = __ldcs(reinterpret_cast<const double2*>(e2 + i)); }
+        }
+      }
+    };
+#pragma unroll
+    for (int u = 0; u < kB; u++) { vn[u] = make_double2(0.0, 0.0); rn[u] = vn[u]; }
+    an[0] = make_double2(0.0, 0.0); bn[0] = an[0];
+    if (p < n_pairs) load(p);
+    while (p < n_pairs) {
+      double2 v[kB], r[kB], x1[SIMPLEX ? kB : 1], x2[SIMPLEX ? kB : 1];
+#pragma unroll
+      for (int u = 0; u < kB; u++) { v[u] = vn[u]; r[u] = rn[u]; if (SIMPLEX) { x1[u] = an[u]; x2[u] = bn[u]; } }
+      if (!SIMPLEX) { x1[0] = an[0]; x2[0] = bn[0]; }
+      const int cur = p;
+      p += kB * stride;
+      if (p < n_pairs) load(p);
+#pragma unroll
+      for (int u = 0; u < kB; u++)
+        if (cur + u * stride < n_pairs) {
+          const int w = SIMPLEX ? u : 0;
+          one(v[u].x, r[u].x, x1[w].x, x2[w].x); one(v[u].y, r[u].y, x1[w].y, x2[w].y);
+        }
+    }
+    if (((rr.hi - rr.lo) & 1) && threadIdx.x == 0) {
+      const int i = rr.hi - 1;
+      one(d.y[i], rest[i], SIMPLEX ? e1[i] : 0.0, SIMPLEX ? e2[i] : 0.0);
+    }
+  }
   BPT_D void annealed(int k, double x, int aux, GroupReducer& red, double& s, int& c) {
+    const int K = d.K;
+    const int j0 = k < K ? k : (k < 2 * K ? k - K : aux);
+    const int j1 = k < 2 * K ? -1 : (aux == K - 1 ? 0 : aux + 1);
     stage_constants(k, x, aux);
     double acc = 0.0; int cnt = 0;
-    sum_obs(acc, cnt);
+    if (first) { pass_first(j0, j1, acc, cnt); first = false; }
+    else if (j1 < 0) pass_cached<false, 4>(j0, j1, acc, cnt);
+    else pass_cached<true, 2>(j0, j1, acc, cnt);
     red.reduce(acc, cnt);
     s = acc; c = cnt;
   }
@@ -585,6 +705,7 @@ struct BetaBinomialFam {
   BPT_D int sampler_type(int) const { return S_REAL_SLICE; }
   BPT_D int sampler_var(int k) const { return k; }
   BPT_D int simplex_dim() const { return 0; }
+  BPT_D void begin_execution() {}
   BPT_D double fixed(int, double x, int) const { return gamma_ab(1.0, d.rate, x); }
   BPT_D void sum_groups(double a, double b, double& s, int& c) const {
     if (a <= 0.0 || b <= 0.0) {

@@ -146,6 +146,7 @@ BPT_D void explore_chain(const DevEngine& E, Fam& fam, GroupReducer& red, double
           curpos = S - 1;
         }
         const int k = order[curpos--];
+        fam.begin_execution();
         Rng rng(E.key0, key1, P_MOVE, (uint32_t)pos, scan, (uint32_t)t);
         int aux = 0;
         typename Sync::template LogDensityOf<Fam> lp{{E, fam, red, k, aux, beta, evals, err}};

@@ -48,6 +48,9 @@ if __name__ == "__main__":
         run("C1 normal 1000 obs, 8 chains", D.normal_meanvar(), 8, scans=200, warm=20, algo_bytes=8000)
     if "C2" in which:
         run("C2 logistic 100k x 32, 64 chains", D.logistic_regression(), 64, init="COPIES", scans=10, algo_bytes=25_700_000)
+    if "C2x1024" in which:   # north_star target regime: >= 1024 chains, eta cache (819 MB) streams from HBM
+        run("C2 logistic 100k x 32, 1024 chains on one GPU", D.logistic_regression(), 1024, init="COPIES", scans=2, warm=2,
+            algo_bytes=25_700_000)
     if "C3" in which:
         run("C3 mixture K=4 1M obs, 256 chains", D.gaussian_mixture(), 256, init="COPIES", scans=2, warm=1, algo_bytes=8_000_000)
     if "C4" in which:
