@@ -1142,6 +1142,8 @@ __global__ void mb_logit_kernel(double* out, int iters) {
   __shared__ int serr;
   double z0 = -3.0 + 9.0 * threadIdx.x / blockDim.x, z1 = 1.0 - z0, acc = 0.0; int cnt = 0;
   __shared__ uint8_t sy[2];
+  logit_table_init();
+  __syncthreads();
   for (int i = 0; i < iters; i++) {
     logit_pair(z0, z1, sy, acc, cnt, &serr);
     z0 += 1e-6; z1 -= 1e-6;
@@ -1200,6 +1202,8 @@ extern "C" int blangpt_microbench(int32_t device, int32_t which, double* out_rat
 __global__ void debug_logit_kernel(const double* z, const int* y, int n, double* out) {
   __shared__ int serr;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  logit_table_init();
+  __syncthreads();
   if (i >= n) return;
   double s = 0.0; int c = 0;
   const uint8_t yb = (uint8_t)y[i];

@@ -71,10 +71,41 @@ __constant__ double kLogitK[7] = {
     -1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
     -0.41421356237309514547, 2.41421356237309514547, 0.34657359027997269783};
 
+// log(u) for u in (1, 2] by table: u = c_j (1 + r) with c_j the centre of the j-th of 32 mantissa intervals,
+// r = u * (1/c_j) - 1, |r| <= 1/64, log u = log c_j + log1p(r) (8-term series).  No reciprocal, 11 fp64
+// instructions instead of 21.  Entry j = {fl(1/c_j), log(1/fl(1/c_j))}: the second is the log of the value
+// the kernel really multiplies by (computed in 50-digit arithmetic), so the identity is exact up to rounding.
+__constant__ double2 kLogTabC[32] = {
+    {0.9846153846153847, 0.015504186535965199}, {0.9552238805970149, 0.04580953603129422},
+    {0.927536231884058, 0.07522342123758752},   {0.9014084507042254, 0.10379679368164355},
+    {0.8767123287671232, 0.13157635778871932},  {0.8533333333333334, 0.15860503017663852},
+    {0.8311688311688312, 0.18492233849401193},  {0.810126582278481, 0.21056476910734964},
+    {0.7901234567901234, 0.23556607131276697},  {0.7710843373493976, 0.259957524436926},
+    {0.7529411764705882, 0.2837681731306446},   {0.735632183908046, 0.3070250352949119},
+    {0.7191011235955056, 0.32975328637246804},  {0.7032967032967034, 0.3519764231571781},
+    {0.6881720430107527, 0.373716409793584},    {0.6736842105263158, 0.394993808240869},
+    {0.6597938144329897, 0.415827895143711},    {0.6464646464646465, 0.43623676677491796},
+    {0.6336633663366337, 0.4562374334815876},   {0.6213592233009708, 0.475845904869964},
+    {0.6095238095238096, 0.4950772667978514},   {0.5981308411214953, 0.5139457511022344},
+    {0.5871559633027523, 0.5324647988694717},   {0.5765765765765766, 0.5506471179526623},
+    {0.5663716814159292, 0.5685047353526688},   {0.5565217391304348, 0.5860490450035782},
+    {0.5470085470085471, 0.6032908514380841},   {0.5378151260504201, 0.6202404097518576},
+    {0.5289256198347108, 0.6369074622370692},   {0.5203252032520326, 0.6533012720127456},
+    {0.512, 0.6694306539426292},                {0.5039370078740157, 0.6853040030989195}};
+__constant__ double kLog1pC[7] = {   // -1/8, 1/7, -1/6, 1/5, -1/4, 1/3, -1/2
+    -0.125, 1.42857142857142857143e-01, -1.66666666666666666667e-01, 0.2, -0.25, 3.33333333333333333333e-01, -0.5};
+
+// the table lives in shared memory (lanes index it with different j); one copy per CTA, filled once
+BPT_D double2* logit_table() { __shared__ double2 tab[32]; return tab; }
+BPT_D void logit_table_init() {   // call before the first __syncthreads() of the kernel
+  if (threadIdx.x < 32) logit_table()[threadIdx.x] = kLogTabC[threadIdx.x];
+}
+
 // W independent lanes evaluated together: min(z,0) - log1p(exp(-|z|)) for -12 <= z, |z| < 700.
-// Straight-line code; the W Horner chains interleave (ILP) and share every coefficient load.
+// Straight-line code; the W chains interleave (ILP) and share every coefficient load.
 template <int W>
 BPT_D void logit_fast(const double (&z)[W], double& s) {
+  const double2* tab = logit_table();
   double kd[W], r[W], p[W]; int k[W];
 #pragma unroll
   for (int w = 0; w < W; w++) {
@@ -90,31 +121,26 @@ BPT_D void logit_fast(const double (&z)[W], double& s) {
   for (int i = 1; i < 12; i++)
 #pragma unroll
     for (int w = 0; w < W; w++) p[w] = fma(p[w], r[w], kExpC[i]);
-  double f[W], f2[W], q[W];
+  double q[W], rr[W], lc[W];
 #pragma unroll
   for (int w = 0; w < W; w++) {
-    // t = exp(-|z|) = p * 2^k in (0, 1]
+    // t = exp(-|z|) = p * 2^k in (0, 1];  u = 1 + t in (1, 2]
     const double t = __hiloint2double(__double2hiint(p[w]) + (k[w] << 20), __double2loint(p[w]));
-    // log(1+t) = log C + 2 atanh(f), f = (1+t-C)/(1+t+C), |f| <= 0.1716
-    const double num = t + kLogitK[4];
-    const double den = t + kLogitK[5];
-    double rc;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(den));
-    double e = fma(-den, rc, 1.0); rc = fma(rc, e, rc);
-    e = fma(-den, rc, 1.0); rc = fma(rc, e, rc);
-    f[w] = num * rc;
-    f2[w] = f[w] * f[w];
-    q[w] = kAtanhC[0];
+    const double u = 1.0 + t;
+    const int j = min(31, (__double2hiint(u) - 0x3ff00000) >> 15);
+    const double2 cj = tab[j];
+    rr[w] = fma(u, cj.x, -1.0);
+    lc[w] = cj.y;
+    q[w] = kLog1pC[0];
   }
 #pragma unroll
-  for (int i = 1; i < 8; i++)
+  for (int i = 1; i < 7; i++)
 #pragma unroll
-    for (int w = 0; w < W; w++) q[w] = fma(q[w], f2[w], kAtanhC[i]);
+    for (int w = 0; w < W; w++) q[w] = fma(q[w], rr[w], kLog1pC[i]);
 #pragma unroll
   for (int w = 0; w < W; w++) {
-    const double s1 = f[w] + f[w];
-    const double l = fma(s1 * f2[w], q[w], s1 + kLogitK[6]);
-    s += fma(0.5, z[w] - fabs(z[w]), -l);       // min(z,0) - log1p(exp(-|z|))
+    const double l = fma(rr[w] * rr[w], q[w], rr[w]) + lc[w];     // log1p(exp(-|z|))
+    s += fma(0.5, z[w] - fabs(z[w]), -l);                           // min(z,0) - log1p(exp(-|z|))
   }
 }
 BPT_D bool logit_is_fast(double zs) { return zs >= -12.0 && fabs(zs) < 700.0; }
@@ -239,6 +265,7 @@ struct NormalFam {
   BPT_D int sampler_var(int k) const { return k; }
   BPT_D int simplex_dim() const { return 0; }
   BPT_D void begin_execution() {}
+  BPT_D static void tables_init() {}
   BPT_D double fixed(int k, double x, int) const {
     return k == 0 ? normal_f2(d.m0, d.v0, x) : gamma_ab(1.0, d.rate, x);   // Exponential.bl:11 -> Gamma(1.0, rate)
   }
@@ -313,6 +340,7 @@ struct LogisticFamT {
   BPT_D int sampler_var(int k) const { return k; }
   BPT_D int simplex_dim() const { return 0; }
   BPT_D void begin_execution() {}
+  BPT_D static void tables_init() { logit_table_init(); }
   BPT_D double fixed(int, double x, int) const { return normal_f2(0.0, d.v0, x); }
 
   // Bernoulli.bl:11-14 -> Categorical.bl:12-15 with p = logistic(eta).  See logit_term() above.
@@ -422,6 +450,7 @@ struct MixtureFam {
     e2 = d.e2 + (size_t)local_slot * d.npad; first = true;
   }
   BPT_D void begin_execution() { first = true; }
+  BPT_D static void tables_init() {}
   BPT_D int sampler_type(int k) const { return k == 2 * d.K ? S_SIMPLEX : S_REAL_SLICE; }
   BPT_D int sampler_var(int k) const { return k; }
   BPT_D int simplex_dim() const { return d.K; }
@@ -706,6 +735,7 @@ struct BetaBinomialFam {
   BPT_D int sampler_var(int k) const { return k; }
   BPT_D int simplex_dim() const { return 0; }
   BPT_D void begin_execution() {}
+  BPT_D static void tables_init() {}
   BPT_D double fixed(int, double x, int) const { return gamma_ab(1.0, d.rate, x); }
   BPT_D void sum_groups(double a, double b, double& s, int& c) const {
     if (a <= 0.0 || b <= 0.0) {

@@ -195,6 +195,7 @@ explore_kernel(DevEngine E, typename Fam::Data D, int G, int mode) {
   for (int v = tid; v < nR; v += blockDim.x) P[v] = E.reals[(size_t)v * E.M_local + l];
   for (int k = tid; k < S; k += blockDim.x) order[k] = E.order[(size_t)l * E.s_max + k];
   int curpos = E.curpos[l];
+  Fam::tables_init();
   __syncthreads();
 
   GroupReducer red;
