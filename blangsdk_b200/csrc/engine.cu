@@ -444,6 +444,7 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
 extern "C" int blangpt_set_ladder(blangpt_handle* h, const double* betas, int64_t n) {
   if (!h || !betas) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   const int N = h->cfg.nChains, R = h->cfg.nReplicas;
   if (n != N && n != (int64_t)N * R) FAIL(h, BLANGPT_EINVAL, "ladder length must be nChains or nReplicas*nChains");
   for (int r = 0; r < R; r++) {
@@ -482,6 +483,7 @@ static int slot_of(blangpt_handle* h, int64_t replica, int position, int* local)
 extern "C" int blangpt_set_state(blangpt_handle* h, int64_t replica, int32_t position, const double* reals, const int32_t* ints) {
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   int l, rc;
   if ((rc = slot_of(h, replica, position, &l))) return rc;
   if (reals && h->n_reals)
@@ -502,6 +504,7 @@ extern "C" int blangpt_set_state(blangpt_handle* h, int64_t replica, int32_t pos
 extern "C" int blangpt_get_state(blangpt_handle* h, int64_t replica, int32_t position, double* reals, int32_t* ints) {
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   int l, rc;
   if ((rc = slot_of(h, replica, position, &l))) return rc;
   if (reals && h->n_reals)
@@ -718,6 +721,7 @@ extern "C" int blangpt_scm_summary(const blangpt_handle* h, double* logNormEstim
 extern "C" int blangpt_initialize(blangpt_handle* h, int32_t init_type) {
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   if (init_type == BLANGPT_INIT_SCM) return scm_initialize(h);
   if (init_type == BLANGPT_INIT_COPIES) { h->tables_valid = false; return ensure_tables(h); }
   if (init_type != BLANGPT_INIT_FORWARD) FAIL(h, BLANGPT_EINVAL, "unknown initialization");
@@ -735,6 +739,7 @@ extern "C" int blangpt_initialize(blangpt_handle* h, int32_t init_type) {
 extern "C" int blangpt_log_density(blangpt_handle* h, double* out_logdens, double* out_loglik, int32_t* out_noos, double* out_fixed) {
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   if (h->cfg.worldSize > 1) FAIL(h, BLANGPT_EUNSUPPORTED, "log_density is a single-process call; with worldSize > 1 gather the table (blangpt_table_ptr)");
   h->tables_valid = false;
   int rc = ensure_tables(h);
@@ -761,6 +766,7 @@ extern "C" int blangpt_log_density(blangpt_handle* h, double* out_logdens, doubl
 extern "C" int blangpt_run_scans(blangpt_handle* h, int32_t n_scans, const blangpt_scan_outputs* out) {
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   if (h->cfg.worldSize > 1) FAIL(h, BLANGPT_EINVAL, "run_scans is the single-GPU path; use blangpt_explore / blangpt_swap with worldSize > 1");
   if (n_scans <= 0) return BLANGPT_OK;
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
@@ -831,6 +837,7 @@ extern "C" int blangpt_run_scans(blangpt_handle* h, int32_t n_scans, const blang
 extern "C" int blangpt_get_round_stats(blangpt_handle* h, blangpt_round_stats* o) {
   if (!h || !o) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   const int64_t M = h->M_total; const int N = h->cfg.nChains, R = h->cfg.nReplicas;
   std::vector<long long> en_n(M), acc_n(M), ls_n(M); std::vector<double> en_m1(M), en_m2(M), cov_c(M), acc_m1(M), ls_sum(M);
   std::vector<int> cov_n(M), oos_seen(R); std::vector<unsigned long long> rej(R); std::vector<double> tab(M * 4);
@@ -880,12 +887,14 @@ extern "C" int blangpt_get_round_stats(blangpt_handle* h, blangpt_round_stats* o
 extern "C" int blangpt_reset_round(blangpt_handle* h) {
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   return reset_round(h);
 }
 
 extern "C" int blangpt_adapt(blangpt_handle* h, double* cum_xy) {
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   const int64_t M = h->M_total; const int N = h->cfg.nChains, R = h->cfg.nReplicas;
   if (N < 2) return reset_round(h);
   std::vector<long long> acc_n(M); std::vector<double> acc_m1(M);
@@ -922,6 +931,7 @@ extern "C" int blangpt_target_accept_ladder(blangpt_handle* h, int64_t replica, 
                                             int32_t capacity, int32_t* n_out) {
   if (!h || !out_desc || !n_out) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   const int N = h->cfg.nChains;
   if (N < 2 || replica < 0 || replica >= h->cfg.nReplicas) FAIL(h, BLANGPT_EINVAL, "bad replica / single chain");
   if (!(targetAccept >= 0.0 && targetAccept < 1.0)) FAIL(h, BLANGPT_EINVAL, "targetAccept must be in [0,1)");
@@ -958,6 +968,7 @@ extern "C" int blangpt_make_ladder(int32_t kind, int32_t nChains, double param, 
 extern "C" int blangpt_get_diagnostics(blangpt_handle* h, int64_t replica, blangpt_diagnostics* d) {
   if (!h || !d) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   const int N = h->cfg.nChains, R = h->cfg.nReplicas; const int64_t M = h->M_total;
   if (replica < 0 || replica >= R) FAIL(h, BLANGPT_EINVAL, "replica out of range");
   if (N < 2) FAIL(h, BLANGPT_EINVAL, "PT diagnostics need at least two chains (PT.java:102)");
@@ -1010,6 +1021,7 @@ extern "C" int blangpt_perform_inference(blangpt_handle* h, int32_t nScans, doub
                                          const blangpt_scan_outputs* out, blangpt_inference_summary* sum) {
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   if (adaptFraction < 0.0 || adaptFraction >= 1.0) FAIL(h, BLANGPT_EINVAL, "adaptFraction must be in [0,1)");
   (void)thinning;   // samples are recorded every scan; thinning is applied by the writer
   const int N = h->cfg.nChains, R = h->cfg.nReplicas; const int64_t M = h->M_total;
@@ -1087,6 +1099,7 @@ extern "C" int blangpt_evaluate(blangpt_handle* h) {
 extern "C" int blangpt_prime(blangpt_handle* h) {
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   prime_prev_kernel<<<(unsigned)((h->M_total + 255) / 256), 256, 0, h->stream>>>(h->E, h->St);
   CUDA_OK(h, cudaGetLastError());
   h->n_launches++;
@@ -1096,6 +1109,7 @@ extern "C" int blangpt_prime(blangpt_handle* h) {
 extern "C" int blangpt_explore(blangpt_handle* h) {
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   if (!h->tables_valid) FAIL(h, BLANGPT_ESTATE, "call blangpt_evaluate, gather the table and blangpt_prime before the first blangpt_explore");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   return launch_explore(h, MODE_EXPLORE);
@@ -1112,6 +1126,7 @@ extern "C" int64_t blangpt_local_chains(const blangpt_handle* h, int64_t* first)
 extern "C" int blangpt_swap(blangpt_handle* h, const blangpt_scan_outputs* out) {
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
   (void)out;
   CUDA_OK(h, cudaMemsetAsync(h->E.batch_counter, 0, sizeof(uint32_t) * h->cfg.nReplicas, h->stream));
   DevOut O{}; O.n_reals = h->n_reals; O.reversible = h->cfg.reversible;

@@ -129,13 +129,11 @@ __global__ void ising_record_kernel(DevEngine E, IsingData D, uint8_t* out, int 
 
 inline int ising_launch(const DevEngine& E, const IsingData& D, int mode, cudaStream_t stream) {
   const size_t smem = (size_t)D.N * D.N;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {   // per device: set on every launch (cheap) rather than remembering which devices have it
     cudaError_t e = cudaFuncSetAttribute(ising_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
-  if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
   const int threads = D.N * D.N / 2 >= kIsingThreads ? kIsingThreads : std::max(32, ((D.N * D.N / 2 + 31) / 32) * 32);
   ising_kernel<<<E.M_local, threads, smem, stream>>>(E, D, mode);
   return (int)cudaGetLastError();
