@@ -96,16 +96,20 @@ __constant__ double kLog1pC[7] = {   // -1/8, 1/7, -1/6, 1/5, -1/4, 1/3, -1/2
     -0.125, 1.42857142857142857143e-01, -1.66666666666666666667e-01, 0.2, -0.25, 3.33333333333333333333e-01, -0.5};
 
 // the table lives in shared memory (lanes index it with different j); one copy per CTA, filled once
-BPT_D double2* logit_table() { __shared__ double2 tab[32]; return tab; }
+__shared__ double2 s_logit_tab[32];
 BPT_D void logit_table_init() {   // call before the first __syncthreads() of the kernel
-  if (threadIdx.x < 32) logit_table()[threadIdx.x] = kLogTabC[threadIdx.x];
+  if (threadIdx.x < 32) s_logit_tab[threadIdx.x] = kLogTabC[threadIdx.x];
 }
 
 // W independent lanes evaluated together: min(z,0) - log1p(exp(-|z|)) for -12 <= z, |z| < 700.
 // Straight-line code; the W chains interleave (ILP) and share every coefficient load.
+BPT_D uint32_t logit_table_address() {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(s_logit_tab);
+  asm volatile("" : "+r"(a));   // opaque: keeps the address in a register instead of re-deriving it per use
+  return a;
+}
 template <int W>
-BPT_D void logit_fast(const double (&z)[W], double& s) {
-  const double2* tab = logit_table();
+BPT_D void logit_fast(const double (&z)[W], double& s, uint32_t tab) {
   double kd[W], r[W], p[W]; int k[W];
 #pragma unroll
   for (int w = 0; w < W; w++) {
@@ -127,8 +131,10 @@ BPT_D void logit_fast(const double (&z)[W], double& s) {
     // t = exp(-|z|) = p * 2^k in (0, 1];  u = 1 + t in (1, 2]
     const double t = __hiloint2double(__double2hiint(p[w]) + (k[w] << 20), __double2loint(p[w]));
     const double u = 1.0 + t;
-    const int j = min(31, (__double2hiint(u) - 0x3ff00000) >> 15);
-    const double2 cj = tab[j];
+    // unsigned: an out-of-range u (callers may evaluate rows they will discard) still indexes the table
+    const unsigned j = min(31u, (unsigned)(__double2hiint(u) - 0x3ff00000) >> 15);
+    double2 cj;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cj.x), "=d"(cj.y) : "r"(tab + (j << 4)));
     rr[w] = fma(u, cj.x, -1.0);
     lc[w] = cj.y;
     q[w] = kLog1pC[0];
@@ -155,11 +161,19 @@ BPT_D void logit_slow(double zs, const uint8_t* yp, double& s, int& c, int* err)
 }
 // zs = sign-folded margin (y ? z : -z); *yp is only read on the rare literal path
 BPT_D void logit_term(double zs, const uint8_t* yp, double& s, int& c, int* err) {
-  if (logit_is_fast(zs)) { const double z[1] = {zs}; logit_fast<1>(z, s); }
+  if (logit_is_fast(zs)) { const double z[1] = {zs}; logit_fast<1>(z, s, logit_table_address()); }
   else logit_slow(zs, yp, s, c, err);
 }
-BPT_D void logit_pair(double za, double zb, const uint8_t* yp, double& s, int& c, int* err) {
-  if (logit_is_fast(za) && logit_is_fast(zb)) { const double z[2] = {za, zb}; logit_fast<2>(z, s); }
+// Two rows.  The lean arithmetic runs unconditionally (straight-line, no divergence bookkeeping on the hot
+// path); its result is kept when both rows are in its range, which one warp vote decides for all lanes that
+// are here together.  Otherwise each row is redone on its own path.
+BPT_D void logit_pair(double za, double zb, const uint8_t* yp, double& s, int& c, int* err, uint32_t tab) {
+  const bool ok = logit_is_fast(za) && logit_is_fast(zb);
+  const double z[2] = {za, zb};
+  double t = s;
+  logit_fast<2>(z, t, tab);
+  if (__all_sync(__activemask(), ok)) { s = t; return; }
+  if (ok) s = t;
   else { logit_term(za, yp, s, c, err); logit_term(zb, yp + 1, s, c, err); }
 }
 
@@ -356,14 +370,19 @@ struct LogisticFamT {
     const double2* px = reinterpret_cast<const double2*>(d.xt + (size_t)k * d.npad + rr.lo) + threadIdx.x;
     const uint8_t* py = d.y + rr.lo + 2 * threadIdx.x;
     int left = n_pairs - (int)threadIdx.x;          // pairs this thread still has to do (stride THREADS)
-    double2 en = make_double2(0.0, 0.0), xn = en;
-    if (left > 0) { en = *pe; xn = *px; }
+    const uint32_t tab = logit_table_address();
+    // two register sets alternate between "being evaluated" and "being loaded" (no copies between them)
+    double2 ea = make_double2(0.0, 0.0), xa = ea, eb = ea, xb = ea;
+    if (left > 0) { ea = *pe; xa = *px; }
     while (left > 0) {
-      const double2 e = en, xv = xn;
-      left -= THREADS; pe += THREADS; px += THREADS;
-      if (left > 0) { en = *pe; xn = *px; }
-      logit_pair(fma(delta, xv.x, e.x), fma(delta, xv.y, e.y), py, acc, cnt, err);
-      py += 2 * THREADS;
+      left -= THREADS;
+      if (left > 0) { eb = pe[THREADS]; xb = px[THREADS]; }
+      logit_pair(fma(delta, xa.x, ea.x), fma(delta, xa.y, ea.y), py, acc, cnt, err, tab);
+      if (left <= 0) break;
+      left -= THREADS; pe += 2 * THREADS; px += 2 * THREADS;
+      if (left > 0) { ea = *pe; xa = *px; }
+      logit_pair(fma(delta, xb.x, eb.x), fma(delta, xb.y, eb.y), py + 2 * THREADS, acc, cnt, err, tab);
+      py += 4 * THREADS;
     }
     if (((rr.hi - rr.lo) & 1) && threadIdx.x == 0) {   // odd tail row of this CTA's range
       const int i = rr.hi - 1;
