@@ -1160,7 +1160,7 @@ __global__ void mb_logit_kernel(double* out, int iters) {
   logit_table_init();
   __syncthreads();
   for (int i = 0; i < iters; i++) {
-    logit_pair(z0, z1, sy, acc, cnt, &serr, logit_table_address());
+    logit_pair<false>(z0, z1, sy, acc, cnt, &serr, logit_table_address());
     z0 += 1e-6; z1 -= 1e-6;
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc + cnt;

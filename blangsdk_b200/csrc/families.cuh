@@ -71,78 +71,152 @@ __constant__ double kLogitK[7] = {
     -1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
     -0.41421356237309514547, 2.41421356237309514547, 0.34657359027997269783};
 
-// log(u) for u in (1, 2] by table: u = c_j (1 + r) with c_j the centre of the j-th of 32 mantissa intervals,
-// r = u * (1/c_j) - 1, |r| <= 1/64, log u = log c_j + log1p(r) (8-term series).  No reciprocal, 11 fp64
-// instructions instead of 21.  Entry j = {fl(1/c_j), log(1/fl(1/c_j))}: the second is the log of the value
-// the kernel really multiplies by (computed in 50-digit arithmetic), so the identity is exact up to rounding.
-__constant__ double2 kLogTabC[32] = {
-    {0.9846153846153847, 0.015504186535965199}, {0.9552238805970149, 0.04580953603129422},
-    {0.927536231884058, 0.07522342123758752},   {0.9014084507042254, 0.10379679368164355},
-    {0.8767123287671232, 0.13157635778871932},  {0.8533333333333334, 0.15860503017663852},
-    {0.8311688311688312, 0.18492233849401193},  {0.810126582278481, 0.21056476910734964},
-    {0.7901234567901234, 0.23556607131276697},  {0.7710843373493976, 0.259957524436926},
-    {0.7529411764705882, 0.2837681731306446},   {0.735632183908046, 0.3070250352949119},
-    {0.7191011235955056, 0.32975328637246804},  {0.7032967032967034, 0.3519764231571781},
-    {0.6881720430107527, 0.373716409793584},    {0.6736842105263158, 0.394993808240869},
-    {0.6597938144329897, 0.415827895143711},    {0.6464646464646465, 0.43623676677491796},
-    {0.6336633663366337, 0.4562374334815876},   {0.6213592233009708, 0.475845904869964},
-    {0.6095238095238096, 0.4950772667978514},   {0.5981308411214953, 0.5139457511022344},
-    {0.5871559633027523, 0.5324647988694717},   {0.5765765765765766, 0.5506471179526623},
-    {0.5663716814159292, 0.5685047353526688},   {0.5565217391304348, 0.5860490450035782},
-    {0.5470085470085471, 0.6032908514380841},   {0.5378151260504201, 0.6202404097518576},
-    {0.5289256198347108, 0.6369074622370692},   {0.5203252032520326, 0.6533012720127456},
-    {0.512, 0.6694306539426292},                {0.5039370078740157, 0.6853040030989195}};
-__constant__ double kLog1pC[7] = {   // -1/8, 1/7, -1/6, 1/5, -1/4, 1/3, -1/2
-    -0.125, 1.42857142857142857143e-01, -1.66666666666666666667e-01, 0.2, -0.25, 3.33333333333333333333e-01, -0.5};
+// Tables for the logistic row term (tools/gen_logit_tables.py writes them, 60-digit arithmetic, rounded once).
+// exp(-a) = 2^k * 2^(j/64) * exp(r): m = round(-a * 64 log2 e) = 64 k + j, r = -a - m ln2/64, |r| <= ln2/128, so a
+// degree-5 polynomial is exact to 4e-17.  log(u) for u in (1, 2]: u = c_j (1 + rr) with c_j the centre of the
+// j-th of 128 mantissa intervals, rr = u * fl(1/c_j) - 1, |rr| <= 1/256, log u = -log fl(1/c_j) + log1p(rr)
+// (series to rr^6, truncation < 3e-18); the table holds the log of the value really multiplied by, so the
+// identity is exact up to rounding.  No division, no reciprocal; 26 fp64 instructions per row.
+// {-64 log2(e), 1.5*2^52, -ln2/64 hi (21 low bits zero: m * hi exact), -ln2/64 lo}
+__constant__ double kLgtK[4] = {-92.33248261689366, 6755399441055744.0, -0.01083042469326756, -2.9815858269852933e-12};
+__constant__ double kLgtExpC[6] = {   // 1/5! .. 1/0!
+    8.33333333333333333333e-03, 4.16666666666666666667e-02, 1.66666666666666666667e-01, 0.5, 1.0, 1.0};
+__constant__ double kLgtLogC[5] = {-1.66666666666666666667e-01, 0.2, -0.25, 3.33333333333333333333e-01, -0.5};
+__constant__ double kLgtExpTabC[64] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+__constant__ double2 kLgtLogTabC[128] = {
+    {0.9961089494163424, 0.003898640415657309}, {0.9884169884169884, 0.01165061721997525},
+    {0.9808429118773946, 0.019342962843130987}, {0.973384030418251, 0.026976587698202083},
+    {0.9660377358490566, 0.03455238150665973}, {0.9588014981273408, 0.042071213920687044},
+    {0.9516728624535316, 0.049533935122276676}, {0.9446494464944649, 0.05694137640013845},
+    {0.9377289377289377, 0.06429435070539725}, {0.9309090909090909, 0.07159365318700882},
+    {0.924187725631769, 0.078840061707776}, {0.9175627240143369, 0.08603433734180316},
+    {0.9110320284697508, 0.09317722485418334}, {0.9045936395759717, 0.10026945316367517},
+    {0.8982456140350877, 0.10731173578908804}, {0.89198606271777, 0.11430477128005863},
+    {0.8858131487889274, 0.12124924363286965}, {0.8797250859106529, 0.12814582269193006},
+    {0.8737201365187713, 0.13499516453750482}, {0.8677966101694915, 0.1417979118602574},
+    {0.8619528619528619, 0.1485546943231372}, {0.8561872909698997, 0.15526612891112396},
+    {0.8504983388704319, 0.16193282026931324}, {0.8448844884488449, 0.16855536102980664},
+    {0.839344262295082, 0.17513433212784915}, {0.8338762214983714, 0.18167030310763463},
+    {0.8284789644012945, 0.18816383241818294}, {0.8231511254019293, 0.19461546769967167},
+    {0.8178913738019169, 0.2010257460605908}, {0.8126984126984127, 0.2073951943460706},
+    {0.807570977917981, 0.21372432939771818}, {0.8025078369905956, 0.22001365830528213},
+    {0.7975077881619937, 0.2262636786504534}, {0.7925696594427245, 0.232474878743094},
+    {0.7876923076923077, 0.238647737850175}, {0.7828746177370031, 0.24478272641769092},
+    {0.7781155015197568, 0.25088030628580943}, {0.7734138972809668, 0.2569409308975004},
+    {0.7687687687687688, 0.26296504550088134}, {0.764179104477612, 0.26895308734550394},
+    {0.7596439169139466, 0.2749054858727992}, {0.7551622418879056, 0.2808226629008878},
+    {0.750733137829912, 0.2867050328039543}, {0.7463556851311953, 0.29255300268637746},
+    {0.7420289855072464, 0.2983669725517973}, {0.7377521613832853, 0.3041473354672968},
+    {0.7335243553008596, 0.3098944777228647}, {0.7293447293447294, 0.3156087789863033},
+    {0.7252124645892352, 0.32129061245373425}, {0.7211267605633803, 0.3269403449958533},
+    {0.7170868347338936, 0.3325583373000766}, {0.713091922005571, 0.3381449440087164},
+    {0.7091412742382271, 0.34370051385331846}, {0.7052341597796143, 0.3492253897852883},
+    {0.7013698630136986, 0.354719909102929}, {0.6975476839237057, 0.3601844035750078},
+    {0.6937669376693767, 0.3656191995609647}, {0.6900269541778976, 0.37102461812787263},
+    {0.6863270777479893, 0.376400975164253}, {0.6826666666666666, 0.3817485814908484},
+    {0.6790450928381963, 0.3870677429684483}, {0.6754617414248021, 0.3923587606028639},
+    {0.6719160104986877, 0.3976219306471385}, {0.6684073107049608, 0.4028575447010835},
+    {0.6649350649350649, 0.4080658898082217}, {0.661498708010336, 0.41324724855021927},
+    {0.6580976863753213, 0.41840189913888387}, {0.6547314578005116, 0.4235301155058032},
+    {0.6513994910941476, 0.42863216738969867}, {0.6481012658227848, 0.4337083204215594},
+    {0.6448362720403022, 0.43875883620762796}, {0.6416040100250626, 0.44378397241030104},
+    {0.6384039900249376, 0.4487839828270067}, {0.6352357320099256, 0.4537591174671205},
+    {0.6320987654320988, 0.4587096226269767}, {0.628992628992629, 0.46363574096303256},
+    {0.6259168704156479, 0.46853771156323926}, {0.6228710462287105, 0.4734157700166721},
+    {0.6198547215496368, 0.47827014848147026}, {0.6168674698795181, 0.48310107575113576},
+    {0.6139088729016786, 0.48790877731923904}, {0.6109785202863962, 0.4926934754425752},
+    {0.6080760095011877, 0.4974553892028189}, {0.6052009456264775, 0.5021947345667155},
+    {0.6023529411764705, 0.5069117244448544}, {0.5995316159250585, 0.5116065687490621},
+    {0.5967365967365967, 0.5162794744484545}, {0.5939675174013921, 0.5209306456241853},
+    {0.5912240184757506, 0.5255602835229274}, {0.5885057471264368, 0.5301685866091216},
+    {0.585812356979405, 0.5347557506160276}, {0.5831435079726651, 0.5393219685956089},
+    {0.5804988662131519, 0.5438674309672835}, {0.5778781038374717, 0.5483923255655733},
+    {0.5752808988764045, 0.5528968376866776}, {0.5727069351230425, 0.5573811501340064},
+    {0.5701559020044543, 0.5618454432626918}, {0.5676274944567627, 0.5662898950231159},
+    {0.565121412803532, 0.5707146810034716}, {0.5626373626373626, 0.575119974471388},
+    {0.5601750547045952, 0.5795059464146423}, {0.5577342047930284, 0.5838727655809826},
+    {0.5553145336225597, 0.588220598517086}, {0.5529157667386609, 0.5925496096066716},
+    {0.5505376344086022, 0.5968599611077938}, {0.5481798715203426, 0.6011518131893347},
+    {0.5458422174840085, 0.6054253239667169}, {0.5435244161358811, 0.6096806495368553},
+    {0.5412262156448203, 0.6139179440123704}, {0.5389473684210526, 0.6181373595550788},
+    {0.5366876310272537, 0.6223390464087787}, {0.534446764091858, 0.6265231529313529},
+    {0.5322245322245323, 0.6306898256261987}, {0.5300207039337475, 0.6348392091730102},
+    {0.5278350515463918, 0.6389714464579207}, {0.5256673511293635, 0.6430866786030273},
+    {0.523517382413088, 0.6471850449953095}, {0.5213849287169042, 0.6512666833149582},
+    {0.5192697768762677, 0.6553317295631277}, {0.5171717171717172, 0.6593803180891278},
+    {0.5150905432595574, 0.6634125816170662}, {0.5130260521042084, 0.6674286512719563},
+    {0.5109780439121756, 0.6714286566053024}, {0.5089463220675944, 0.6754127256201768},
+    {0.5069306930693069, 0.6793809847957973}, {0.504930966469428, 0.6833335591116206},
+    {0.5029469548133595, 0.6872705720709603}, {0.5009784735812133, 0.691192145724142}};
 
-// the table lives in shared memory (lanes index it with different j); one copy per CTA, filled once
-__shared__ double2 s_logit_tab[32];
+// the tables live in shared memory (lanes index them with different j); one copy per CTA, filled once
+struct LogitTables { double2 lg[128]; double ex[64]; };
+__shared__ LogitTables s_logit_tab;
 BPT_D void logit_table_init() {   // call before the first __syncthreads() of the kernel
-  if (threadIdx.x < 32) s_logit_tab[threadIdx.x] = kLogTabC[threadIdx.x];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_logit_tab.lg[i] = kLgtLogTabC[i];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_logit_tab.ex[i] = kLgtExpTabC[i];
 }
 
-// W independent lanes evaluated together: min(z,0) - log1p(exp(-|z|)) for -12 <= z, |z| < 700.
-// Straight-line code; the W chains interleave (ILP) and share every coefficient load.
 BPT_D uint32_t logit_table_address() {
-  uint32_t a = (uint32_t)__cvta_generic_to_shared(s_logit_tab);
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(&s_logit_tab);
   asm volatile("" : "+r"(a));   // opaque: keeps the address in a register instead of re-deriving it per use
   return a;
 }
+// W independent lanes evaluated together: min(z,0) - log1p(exp(-|z|)) for -12 <= z, |z| < 700.
+// Straight-line code; the W chains interleave (ILP) and share every coefficient.  Inputs outside the range
+// produce garbage but never fault (callers may evaluate rows they will discard).
 template <int W>
 BPT_D void logit_fast(const double (&z)[W], double& s, uint32_t tab) {
-  double kd[W], r[W], p[W]; int k[W];
+  double kd[W], r[W], p[W], te[W]; int m[W];
 #pragma unroll
   for (int w = 0; w < W; w++) {
     const double a = fabs(z[w]);
-    kd[w] = fma(a, kLogitK[0], kLogitK[1]);     // magic add: low word = round(-a*log2e)
-    k[w] = __double2loint(kd[w]);
-    kd[w] -= kLogitK[1];
-    r[w] = fma(kd[w], kLogitK[2], -a);
-    r[w] = fma(kd[w], kLogitK[3], r[w]);
-    p[w] = kExpC[0];
+    kd[w] = fma(a, kLgtK[0], kLgtK[1]);     // magic add: low word = round(-a * 64 log2 e)
+    m[w] = __double2loint(kd[w]);
+    kd[w] -= kLgtK[1];
+    asm("ld.shared.f64 %0, [%1];" : "=d"(te[w]) : "r"(tab + 2048u + ((uint32_t)(m[w] & 63) << 3)));
+    r[w] = fma(kd[w], kLgtK[2], -a);
+    r[w] = fma(kd[w], kLgtK[3], r[w]);
+    p[w] = kLgtExpC[0];
   }
 #pragma unroll
-  for (int i = 1; i < 12; i++)
+  for (int i = 1; i < 6; i++)
 #pragma unroll
-    for (int w = 0; w < W; w++) p[w] = fma(p[w], r[w], kExpC[i]);
+    for (int w = 0; w < W; w++) p[w] = fma(p[w], r[w], kLgtExpC[i]);
   double q[W], rr[W], lc[W];
 #pragma unroll
   for (int w = 0; w < W; w++) {
-    // t = exp(-|z|) = p * 2^k in (0, 1];  u = 1 + t in (1, 2]
-    const double t = __hiloint2double(__double2hiint(p[w]) + (k[w] << 20), __double2loint(p[w]));
+    // t = exp(-|z|) = 2^k * (2^(j/64) * p) in (0, 1];  u = 1 + t in (1, 2]
+    const double tp = te[w] * p[w];
+    const double t = __hiloint2double(__double2hiint(tp) + ((m[w] >> 6) << 20), __double2loint(tp));
     const double u = 1.0 + t;
-    // unsigned: an out-of-range u (callers may evaluate rows they will discard) still indexes the table
-    const unsigned j = min(31u, (unsigned)(__double2hiint(u) - 0x3ff00000) >> 15);
+    const unsigned j = min(127u, (unsigned)(__double2hiint(u) - 0x3ff00000) >> 13);
     double2 cj;
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cj.x), "=d"(cj.y) : "r"(tab + (j << 4)));
     rr[w] = fma(u, cj.x, -1.0);
     lc[w] = cj.y;
-    q[w] = kLog1pC[0];
+    q[w] = kLgtLogC[0];
   }
 #pragma unroll
-  for (int i = 1; i < 7; i++)
+  for (int i = 1; i < 5; i++)
 #pragma unroll
-    for (int w = 0; w < W; w++) q[w] = fma(q[w], rr[w], kLog1pC[i]);
+    for (int w = 0; w < W; w++) q[w] = fma(q[w], rr[w], kLgtLogC[i]);
 #pragma unroll
   for (int w = 0; w < W; w++) {
     const double l = fma(rr[w] * rr[w], q[w], rr[w]) + lc[w];     // log1p(exp(-|z|))
@@ -167,12 +241,14 @@ BPT_D void logit_term(double zs, const uint8_t* yp, double& s, int& c, int* err)
 // Two rows.  The lean arithmetic runs unconditionally (straight-line, no divergence bookkeeping on the hot
 // path); its result is kept when both rows are in its range, which one warp vote decides for all lanes that
 // are here together.  Otherwise each row is redone on its own path.
+template <bool FULL_WARP = false>
 BPT_D void logit_pair(double za, double zb, const uint8_t* yp, double& s, int& c, int* err, uint32_t tab) {
   const bool ok = logit_is_fast(za) && logit_is_fast(zb);
   const double z[2] = {za, zb};
   double t = s;
   logit_fast<2>(z, t, tab);
-  if (__all_sync(__activemask(), ok)) { s = t; return; }
+  // FULL_WARP: the caller guarantees that all 32 lanes are here together
+  if (__all_sync(FULL_WARP ? 0xffffffffu : __activemask(), ok)) { s = t; return; }
   if (ok) s = t;
   else { logit_term(za, yp, s, c, err); logit_term(zb, yp + 1, s, c, err); }
 }
@@ -369,20 +445,27 @@ struct LogisticFamT {
     const double2* pe = reinterpret_cast<const double2*>(eta + rr.lo) + threadIdx.x;
     const double2* px = reinterpret_cast<const double2*>(d.xt + (size_t)k * d.npad + rr.lo) + threadIdx.x;
     const uint8_t* py = d.y + rr.lo + 2 * threadIdx.x;
-    int left = n_pairs - (int)threadIdx.x;          // pairs this thread still has to do (stride THREADS)
     const uint32_t tab = logit_table_address();
+    // `whole` counts the pairs from this warp's first lane on: while it is >= 32 all lanes of the warp have a
+    // pair, so the loop is warp-uniform (full-mask vote inside logit_pair); the ragged rest is one more step.
+    int whole = n_pairs - (int)(threadIdx.x & ~31u);
     // two register sets alternate between "being evaluated" and "being loaded" (no copies between them)
     double2 ea = make_double2(0.0, 0.0), xa = ea, eb = ea, xb = ea;
-    if (left > 0) { ea = *pe; xa = *px; }
-    while (left > 0) {
-      left -= THREADS;
-      if (left > 0) { eb = pe[THREADS]; xb = px[THREADS]; }
-      logit_pair(fma(delta, xa.x, ea.x), fma(delta, xa.y, ea.y), py, acc, cnt, err, tab);
-      if (left <= 0) break;
-      left -= THREADS; pe += 2 * THREADS; px += 2 * THREADS;
-      if (left > 0) { ea = *pe; xa = *px; }
-      logit_pair(fma(delta, xb.x, eb.x), fma(delta, xb.y, eb.y), py + 2 * THREADS, acc, cnt, err, tab);
-      py += 4 * THREADS;
+    if (whole >= 32) { ea = *pe; xa = *px; }
+    while (whole >= 32) {
+      whole -= THREADS;
+      if (whole >= 32) { eb = pe[THREADS]; xb = px[THREADS]; }
+      logit_pair<true>(fma(delta, xa.x, ea.x), fma(delta, xa.y, ea.y), py, acc, cnt, err, tab);
+      pe += THREADS; px += THREADS; py += 2 * THREADS;
+      if (whole < 32) break;
+      whole -= THREADS;
+      if (whole >= 32) { ea = pe[THREADS]; xa = px[THREADS]; }
+      logit_pair<true>(fma(delta, xb.x, eb.x), fma(delta, xb.y, eb.y), py, acc, cnt, err, tab);
+      pe += THREADS; px += THREADS; py += 2 * THREADS;
+    }
+    if (whole - (int)(threadIdx.x & 31u) > 0) {      // last, partly filled warp step
+      const double2 e = *pe, xv = *px;
+      logit_pair<false>(fma(delta, xv.x, e.x), fma(delta, xv.y, e.y), py, acc, cnt, err, tab);
     }
     if (((rr.hi - rr.lo) & 1) && threadIdx.x == 0) {   // odd tail row of this CTA's range
       const int i = rr.hi - 1;
