@@ -74,14 +74,14 @@ __constant__ double kLogitK[7] = {
 // Tables for the logistic row term (tools/gen_logit_tables.py writes them, 60-digit arithmetic, rounded once).
 // exp(-a) = 2^k * 2^(j/64) * exp(r): m = round(-a * 64 log2 e) = 64 k + j, r = -a - m ln2/64, |r| <= ln2/128, so a
 // degree-5 polynomial is exact to 4e-17.  log(u) for u in (1, 2]: u = c_j (1 + rr) with c_j the centre of the
-// j-th of 128 mantissa intervals, rr = u * fl(1/c_j) - 1, |rr| <= 1/256, log u = -log fl(1/c_j) + log1p(rr)
-// (series to rr^6, truncation < 3e-18); the table holds the log of the value really multiplied by, so the
-// identity is exact up to rounding.  No division, no reciprocal; 26 fp64 instructions per row.
+// j-th of 256 mantissa intervals, rr = u * fl(1/c_j) - 1, |rr| <= 1/512, log u = -log fl(1/c_j) + log1p(rr)
+// (series to rr^5, truncation < 1e-17); the table holds the log of the value really multiplied by, so the
+// identity is exact up to rounding.  No division, no reciprocal; 25 fp64 instructions per row.
 // {-64 log2(e), 1.5*2^52, -ln2/64 hi (21 low bits zero: m * hi exact), -ln2/64 lo}
 __constant__ double kLgtK[4] = {-92.33248261689366, 6755399441055744.0, -0.01083042469326756, -2.9815858269852933e-12};
 __constant__ double kLgtExpC[6] = {   // 1/5! .. 1/0!
     8.33333333333333333333e-03, 4.16666666666666666667e-02, 1.66666666666666666667e-01, 0.5, 1.0, 1.0};
-__constant__ double kLgtLogC[5] = {-1.66666666666666666667e-01, 0.2, -0.25, 3.33333333333333333333e-01, -0.5};
+__constant__ double kLgtLogC[4] = {0.2, -0.25, 3.33333333333333333333e-01, -0.5};
 __constant__ double kLgtExpTabC[64] = {
     1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
     1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
@@ -99,77 +99,141 @@ __constant__ double kLgtExpTabC[64] = {
     1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
     1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
     1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
-__constant__ double2 kLgtLogTabC[128] = {
-    {0.9961089494163424, 0.003898640415657309}, {0.9884169884169884, 0.01165061721997525},
-    {0.9808429118773946, 0.019342962843130987}, {0.973384030418251, 0.026976587698202083},
-    {0.9660377358490566, 0.03455238150665973}, {0.9588014981273408, 0.042071213920687044},
-    {0.9516728624535316, 0.049533935122276676}, {0.9446494464944649, 0.05694137640013845},
-    {0.9377289377289377, 0.06429435070539725}, {0.9309090909090909, 0.07159365318700882},
-    {0.924187725631769, 0.078840061707776}, {0.9175627240143369, 0.08603433734180316},
-    {0.9110320284697508, 0.09317722485418334}, {0.9045936395759717, 0.10026945316367517},
-    {0.8982456140350877, 0.10731173578908804}, {0.89198606271777, 0.11430477128005863},
-    {0.8858131487889274, 0.12124924363286965}, {0.8797250859106529, 0.12814582269193006},
-    {0.8737201365187713, 0.13499516453750482}, {0.8677966101694915, 0.1417979118602574},
-    {0.8619528619528619, 0.1485546943231372}, {0.8561872909698997, 0.15526612891112396},
-    {0.8504983388704319, 0.16193282026931324}, {0.8448844884488449, 0.16855536102980664},
-    {0.839344262295082, 0.17513433212784915}, {0.8338762214983714, 0.18167030310763463},
-    {0.8284789644012945, 0.18816383241818294}, {0.8231511254019293, 0.19461546769967167},
-    {0.8178913738019169, 0.2010257460605908}, {0.8126984126984127, 0.2073951943460706},
-    {0.807570977917981, 0.21372432939771818}, {0.8025078369905956, 0.22001365830528213},
-    {0.7975077881619937, 0.2262636786504534}, {0.7925696594427245, 0.232474878743094},
-    {0.7876923076923077, 0.238647737850175}, {0.7828746177370031, 0.24478272641769092},
-    {0.7781155015197568, 0.25088030628580943}, {0.7734138972809668, 0.2569409308975004},
-    {0.7687687687687688, 0.26296504550088134}, {0.764179104477612, 0.26895308734550394},
-    {0.7596439169139466, 0.2749054858727992}, {0.7551622418879056, 0.2808226629008878},
-    {0.750733137829912, 0.2867050328039543}, {0.7463556851311953, 0.29255300268637746},
-    {0.7420289855072464, 0.2983669725517973}, {0.7377521613832853, 0.3041473354672968},
-    {0.7335243553008596, 0.3098944777228647}, {0.7293447293447294, 0.3156087789863033},
-    {0.7252124645892352, 0.32129061245373425}, {0.7211267605633803, 0.3269403449958533},
-    {0.7170868347338936, 0.3325583373000766}, {0.713091922005571, 0.3381449440087164},
-    {0.7091412742382271, 0.34370051385331846}, {0.7052341597796143, 0.3492253897852883},
-    {0.7013698630136986, 0.354719909102929}, {0.6975476839237057, 0.3601844035750078},
-    {0.6937669376693767, 0.3656191995609647}, {0.6900269541778976, 0.37102461812787263},
-    {0.6863270777479893, 0.376400975164253}, {0.6826666666666666, 0.3817485814908484},
-    {0.6790450928381963, 0.3870677429684483}, {0.6754617414248021, 0.3923587606028639},
-    {0.6719160104986877, 0.3976219306471385}, {0.6684073107049608, 0.4028575447010835},
-    {0.6649350649350649, 0.4080658898082217}, {0.661498708010336, 0.41324724855021927},
-    {0.6580976863753213, 0.41840189913888387}, {0.6547314578005116, 0.4235301155058032},
-    {0.6513994910941476, 0.42863216738969867}, {0.6481012658227848, 0.4337083204215594},
-    {0.6448362720403022, 0.43875883620762796}, {0.6416040100250626, 0.44378397241030104},
-    {0.6384039900249376, 0.4487839828270067}, {0.6352357320099256, 0.4537591174671205},
-    {0.6320987654320988, 0.4587096226269767}, {0.628992628992629, 0.46363574096303256},
-    {0.6259168704156479, 0.46853771156323926}, {0.6228710462287105, 0.4734157700166721},
-    {0.6198547215496368, 0.47827014848147026}, {0.6168674698795181, 0.48310107575113576},
-    {0.6139088729016786, 0.48790877731923904}, {0.6109785202863962, 0.4926934754425752},
-    {0.6080760095011877, 0.4974553892028189}, {0.6052009456264775, 0.5021947345667155},
-    {0.6023529411764705, 0.5069117244448544}, {0.5995316159250585, 0.5116065687490621},
-    {0.5967365967365967, 0.5162794744484545}, {0.5939675174013921, 0.5209306456241853},
-    {0.5912240184757506, 0.5255602835229274}, {0.5885057471264368, 0.5301685866091216},
-    {0.585812356979405, 0.5347557506160276}, {0.5831435079726651, 0.5393219685956089},
-    {0.5804988662131519, 0.5438674309672835}, {0.5778781038374717, 0.5483923255655733},
-    {0.5752808988764045, 0.5528968376866776}, {0.5727069351230425, 0.5573811501340064},
-    {0.5701559020044543, 0.5618454432626918}, {0.5676274944567627, 0.5662898950231159},
-    {0.565121412803532, 0.5707146810034716}, {0.5626373626373626, 0.575119974471388},
-    {0.5601750547045952, 0.5795059464146423}, {0.5577342047930284, 0.5838727655809826},
-    {0.5553145336225597, 0.588220598517086}, {0.5529157667386609, 0.5925496096066716},
-    {0.5505376344086022, 0.5968599611077938}, {0.5481798715203426, 0.6011518131893347},
-    {0.5458422174840085, 0.6054253239667169}, {0.5435244161358811, 0.6096806495368553},
-    {0.5412262156448203, 0.6139179440123704}, {0.5389473684210526, 0.6181373595550788},
-    {0.5366876310272537, 0.6223390464087787}, {0.534446764091858, 0.6265231529313529},
-    {0.5322245322245323, 0.6306898256261987}, {0.5300207039337475, 0.6348392091730102},
-    {0.5278350515463918, 0.6389714464579207}, {0.5256673511293635, 0.6430866786030273},
-    {0.523517382413088, 0.6471850449953095}, {0.5213849287169042, 0.6512666833149582},
-    {0.5192697768762677, 0.6553317295631277}, {0.5171717171717172, 0.6593803180891278},
-    {0.5150905432595574, 0.6634125816170662}, {0.5130260521042084, 0.6674286512719563},
-    {0.5109780439121756, 0.6714286566053024}, {0.5089463220675944, 0.6754127256201768},
-    {0.5069306930693069, 0.6793809847957973}, {0.504930966469428, 0.6833335591116206},
-    {0.5029469548133595, 0.6872705720709603}, {0.5009784735812133, 0.691192145724142}};
+__constant__ double2 kLgtLogTabC[256] = {
+    {0.9980506822612085, 0.0019512201312618048}, {0.9941747572815534, 0.0058422756242284025},
+    {0.9903288201160542, 0.00971824946892134}, {0.9865125240847784, 0.013579258126380866},
+    {0.982725527831094, 0.01742541671385917}, {0.9789674952198852, 0.021256839025415152},
+    {0.9752380952380952, 0.025073637552115963}, {0.9715370018975332, 0.02887592350185452},
+    {0.9678638941398866, 0.03266380681879157}, {0.9642184557438794, 0.03643739620243109},
+    {0.9606003752345216, 0.04019679912633676}, {0.9570093457943926, 0.04394212185649872},
+    {0.9534450651769087, 0.04767346946935691}, {0.9499072356215214, 0.051390945869489356},
+    {0.9463955637707948, 0.05509465380697375}, {0.9429097605893186, 0.058784694894427614},
+    {0.9394495412844037, 0.06246116962373623}, {0.9360146252285192, 0.06612417738247342},
+    {0.9326047358834244, 0.06977381647002284}, {0.9292196007259528, 0.07341018411340675},
+    {0.9258589511754068, 0.07703337648282704}, {0.9225225225225225, 0.08064348870692671},
+    {0.9192100538599641, 0.0842406148877762}, {0.9159212880143113, 0.08782484811559137},
+    {0.9126559714795008, 0.09139628048318858}, {0.9094138543516874, 0.09495500310018257},
+    {0.9061946902654867, 0.09850110610693318}, {0.9029982363315696, 0.10203467868824434},
+    {0.8998242530755711, 0.1055558090868232}, {0.8966725043782837, 0.10906458461650242},
+    {0.893542757417103, 0.11256109167523176}, {0.8904347826086957, 0.11604541575784262},
+    {0.8873483535528596, 0.11951764146859183}, {0.8842832469775475, 0.1229778525334875},
+    {0.8812392426850258, 0.12642613181240342}, {0.8782161234991424, 0.12986256131098461},
+    {0.8752136752136752, 0.1332872221923487}, {0.8722316865417377, 0.13670019478858866},
+    {0.8692699490662139, 0.14010155861207893}, {0.8663282571912013, 0.14349139236659045},
+    {0.863406408094435, 0.1468697739582177}, {0.8605042016806723, 0.1502367805061219},
+    {0.8576214405360134, 0.15359248835309428}, {0.8547579298831386, 0.15693697307594154},
+    {0.8519134775374376, 0.16027030949569976}, {0.8490878938640133, 0.16359257168767763},
+    {0.8462809917355372, 0.1669038329913337}, {0.8434925864909391, 0.17020416601999047},
+    {0.8407224958949097, 0.17349364267038928}, {0.8379705400981997, 0.17677233413208748},
+    {0.835236541598695, 0.18004031089670358}, {0.832520325203252, 0.18329764276701008},
+    {0.8298217179902755, 0.1865443988658801}, {0.827140549273021, 0.18978064764508826},
+    {0.8244766505636071, 0.19300645689397097}, {0.8218298555377207, 0.19622189374794538},
+    {0.8192, 0.19942702469689366}, {0.8165869218500797, 0.20262191559341292},
+    {0.8139904610492846, 0.2058066316609327}, {0.8114104595879557, 0.20898123750170533},
+    {0.8088467614533965, 0.2121457971046684}, {0.8062992125984252, 0.21530037385318387},
+    {0.8037676609105181, 0.21844503053265552}, {0.8012519561815337, 0.221579829338027},
+    {0.7987519500780031, 0.22470483188116222}, {0.7962674961119751, 0.2278200991981116},
+    {0.7937984496124031, 0.2309256917562647}, {0.7913446676970634, 0.2340216694613928},
+    {0.7889060092449923, 0.2371080916645822}, {0.7864823348694316, 0.24018501716906146},
+    {0.7840735068912711, 0.24325250423692324}, {0.7816793893129771, 0.24631061059574413},
+    {0.7792998477929984, 0.24935939344510277}, {0.7769347496206374, 0.2523989094629994},
+    {0.7745839636913767, 0.25542921481217845}, {0.7722473604826546, 0.25845036514635467},
+    {0.7699248120300752, 0.2614624156163463}, {0.767616191904048, 0.26446542087611596},
+    {0.7653213751868461, 0.2674594350887206}, {0.7630402384500745, 0.270444511932174},
+    {0.7607726597325408, 0.27342070460522006}, {0.7585185185185185, 0.2763880658330221},
+    {0.7562776957163959, 0.27934664787276714}, {0.7540500736377025, 0.28229650251918836},
+    {0.7518355359765051, 0.28523768111000464}, {0.7496339677891655, 0.28817023453128227},
+    {0.7474452554744525, 0.29109421322271756}, {0.745269286754003, 0.2940096671828415},
+    {0.7431059506531205, 0.2969166459741508}, {0.7409551374819102, 0.2998151987281622},
+    {0.7388167388167388, 0.30270537415039545}, {0.7366906474820144, 0.3055872205252843},
+    {0.7345767575322812, 0.30846078572101604}, {0.7324749642346209, 0.3113261171943025},
+    {0.7303851640513552, 0.3141832619950823}, {0.7283072546230441, 0.3170322667711571},
+    {0.7262411347517731, 0.3198731777727608}, {0.7241867043847242, 0.32270604085706495},
+    {0.7221438645980254, 0.3255309014926197}, {0.720112517580872, 0.3283478047637331},
+    {0.7180925666199158, 0.3311567953747882}, {0.7160839160839161, 0.3339579176544999},
+    {0.7140864714086471, 0.3367512155601126}, {0.7121001390820584, 0.33953673268153894},
+    {0.710124826629681, 0.3423145122454413}, {0.7081604426002767, 0.3450845971192569},
+    {0.7062068965517241, 0.3478470298151671}, {0.7042640990371389, 0.35060185249401155},
+    {0.7023319615912208, 0.35334910696915045}, {0.7004103967168263, 0.35608883471027075},
+    {0.6984993178717599, 0.3588210768471437}, {0.6965986394557823, 0.36154587417332895},
+    {0.694708276797829, 0.3642632671498289}, {0.6928281461434371, 0.36697329590869393},
+    {0.6909581646423751, 0.36967600025657915}, {0.6890982503364738, 0.3723714196782514},
+    {0.687248322147651, 0.3750595933400518}, {0.6854082998661312, 0.3777405600933096},
+    {0.6835781041388518, 0.3804143584777117}, {0.681757656458056, 0.3830810267246269},
+    {0.6799468791500664, 0.38574060276038585}, {0.6781456953642384, 0.38839312420951694},
+    {0.6763540290620872, 0.39103862839794096}, {0.6745718050065876, 0.3936771523561221},
+    {0.6727989487516426, 0.39630873282217804}, {0.6710353866317169, 0.3989334062449492},
+    {0.6692810457516339, 0.4015512087870281}, {0.6675358539765319, 0.4041621763277484},
+    {0.6657997399219766, 0.4067663444661362}, {0.6640726329442282, 0.40936374852382174},
+    {0.6623544631306598, 0.4119544235479141}, {0.6606451612903226, 0.4145384043138392},
+    {0.6589446589446589, 0.4171157253281397}, {0.6572528883183568, 0.4196864208312405},
+    {0.6555697823303457, 0.4222505248001782}, {0.6538952745849298, 0.42480807095129525},
+    {0.6522292993630573, 0.4273590927429007}, {0.650571791613723, 0.4299036233778954},
+    {0.6489226869455006, 0.43244169580636654}, {0.6472819216182049, 0.43497334272814603},
+    {0.6456494325346784, 0.4374985965953402}, {0.6440251572327044, 0.4400174896148242},
+    {0.6424090338770388, 0.4425300537507073}, {0.6408010012515645, 0.44503632072676685},
+    {0.6392009987515606, 0.4475363220288514}, {0.6376089663760897, 0.4500300889072539},
+    {0.6360248447204969, 0.45251765237905556}, {0.6344485749690211, 0.454999043230441},
+    {0.6328800988875154, 0.457474292018984}, {0.6313193588162762, 0.45994342907590513},
+    {0.6297662976629766, 0.4624064845083028}, {0.6282208588957056, 0.46486348820135487},
+    {0.6266829865361077, 0.4673144698204952}, {0.6251526251526252, 0.4697594588135616},
+    {0.6236297198538368, 0.4721984844129205}, {0.6221142162818954, 0.47463157563756214},
+    {0.6206060606060606, 0.4770587612951732}, {0.619105199516324, 0.4794800699841836},
+    {0.617611580217129, 0.4818955300957873}, {0.6161251504211793, 0.48430516981594035},
+    {0.6146458583433373, 0.486709017127335}, {0.6131736526946108, 0.4891070998113477},
+    {0.6117084826762246, 0.4914994454499676}, {0.6102502979737783, 0.49388608142769846},
+    {0.6087990487514863, 0.4962670349334404}, {0.6073546856465006, 0.4986423329623476},
+    {0.6059171597633136, 0.5010120023176661}, {0.6044864226682408, 0.5033760696125467},
+    {0.6030624263839811, 0.5057345612718396}, {0.6016451233842538, 0.5080875035338663},
+    {0.6002344665885111, 0.5104349224521714}, {0.5988304093567252, 0.5127768438972524},
+    {0.5974329054842473, 0.5151132935582721}, {0.5960419091967404, 0.5174442969447476},
+    {0.59465737514518, 0.519769879388223}, {0.593279258400927, 0.5220900660439202},
+    {0.5919075144508671, 0.5244048818923714}, {0.5905420991926182, 0.526714351741034},
+    {0.5891829689298044, 0.5290185002258843}, {0.5878300803673938, 0.531317351812995},
+    {0.586483390607102, 0.5336109308000944}, {0.5851428571428572, 0.5358992613181066},
+    {0.5838084378563284, 0.5381823673326752}, {0.5824800910125142, 0.5404602726456693},
+    {0.5811577752553916, 0.5427330008966718}, {0.579841449603624, 0.5450005755644521},
+    {0.5785310734463277, 0.5472630199684217}, {0.5772266065388951, 0.5495203572700718},
+    {0.5759280089988752, 0.5517726104743967}, {0.574635241301908, 0.5540198024313014},
+    {0.5733482642777156, 0.5562619558369912}, {0.5720670391061452, 0.5584990932353476},
+    {0.5707915273132664, 0.5607312370192884}, {0.5695216907675195, 0.5629584094321125},
+    {0.5682574916759157, 0.5651806325688301}, {0.5669988925802879, 0.5673979283774777},
+    {0.5657458563535912, 0.5696103186604182}, {0.5644983461962514, 0.5718178250756288},
+    {0.5632563256325632, 0.5740204691379711}, {0.562019758507135, 0.5762182722204505},
+    {0.56078860898138, 0.5784112555554607}, {0.5595628415300546, 0.5805994402360135},
+    {0.5583424209378408, 0.5827828472169571}, {0.5571273122959739, 0.5849614973161792},
+    {0.5559174809989142, 0.587135411215799}, {0.5547128927410617, 0.5893046094633444},
+    {0.5535135135135135, 0.5914691124729174}, {0.552319309600863, 0.5936289405263474},
+    {0.5511302475780409, 0.5957841137743308}, {0.5499462943071965, 0.5979346522375593},
+    {0.5487674169346195, 0.600080575807836}, {0.5475935828877005, 0.6022219042491792},
+    {0.5464247598719317, 0.6043586571989144}, {0.5452609158679447, 0.606490854168755},
+    {0.5441020191285866, 0.6086185145458719}, {0.542948038176034, 0.6107416575939496},
+    {0.5417989417989418, 0.612860302454235}, {0.5406546990496304, 0.6149744681465705},
+    {0.5395152792413066, 0.6170841735704201}, {0.5383806519453207, 0.6191894375058825},
+    {0.5372507869884575, 0.6212902786146943}, {0.5361256544502618, 0.6233867154412224},
+    {0.5350052246603971, 0.6254787664134464}, {0.5338894681960376, 0.6275664498439304},
+    {0.5327783558792925, 0.6296497839307846}, {0.5316718587746625, 0.6317287867586178},
+    {0.5305699481865285, 0.6338034762994782}, {0.5294725956566702, 0.6358738704137865},
+    {0.5283797729618163, 0.6379399868512585}, {0.5272914521112255, 0.6400018432518172},
+    {0.526207605344296, 0.6420594571464973}, {0.5251282051282051, 0.6441128459583394},
+    {0.5240532241555783, 0.646162027003275}, {0.5229826353421859, 0.6482070174910025},
+    {0.5219164118246687, 0.6502478345258552}, {0.5208545269582909, 0.6522844951076588},
+    {0.5197969543147208, 0.6543170161325811}, {0.5187436676798379, 0.6563454143939738},
+    {0.5176946410515673, 0.6583697065832043}, {0.5166498486377397, 0.6603899092904802},
+    {0.5156092648539778, 0.6624060390056649}, {0.5145728643216081, 0.6644181121190849},
+    {0.5135406218655968, 0.6664261449223305}, {0.5125125125125125, 0.6684301536090458},
+    {0.5114885114885115, 0.6704301542757128}, {0.5104685942173479, 0.6724261629224279},
+    {0.5094527363184079, 0.6744181954536684}, {0.5084409136047666, 0.6764062676790545},
+    {0.5074331020812686, 0.6783903953141012}, {0.506429277942631, 0.6803705939809637},
+    {0.5054294175715696, 0.6823468792091757}, {0.5044334975369458, 0.68431926643638},
+    {0.5034414945919371, 0.6862877710090521}, {0.5024533856722276, 0.6882524081832171},
+    {0.5014691478942214, 0.6902131931251577}, {0.5004887585532747, 0.6921701409121187}};
 
 // the tables live in shared memory (lanes index them with different j); one copy per CTA, filled once
-struct LogitTables { double2 lg[128]; double ex[64]; };
+struct LogitTables { double2 lg[256]; double ex[64]; };
 __shared__ LogitTables s_logit_tab;
 BPT_D void logit_table_init() {   // call before the first __syncthreads() of the kernel
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_logit_tab.lg[i] = kLgtLogTabC[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_logit_tab.lg[i] = kLgtLogTabC[i];
   for (int i = threadIdx.x; i < 64; i += blockDim.x) s_logit_tab.ex[i] = kLgtExpTabC[i];
 }
 
@@ -190,7 +254,7 @@ BPT_D void logit_fast(const double (&z)[W], double& s, uint32_t tab) {
     kd[w] = fma(a, kLgtK[0], kLgtK[1]);     // magic add: low word = round(-a * 64 log2 e)
     m[w] = __double2loint(kd[w]);
     kd[w] -= kLgtK[1];
-    asm("ld.shared.f64 %0, [%1];" : "=d"(te[w]) : "r"(tab + 2048u + ((uint32_t)(m[w] & 63) << 3)));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(te[w]) : "r"(tab + 4096u + ((uint32_t)(m[w] & 63) << 3)));
     r[w] = fma(kd[w], kLgtK[2], -a);
     r[w] = fma(kd[w], kLgtK[3], r[w]);
     p[w] = kLgtExpC[0];
@@ -206,7 +270,7 @@ BPT_D void logit_fast(const double (&z)[W], double& s, uint32_t tab) {
     const double tp = te[w] * p[w];
     const double t = __hiloint2double(__double2hiint(tp) + ((m[w] >> 6) << 20), __double2loint(tp));
     const double u = 1.0 + t;
-    const unsigned j = min(127u, (unsigned)(__double2hiint(u) - 0x3ff00000) >> 13);
+    const unsigned j = min(255u, (unsigned)(__double2hiint(u) - 0x3ff00000) >> 12);
     double2 cj;
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cj.x), "=d"(cj.y) : "r"(tab + (j << 4)));
     rr[w] = fma(u, cj.x, -1.0);
@@ -214,7 +278,7 @@ BPT_D void logit_fast(const double (&z)[W], double& s, uint32_t tab) {
     q[w] = kLgtLogC[0];
   }
 #pragma unroll
-  for (int i = 1; i < 5; i++)
+  for (int i = 1; i < 4; i++)
 #pragma unroll
     for (int w = 0; w < W; w++) q[w] = fma(q[w], rr[w], kLgtLogC[i]);
 #pragma unroll

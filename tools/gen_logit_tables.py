@@ -3,14 +3,14 @@ from decimal import Decimal, getcontext
 import struct
 getcontext().prec = 60
 def d2f(x): return float(x)   # Decimal -> nearest double (Python rounds correctly)
-NE, NL = 64, 128
+NE, NL = 64, 256
 print("// 2^(j/64), j = 0..63")
 rows = []
 for j in range(NE):
     v = Decimal(2) ** (Decimal(j) / NE)
     rows.append(repr(d2f(v)))
 print(", ".join(rows))
-print("// {fl(1/c_j), -log(fl(1/c_j))}, c_j = 1 + (j + 1/2)/128")
+print("// {fl(1/c_j), -log(fl(1/c_j))}, c_j = 1 + (j + 1/2)/NL")
 rows = []
 for j in range(NL):
     c = Decimal(1) + (Decimal(j) + Decimal("0.5")) / NL
