@@ -234,19 +234,24 @@ def run_gpu(args):
         xs, _k1 = pinned(spec["x"]); ys, _k2 = pinned(spec["y"])
         spec_p = dict(spec, x=xs, y=ys)
         k_e2e = args.steps
-        barrier()
-        t0 = time.perf_counter()
-        e2 = Engine(nChains=CHAINS_PER_GPU, random=2 + rank, device=local_rank, ctasPerChain=args.ctas)
-        e2.set_model(spec_p)                      # H2D of the data set (host pointers)
-        e2.initialize("COPIES")
-        out = e2.run_scans(k_e2e, want=("energy", "swapIndicators", "samples", "logDensity", "nOutOfSupport"))
-        cc = e2.counters()
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
+        runs = []
+        for _rep in range(3):                         # three complete repetitions, the median is reported:
+            barrier()                                 # a driver hiccup in create/free (seen: +0.3 s) is not the path
+            t0 = time.perf_counter()
+            e2 = Engine(nChains=CHAINS_PER_GPU, random=2 + rank, device=local_rank, ctasPerChain=args.ctas)
+            e2.set_model(spec_p)                      # H2D of the data set (host pointers)
+            e2.initialize("COPIES")
+            out = e2.run_scans(k_e2e, want=("energy", "swapIndicators", "samples", "logDensity", "nOutOfSupport"))
+            cc = e2.counters()
+            torch.cuda.synchronize(dev)
+            runs.append((time.perf_counter() - t0, cc["evals"]))
+            e2.close()
+        runs.sort()
+        dt, n_evals = runs[1]
+        cc = {"evals": n_evals}
         d2h = sum(v.nbytes for v in out.values()) / k_e2e
         h2d = (xs.nbytes + ys.nbytes) / k_e2e
         e2e_local = cc["evals"] / dt
-        e2.close()
         if world > 1:
             t = torch.tensor([dt, float(cc["evals"])], dtype=torch.float64, device=dev)
             tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -254,8 +259,8 @@ def run_gpu(args):
             e2e_local = float(tsum[1]) / float(tmax[0])
         e2e = {"value": e2e_local, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "what": "blangpt_create + set_model (data set H2D from pinned host memory) + initialize + "
-                       "run_scans(%d) with per-scan outputs copied D2H + counters, wall clock; N independent "
-                       "64-chain engines when N > 1" % k_e2e}
+                       "run_scans(%d) with per-scan outputs copied D2H + counters, wall clock, median of 3 "
+                       "complete repetitions; N independent 64-chain engines when N > 1" % k_e2e}
 
     if rank == 0:
         peak, peak_src = read_peaks()
