@@ -31,7 +31,7 @@ struct blangpt_handle {
   int family = 0;
   int n_reals = 0, n_ints = 0, n_samplers = 0;
   int G = 1;                      // CTAs per chain
-  int logistic_threads = 512;     // CTA size of the C2 kernel (BLANGPT_LOGISTIC_THREADS=512|1024)
+  int logistic_threads = 0;       // CTA size of the C2 kernel: 0 = choose in set_model, or BLANGPT_LOGISTIC_THREADS=256|512|768|1024
   bool model_set = false, tables_valid = false;
   cudaStream_t stream = nullptr;  // nullptr = legacy default stream
   bool own_stream = false;
@@ -107,7 +107,7 @@ extern "C" int blangpt_create(const blangpt_config* cfg, blangpt_handle** out) {
   if (prop.major < 10) { set_error(nullptr, "device sm_%d%d is not Blackwell (kernels are built for sm_100a only)", prop.major, prop.minor); return BLANGPT_ECUDA; }
   blangpt_handle* h = new blangpt_handle();
   h->cfg = *cfg;
-  if (const char* t = getenv("BLANGPT_LOGISTIC_THREADS")) h->logistic_threads = atoi(t) == 1024 ? 1024 : (atoi(t) == 768 ? 768 : 512);
+  if (const char* t = getenv("BLANGPT_LOGISTIC_THREADS")) { const int v = atoi(t); h->logistic_threads = (v == 256 || v == 768 || v == 1024) ? v : 512; }
   h->M_total = (int64_t)cfg->nReplicas * cfg->nChains;
   *out = h;
   return BLANGPT_OK;
@@ -153,6 +153,10 @@ static int launch_explore(blangpt_handle* h, int mode) {
       if (h->logistic_threads == 1024) {
         LogisticFamT<1024>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
         return launch_explore_t<LogisticFamT<1024>>(h, d2, mode);
+      }
+      if (h->logistic_threads == 256) {   // two 256-thread CTAs per SM: another chain's CTA fills this one's barrier waits
+        LogisticFamT<256, 2>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
+        return launch_explore_t<LogisticFamT<256, 2>>(h, d2, mode);
       }
       if (h->logistic_threads == 768) {
         LogisticFamT<768>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
@@ -424,6 +428,9 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
     default: FAIL(h, BLANGPT_EUNSUPPORTED, "unknown model family %d: the engine only runs the closed catalogue (no CPU fallback)", family);
   }
   h->G = family == BLANGPT_FAM_ISING ? 1 : pick_ctas_per_chain(h, rows);
+  // 256 threads x two CTAs per SM x twice the cluster was measured too (another chain's CTA fills this one's
+  // barrier waits): 19.3 vs 19.8 ms per scan with a warm L2, 19.9 vs 19.5 ms under bench.py's L2 flush -> not the default
+  if (family == BLANGPT_FAM_LOGISTIC && h->logistic_threads == 0) h->logistic_threads = 512;
   if (h->G != 1 && h->G != 2 && h->G != 4 && h->G != 8) FAIL(h, BLANGPT_EINVAL, "ctasPerChain must be 1, 2, 4 or 8");
   if ((rc = alloc_engine(h))) return rc;
   // initial state: reals as in the oracle's prototypes (latent scalars start at their constructor value)

@@ -472,8 +472,9 @@ struct NormalFam {
 //     the device copy of X are sign-folded once at set_model, which is exact); a move of w_k
 //     needs only column k of X:  eta_i(x) = eta_i + (x - w_k) * s_i X[i][k]
 // ===========================================================================
-template <int THREADS>
+template <int THREADS, int MINB = 1>
 struct LogisticFamT {
+  static constexpr int kMinBlocks = MINB;   // CTAs per SM the register budget must allow
   struct Data {
     const double* xt;      // [p][npad] column-major, sign-folded copy of the design matrix
     const uint8_t* y;      // [npad]

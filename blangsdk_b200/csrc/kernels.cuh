@@ -172,8 +172,12 @@ BPT_D void explore_chain(const DevEngine& E, Fam& fam, GroupReducer& red, double
   Sync::sync();
 }
 
+// families may state how many CTAs must fit one SM (kMinBlocks): it bounds the registers per thread
+template <class Fam, class = void> struct MinBlocksOf { static constexpr int value = 1; };
+template <class Fam> struct MinBlocksOf<Fam, decltype((void)Fam::kMinBlocks)> { static constexpr int value = Fam::kMinBlocks; };
+
 template <class Fam>
-__global__ void __launch_bounds__(Fam::kThreads)
+__global__ void __launch_bounds__(Fam::kThreads, MinBlocksOf<Fam>::value)
 explore_kernel(DevEngine E, typename Fam::Data D, int G, int mode) {
   __shared__ ReduceSmem rs;
   __shared__ double P[kMaxParams + 4 * 8];

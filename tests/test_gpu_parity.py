@@ -114,6 +114,17 @@ def test_cluster_sizes(oracle, datasets, ctas):
         eng.close()
 
 
+@pytest.mark.parametrize("threads,ctas", [(256, 1), (256, 4), (768, 2), (1024, 2)])
+def test_logistic_cta_shapes(oracle, datasets, monkeypatch, threads, ctas):
+    """the C2 kernel's other CTA shapes (256 threads x two CTAs per SM is what set_model picks for the bench
+    configuration) walk the same trajectory as the oracle"""
+    monkeypatch.setenv("BLANGPT_LOGISTIC_THREADS", str(threads))
+    spec = datasets.logistic_regression(4099, 5)
+    eng, ref = make_pair(oracle, spec, 6, seed=29, ctas=ctas)
+    assert_trajectory_parity(eng, ref, 6)
+    eng.close()
+
+
 @pytest.mark.parametrize("opts", [dict(usePriorSamples=False), dict(reversible=True), dict(annealSupport=False),
                                   dict(nPassesPerScan=2.5), dict(nPassesPerScan=0.5)])
 def test_engine_options(oracle, datasets, opts):
