@@ -1,0 +1,41 @@
+"""-m gpu randomised parity sweep: random family, data size, number of chains, cluster size and engine options;
+the CUDA engine must walk the oracle's trajectory in every case (same bar as test_gpu_parity.py: energies and
+states within 1e-9 relative, swap decisions and evaluation counts identical).  Seeds are fixed, so a failure
+names a reproducible case."""
+import numpy as np
+import pytest
+
+from gpu_util import assert_trajectory_parity, make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(D, rng):
+    fam = ["normal", "logistic", "mixture", "betabinomial", "ising"][rng.integers(0, 5)]
+    if fam == "normal":
+        spec = D.normal_meanvar(n=int(rng.integers(1, 3000)), seed=int(rng.integers(1, 1 << 30)))
+    elif fam == "logistic":
+        spec = D.logistic_regression(int(rng.integers(1, 5000)), int(rng.integers(1, 9)), seed=int(rng.integers(1, 1 << 30)))
+    elif fam == "mixture":
+        spec = D.gaussian_mixture(int(rng.integers(1, 4000)), seed=int(rng.integers(1, 1 << 30)))
+    elif fam == "betabinomial":
+        spec = D.beta_binomial(int(rng.integers(0, 1000)), groups=int(rng.integers(1, 70)), trials=int(rng.integers(1, 80)))
+    else:
+        # the checkerboard sweep needs an even lattice side
+        spec = D.ising(2 * int(rng.integers(1, 7)), moment=float(rng.choice([0.0, 0.1, -0.3])))
+    opts = dict(usePriorSamples=bool(rng.integers(0, 2)), reversible=bool(rng.integers(0, 2)),
+                annealSupport=bool(rng.integers(0, 4) > 0), nPassesPerScan=float(rng.choice([0.5, 1.0, 3.0, 3.7])))
+    ctas = 0 if fam == "ising" else int(rng.choice([0, 1, 2, 4, 8]))
+    return fam, spec, int(rng.integers(1, 14)), int(rng.integers(1, 1 << 20)), ctas, opts
+
+
+@pytest.mark.parametrize("case", range(40))
+def test_random_configuration(oracle, datasets, case):
+    rng = np.random.default_rng(9000 + case)
+    fam, spec, n_chains, seed, ctas, opts = _case(datasets, rng)
+    init = "FORWARD" if rng.integers(0, 3) else "COPIES"
+    eng, ref = make_pair(oracle, spec, n_chains, seed=seed, init=init, ctas=ctas, **opts)
+    try:
+        assert_trajectory_parity(eng, ref, int(rng.integers(2, 7)))
+    finally:
+        eng.close()
