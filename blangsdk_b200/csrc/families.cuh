@@ -800,6 +800,39 @@ struct MixtureFam {
       if (S > 1e-250 && S < 1e250) s += log_tab(S, tab);
       else slow(yv);
     };
+    // 2*kB rows as straight-line code (their exp/log chains interleave); one warp vote decides whether every
+    // lane may keep the lean results, otherwise the rows are redone one by one (same values, same order)
+    auto group = [&](const double2* v, const double2* r, const double2* x1, const double2* x2, int n_valid) {
+      double S[2 * kB], l[2 * kB];
+      bool ok = true;
+#pragma unroll
+      for (int u = 0; u < kB; u++) {
+        const int w = SIMPLEX ? u : 0;
+        const double yv[2] = {v[u].x, v[u].y}, R[2] = {r[u].x, r[u].y};
+        const double E1[2] = {x1[w].x, x1[w].y}, E2[2] = {x2[w].x, x2[w].y};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          if (!SIMPLEX) { const double dd = mu0 - yv[h]; S[2 * u + h] = fma(pi0, exp_tab(fmax(fma(b0, dd * dd, a0), -700.0), tab), R[h]); }
+          else S[2 * u + h] = fma(pi0, E1[h], fma(pi1, E2[h], R[h]));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2 * kB; i++) {
+        l[i] = log_tab(S[i], tab);
+        ok = ok && ((S[i] > 1e-250 && S[i] < 1e250) || (i >> 1) >= n_valid);
+      }
+      if (__all_sync(__activemask(), ok)) {
+#pragma unroll
+        for (int i = 0; i < 2 * kB; i++) if ((i >> 1) < n_valid) s += l[i];
+        return;
+      }
+#pragma unroll
+      for (int u = 0; u < kB; u++)
+        if (u < n_valid) {
+          const int w = SIMPLEX ? u : 0;
+          one(v[u].x, r[u].x, x1[w].x, x2[w].x); one(v[u].y, r[u].y, x1[w].y, x2[w].y);
+        }
+    };
     const int n_pairs = (rr.hi - rr.lo) >> 1;
     const int stride = blockDim.x;
     int p = threadIdx.x;
@@ -827,12 +860,8 @@ struct MixtureFam {
       const int cur = p;
       p += kB * stride;
       if (p < n_pairs) load(p);
-#pragma unroll
-      for (int u = 0; u < kB; u++)
-        if (cur + u * stride < n_pairs) {
-          const int w = SIMPLEX ? u : 0;
-          one(v[u].x, r[u].x, x1[w].x, x2[w].x); one(v[u].y, r[u].y, x1[w].y, x2[w].y);
-        }
+      const int n_valid = min(kB, (n_pairs - cur + stride - 1) / stride);   // pairs of this batch that exist
+      group(v, r, x1, x2, n_valid);
     }
     if (((rr.hi - rr.lo) & 1) && threadIdx.x == 0) {
       const int i = rr.hi - 1;
