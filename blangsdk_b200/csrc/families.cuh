@@ -741,8 +741,9 @@ struct MixtureFam {
     double mu[KT], a[KT], b[KT], pi[KT];
 #pragma unroll
     for (int q = 0; q < KT; q++) { mu[q] = Cst[q]; a[q] = Cst[KT + q]; b[q] = Cst[2 * KT + q]; pi[q] = Cst[3 * KT + q]; }
-    auto one = [&](double yv, double& r_out, double& e1_out, double& e2_out) {
-      double R = 0.0, M = 0.0, E1 = 0.0, E2 = 0.0;
+    // lean evaluation of one row, no side effects: R (unmoved components), S (all), the moved components' densities
+    auto lean = [&](double yv, double& R, double& S, double& E1, double& E2) {
+      double M = 0.0; R = 0.0; E1 = 0.0; E2 = 0.0;
 #pragma unroll
       for (int q0 = 0; q0 < KT; q0 += 4) {
         double arg[4];
@@ -757,17 +758,26 @@ struct MixtureFam {
           if (moved) M = fma(pi[q0 + q], e, M); else R = fma(pi[q0 + q], e, R);
         }
       }
-      const double S = R + M;
+      S = R + M;
+    };
+    auto one = [&](double yv, double& r_out, double& e1_out, double& e2_out) {
+      double R, S;
+      lean(yv, R, S, e1_out, e2_out);
       if (S > 1e-250 && S < 1e250) { s += log_tab(S, tab); r_out = R; }
       else { obs_slow(yv, mu, a, b, pi, s, c); r_out = CUDART_NAN; }   // NaN marks a row the cached passes redo literally
-      e1_out = E1; e2_out = E2;
     };
     const int n_pairs = (rr.hi - rr.lo) >> 1;
     for (int p = threadIdx.x; p < n_pairs; p += blockDim.x) {
       const int i = rr.lo + 2 * p;
       const double2 v = *reinterpret_cast<const double2*>(d.y + i);
       double2 r, x1, x2;
-      one(v.x, r.x, x1.x, x2.x); one(v.y, r.y, x1.y, x2.y);
+      // both rows as straight-line code; one warp vote decides whether all lanes keep the lean logs
+      double S0, S1;
+      lean(v.x, r.x, S0, x1.x, x2.x); lean(v.y, r.y, S1, x1.y, x2.y);
+      const double l0 = log_tab(S0, tab), l1 = log_tab(S1, tab);
+      const bool ok = S0 > 1e-250 && S0 < 1e250 && S1 > 1e-250 && S1 < 1e250;
+      if (__all_sync(__activemask(), ok)) { s += l0; s += l1; }
+      else { one(v.x, r.x, x1.x, x2.x); one(v.y, r.y, x1.y, x2.y); }
       *reinterpret_cast<double2*>(rest + i) = r;
       if (j1 >= 0) { *reinterpret_cast<double2*>(e1 + i) = x1; *reinterpret_cast<double2*>(e2 + i) = x2; }
     }
