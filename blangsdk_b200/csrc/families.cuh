@@ -885,7 +885,7 @@ struct MixtureFam {
     stage_constants(k, x, aux);
     double acc = 0.0; int cnt = 0;
     if (first) { pass_first(j0, j1, acc, cnt); first = false; }
-    else if (j1 < 0) pass_cached<false, 4>(j0, j1, acc, cnt);
+    else if (j1 < 0) pass_cached<false, 2>(j0, j1, acc, cnt);
     else pass_cached<true, 2>(j0, j1, acc, cnt);
     red.reduce(acc, cnt);
     s = acc; c = cnt;
