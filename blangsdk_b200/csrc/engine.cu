@@ -31,6 +31,7 @@ struct blangpt_handle {
   int family = 0;
   int n_reals = 0, n_ints = 0, n_samplers = 0;
   int G = 1;                      // CTAs per chain
+  bool logistic_l2ahead = false;  // eta cache > L2: use the kernel variant with L2 prefetch hints
   int logistic_threads = 0;       // CTA size of the C2 kernel: 0 = choose in set_model, or BLANGPT_LOGISTIC_THREADS=256|512|768|1024
   bool model_set = false, tables_valid = false;
   cudaStream_t stream = nullptr;  // nullptr = legacy default stream
@@ -157,6 +158,10 @@ static int launch_explore(blangpt_handle* h, int mode) {
       if (h->logistic_threads == 256) {   // two 256-thread CTAs per SM: another chain's CTA fills this one's barrier waits
         LogisticFamT<256, 2>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
         return launch_explore_t<LogisticFamT<256, 2>>(h, d2, mode);
+      }
+      if (h->logistic_l2ahead) {   // per-chain cache larger than the L2: stream it with L2 prefetch hints
+        LogisticFamT<512, 1, 3>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
+        return launch_explore_t<LogisticFamT<512, 1, 3>>(h, d2, mode);
       }
       if (h->logistic_threads == 768) {
         LogisticFamT<768>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
@@ -430,7 +435,14 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
   h->G = family == BLANGPT_FAM_ISING ? 1 : pick_ctas_per_chain(h, rows);
   // 256 threads x two CTAs per SM x twice the cluster was measured too (another chain's CTA fills this one's
   // barrier waits): 19.3 vs 19.8 ms per scan with a warm L2, 19.9 vs 19.5 ms under bench.py's L2 flush -> not the default
-  if (family == BLANGPT_FAM_LOGISTIC && h->logistic_threads == 0) h->logistic_threads = 512;
+  if (family == BLANGPT_FAM_LOGISTIC && h->logistic_threads == 0) {
+    h->logistic_threads = 512;
+    int l2 = 0;
+    cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, c.device);
+    const size_t cache_bytes = (size_t)h->logistic.npad * (h->M_total / c.worldSize) * sizeof(double);
+    h->logistic_l2ahead = l2 > 0 && cache_bytes + (size_t)h->logistic.npad * h->logistic.p * sizeof(double) > (size_t)l2;
+    if (const char* t = getenv("BLANGPT_L2AHEAD")) h->logistic_l2ahead = atoi(t) != 0;
+  }
   if (h->G != 1 && h->G != 2 && h->G != 4 && h->G != 8) FAIL(h, BLANGPT_EINVAL, "ctasPerChain must be 1, 2, 4 or 8");
   if ((rc = alloc_engine(h))) return rc;
   // initial state: reals as in the oracle's prototypes (latent scalars start at their constructor value)

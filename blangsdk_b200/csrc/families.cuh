@@ -502,9 +502,12 @@ struct NormalFam {
 //     the device copy of X are sign-folded once at set_model, which is exact); a move of w_k
 //     needs only column k of X:  eta_i(x) = eta_i + (x - w_k) * s_i X[i][k]
 // ===========================================================================
-template <int THREADS, int MINB = 1>
+template <int THREADS, int MINB = 1, int L2AHEAD = 0>
 struct LogisticFamT {
   static constexpr int kMinBlocks = MINB;   // CTAs per SM the register budget must allow
+  // L2AHEAD > 0: the per-chain cache does not fit the L2 (many chains per GPU) and streams from HBM; each step
+  // also asks the L2 for the cache lines L2AHEAD steps ahead, so the register prefetch (one step) only ever
+  // waits for an L2 hit
   struct Data {
     const double* xt;      // [p][npad] column-major, sign-folded copy of the design matrix
     const uint8_t* y;      // [npad]
@@ -550,11 +553,13 @@ struct LogisticFamT {
     while (whole >= 32) {
       whole -= THREADS;
       if (whole >= 32) { eb = pe[THREADS]; xb = px[THREADS]; }
+      if (L2AHEAD > 0 && (threadIdx.x & 7) == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(pe + (1 + L2AHEAD) * THREADS));
       logit_pair<true>(fma(delta, xa.x, ea.x), fma(delta, xa.y, ea.y), py, acc, cnt, err, tab);
       pe += THREADS; px += THREADS; py += 2 * THREADS;
       if (whole < 32) break;
       whole -= THREADS;
       if (whole >= 32) { ea = pe[THREADS]; xa = px[THREADS]; }
+      if (L2AHEAD > 0 && (threadIdx.x & 7) == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(pe + (1 + L2AHEAD) * THREADS));
       logit_pair<true>(fma(delta, xb.x, eb.x), fma(delta, xb.y, eb.y), py, acc, cnt, err, tab);
       pe += THREADS; px += THREADS; py += 2 * THREADS;
     }

@@ -114,11 +114,14 @@ def test_cluster_sizes(oracle, datasets, ctas):
         eng.close()
 
 
-@pytest.mark.parametrize("threads,ctas", [(256, 1), (256, 4), (768, 2), (1024, 2)])
+@pytest.mark.parametrize("threads,ctas", [(256, 1), (256, 4), (768, 2), (1024, 2), ("l2ahead", 1), ("l2ahead", 2)])
 def test_logistic_cta_shapes(oracle, datasets, monkeypatch, threads, ctas):
-    """the C2 kernel's other CTA shapes (256 threads x two CTAs per SM is what set_model picks for the bench
-    configuration) walk the same trajectory as the oracle"""
-    monkeypatch.setenv("BLANGPT_LOGISTIC_THREADS", str(threads))
+    """the C2 kernel's other shapes (256/768/1024-thread CTAs; the variant with L2 prefetch hints that set_model
+    picks when the per-chain caches exceed the L2) walk the same trajectory as the oracle"""
+    if threads == "l2ahead":
+        monkeypatch.setenv("BLANGPT_L2AHEAD", "1")
+    else:
+        monkeypatch.setenv("BLANGPT_LOGISTIC_THREADS", str(threads))
     spec = datasets.logistic_regression(4099, 5)
     eng, ref = make_pair(oracle, spec, 6, seed=29, ctas=ctas)
     assert_trajectory_parity(eng, ref, 6)
