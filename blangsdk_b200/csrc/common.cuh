@@ -114,6 +114,16 @@ BPT_HD double gen_gamma(Rng& r, double shape, double rate) {
   if (result == 0.0) result = 1e-300;   // ZERO_PLUS_EPS :322
   return result;
 }
+// :143-152.  commons-math3's BetaDistribution.sample() is Cheng's BB/BC rejection sampler; the draw stream is
+// unpinned against the JVM anyway, so this uses the two-gamma identity X / (X + Y) and keeps the end-point guards
+BPT_HD double gen_beta(Rng& r, double alpha, double beta) {
+  const double x = gen_gamma(r, alpha, 1.0);
+  const double y = gen_gamma(r, beta, 1.0);
+  double result = x / (x + y);
+  if (result == 0.0) result = 1e-300;
+  if (result == 1.0) result = 1.0 - 1e-16;   // ONE_MINUS_EPS :323
+  return result;
+}
 
 // ---- R/mcmc/internals/ExponentiatedFactor.java:82-87 ----------------------
 BPT_HD double annealed_minus_infinity(double exponent) {

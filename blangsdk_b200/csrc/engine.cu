@@ -41,6 +41,7 @@ struct blangpt_handle {
   DevStats St{};
   // family data
   NormalFam::Data normal{};
+  IidFam::Data iid{};
   LogisticFam::Data logistic{};
   MixtureFam<4>::Data mixture{};
   BetaBinomialFam::Data betabin{};
@@ -150,6 +151,7 @@ static int launch_explore_t(blangpt_handle* h, const typename Fam::Data& D, int 
 static int launch_explore(blangpt_handle* h, int mode) {
   switch (h->family) {
     case BLANGPT_FAM_NORMAL: return launch_explore_t<NormalFam>(h, h->normal, mode);
+    case BLANGPT_FAM_IID: return launch_explore_t<IidFam>(h, h->iid, mode);
     case BLANGPT_FAM_LOGISTIC:
       if (h->logistic_threads == 1024) {
         LogisticFamT<1024>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
@@ -190,6 +192,7 @@ static bool use_fused(const blangpt_handle* h) {
   const bool forced = env && atoi(env) == 1;
   if (h->family == BLANGPT_FAM_BETABINOMIAL) return forced || h->cfg.nReplicas >= 8;
   if (h->family == BLANGPT_FAM_NORMAL) return h->normal.n <= 65536 && (forced || h->cfg.nReplicas >= 8);
+  if (h->family == BLANGPT_FAM_IID) return h->iid.n <= 65536 && (forced || h->cfg.nReplicas >= 8);
   return false;
 }
 
@@ -356,6 +359,32 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
       CUDA_OK(h, cudaMemcpyAsync(y, a[0].data, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
       h->normal = {y, n, hyper[0], hyper[1], hyper[2]};
       h->n_reals = 2; h->n_samplers = 2; rows = n;
+    } break;
+    case BLANGPT_FAM_IID: {
+      static const int n_params_of[] = {0, 1, 1, 2, 3, 1, 2};
+      const int dist = nh >= 1 ? (int)hyper[0] : 0;
+      if (dist < IID_POISSON || dist > IID_LAPLACE) FAIL(h, BLANGPT_EUNSUPPORTED, "iid: unknown distribution code %d", dist);
+      const int P = n_params_of[dist];
+      if (nh != 1 + 3 * P) FAIL(h, BLANGPT_EINVAL, "iid: hyper must be (dist, then kind, a, b for each of the %d parameters)", P);
+      const int want_arrays = dist == IID_BINOMIAL ? 2 : 1;
+      if (na != want_arrays || a[0].dtype != BLANGPT_F64 || (na == 2 && (a[1].dtype != BLANGPT_F64 || a[1].n_elem != a[0].n_elem)))
+        FAIL(h, BLANGPT_EINVAL, "iid: expects y[f64 n]%s", dist == IID_BINOMIAL ? ", trials[f64 n]" : "");
+      const int n = (int)a[0].n_elem;
+      double *y, *tr = nullptr;
+      if ((rc = dev_alloc(h, &y, n + 2))) return rc;
+      CUDA_OK(h, cudaMemcpyAsync(y, a[0].data, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      if (na == 2) {
+        if ((rc = dev_alloc(h, &tr, n + 2))) return rc;
+        CUDA_OK(h, cudaMemcpyAsync(tr, a[1].data, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      }
+      h->iid = IidFam::Data{};
+      h->iid.y = y; h->iid.trials = tr; h->iid.n = n; h->iid.dist = dist; h->iid.n_params = P;
+      for (int j = 0; j < P; j++) {
+        const int kind = (int)hyper[1 + 3 * j];
+        if (kind < PRIOR_NORMAL || kind > PRIOR_UNIFORM) FAIL(h, BLANGPT_EUNSUPPORTED, "iid: unknown prior code %d", kind);
+        h->iid.prior_kind[j] = kind; h->iid.prior_a[j] = hyper[2 + 3 * j]; h->iid.prior_b[j] = hyper[3 + 3 * j];
+      }
+      h->n_reals = P; h->n_samplers = P; rows = n;
     } break;
     case BLANGPT_FAM_LOGISTIC: {
       if (na != 2 || nh != 1 || a[0].dtype != BLANGPT_F64 || a[1].dtype != BLANGPT_I32) FAIL(h, BLANGPT_EINVAL, "logistic: expects x[f64 n*p], y[i32 n], hyper (v0)");
@@ -627,7 +656,7 @@ static int scm_initialize(blangpt_handle* h) {
   c->cfg.random = h->cfg.random ^ 0x53434D2D696E6974ULL;   // its own Philox key ("SCM-init")
   c->M_total = P; c->family = h->family; c->stream = h->stream; c->logistic_threads = h->logistic_threads;
   c->n_reals = h->n_reals; c->n_ints = h->n_ints; c->n_samplers = h->n_samplers;
-  c->normal = h->normal; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising;
+  c->normal = h->normal; c->iid = h->iid; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising;
   c->betabin.chains_per_replica = P;
   auto fail = [&](int code) { for (void* p : c->allocs) cudaFree(p); if (code) h->error = c->error; delete c; return code; };
   if (h->family == BLANGPT_FAM_LOGISTIC && (rc = dev_alloc(c, &c->logistic.eta, (size_t)c->logistic.npad * P))) return fail(rc);
@@ -637,7 +666,7 @@ static int scm_initialize(blangpt_handle* h) {
     if ((rc = dev_alloc(c, &c->mixture.rest, sz, false)) || (rc = dev_alloc(c, &c->mixture.e1, sz, false)) ||
         (rc = dev_alloc(c, &c->mixture.e2, sz, false))) return fail(rc);
   }
-  int64_t rows = h->family == BLANGPT_FAM_NORMAL ? h->normal.n : h->family == BLANGPT_FAM_LOGISTIC ? h->logistic.n
+  int64_t rows = h->family == BLANGPT_FAM_NORMAL ? h->normal.n : h->family == BLANGPT_FAM_IID ? h->iid.n : h->family == BLANGPT_FAM_LOGISTIC ? h->logistic.n
                : h->family == BLANGPT_FAM_MIXTURE ? h->mixture.n : 1;
   c->G = h->family == BLANGPT_FAM_ISING || h->family == BLANGPT_FAM_BETABINOMIAL ? 1 : pick_ctas_per_chain(c, rows);
   if ((rc = alloc_engine(c))) return fail(rc);
@@ -820,6 +849,7 @@ extern "C" int blangpt_run_scans(blangpt_handle* h, int32_t n_scans, const blang
   if (use_fused(h)) {   // many small replicas: the whole batch of scans in one launch, one warp per chain
     const int threads = 32 * h->cfg.nChains;
     if (h->family == BLANGPT_FAM_NORMAL) replica_kernel<NormalFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->normal, n_scans);
+    else if (h->family == BLANGPT_FAM_IID) replica_kernel<IidFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->iid, n_scans);
     else replica_kernel<BetaBinomialFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->betabin, n_scans);
     CUDA_OK(h, cudaGetLastError());
     h->n_launches++;

@@ -497,6 +497,179 @@ struct NormalFam {
 };
 
 // ===========================================================================
+// Family 6: i.i.d. observations from a law with 1-3 latent parameters, each with its own prior (SURVEY 8(f)-4:
+// more of R/distributions/*.bl).  Every law of the distribution is one factor PER OBSERVATION, also the laws that
+// read only parameters (Poisson's -mean, Student's -log sigma ...): n of them, and n out-of-support counts.
+// ===========================================================================
+enum { IID_POISSON = 1, IID_BINOMIAL = 2, IID_NEGBINOMIAL = 3, IID_STUDENTT = 4, IID_GEOMETRIC = 5, IID_LAPLACE = 6 };
+enum { PRIOR_NORMAL = 0, PRIOR_GAMMA = 1, PRIOR_EXPONENTIAL = 2, PRIOR_BETA = 3, PRIOR_UNIFORM = 4 };
+
+struct IidFam {
+  struct Data {
+    const double* y; const double* trials; int n, dist, n_params;
+    int prior_kind[3]; double prior_a[3], prior_b[3];
+  };
+  static constexpr int kThreads = 128;
+  static constexpr bool kWarpCapable = true;
+  Data d; double* P; RowRange rr; int* err;
+  int t0, tn;   // this thread's index in the chain group and the group size
+
+  BPT_D static int n_reals(const Data& d) { return d.n_params; }
+  BPT_D static int n_samplers(const Data& d) { return d.n_params; }
+  BPT_D void init(const Data& d_, int, double* P_, int G, int crank, int* err_) {
+    d = d_; P = P_; rr = group_rows(d.n, G, crank); err = err_; t0 = threadIdx.x; tn = blockDim.x;
+  }
+  BPT_D void set_lanes(int lane, int width) { t0 = lane; tn = width; }
+  BPT_D int sampler_type(int) const { return S_REAL_SLICE; }
+  BPT_D int sampler_var(int k) const { return k; }
+  BPT_D int simplex_dim() const { return 0; }
+  BPT_D void begin_execution() {}
+  BPT_D static void tables_init() {}
+
+  // the prior's factors that read the realization
+  BPT_D double fixed(int k, double x, int) const {
+    const double a = d.prior_a[k], b = d.prior_b[k];
+    switch (d.prior_kind[k]) {
+      case PRIOR_NORMAL: return normal_f2(a, b, x);
+      case PRIOR_GAMMA: return gamma_ab(a, b, x);
+      case PRIOR_EXPONENTIAL: return gamma_ab(1.0, a, x);          // Exponential.bl:11 -> Gamma(1.0, rate)
+      case PRIOR_BETA:                                                // Beta.bl:14-27
+        if (x <= 0.0 || x >= 1.0 || a <= 0.0 || b <= 0.0) return BPT_NEG_INF;
+        return (a - 1.0) * log(x) + (b - 1.0) * log1p(-x);
+      default: return (a <= x && x <= b) ? 0.0 : BPT_NEG_INF;       // ContinuousUniform.bl:16-19
+    }
+  }
+  // the prior's constant factors
+  BPT_D double fixed_constants(int k) const {
+    const double a = d.prior_a[k], b = d.prior_b[k];
+    switch (d.prior_kind[k]) {
+      case PRIOR_NORMAL: return -0.5 * BPT_LOG_2PI + (b <= 0.0 ? BPT_NEG_INF : -0.5 * log(b));
+      case PRIOR_GAMMA: return gamma_cd(a, b);
+      case PRIOR_EXPONENTIAL: return gamma_cd(1.0, a);
+      case PRIOR_BETA: return (a <= 0.0 || b <= 0.0) ? BPT_NEG_INF : lgamma(a + b) - lgamma(a) - lgamma(b);
+      default: return (b - a <= 0.0) ? BPT_NEG_INF : -log(b - a);
+    }
+  }
+  // Sum and out-of-support count of the annealed factors connected to parameter k (k < 0: of all of them),
+  // at parameters th.  Parameter-only laws are evaluated once and counted n times.
+  BPT_D void factors(int k, const double* th, GroupReducer& red, double& s, int& c) const {
+    const int n = d.n;
+    double acc = 0.0, par = 0.0; int cnt = 0, pc = 0;
+    const bool all = k < 0;
+    switch (d.dist) {
+      case IID_POISSON: {                                     // Poisson.bl:11-26
+        const double mean = th[0];
+        const bool bad = mean <= 0.0;
+        const double L = bad ? 0.0 : log(mean);
+        if (bad) pc += 2 * n; else par += n * (-mean);
+        for (int i = rr.lo + t0; i < rr.hi; i += tn) {
+          const double y = d.y[i];
+          if (!bad) { if (y < 0.0) cnt++; else acc += y * L; }
+          if (all) { if (y < 0.0) cnt++; else acc += -lgamma(y + 1.0); }
+        }
+      } break;
+      case IID_BINOMIAL: {                                    // Binomial.bl:14-27
+        const double p = th[0];
+        const bool bad = p < 0.0 || p > 1.0;
+        const double lp = log(p), lq = log(1.0 - p);
+        if (bad) pc += n;
+        for (int i = rr.lo + t0; i < rr.hi; i += tn) {
+          const double y = d.y[i], m = d.trials[i];
+          const bool bad_row = y < 0.0 || m <= 0.0 || y > m;
+          if (!bad) { if (bad_row) cnt++; else acc_term(y * lp + (m - y) * lq, acc, cnt, err); }   // p = 0 or 1: -inf / NaN as in Java
+          if (all) { if (bad_row) cnt++; else acc += lgamma(m + 1.0) - lgamma(y + 1.0) - lgamma(m - y + 1.0); }
+        }
+      } break;
+      case IID_NEGBINOMIAL: {                                 // NegativeBinomial.bl:14-28
+        const double r = th[0], p = th[1];
+        const bool bad_r = r <= 0.0, bad_p = p <= 0.0 || p >= 1.0;
+        const double lp = log(p), lq = log(1.0 - p);
+        const bool f1 = all || k == 0;                        // logBinomial(k + r - 1, k): reads r
+        if (f1 && bad_r) pc += n;
+        if (bad_p || bad_r) pc += n;
+        for (int i = rr.lo + t0; i < rr.hi; i += tn) {
+          const double y = d.y[i];
+          if (f1 && !bad_r) {
+            if (y < 0.0) cnt++;
+            else {
+              const double nn = y + r - 1.0;
+              const double t = lgamma(nn + 1.0) - lgamma(y + 1.0) - lgamma(nn - y + 1.0);
+              if (t != t) cnt++; else acc_term(t, acc, cnt, err);
+            }
+          }
+          if (!(bad_p || bad_r)) { if (y < 0.0) cnt++; else acc_term(y * lp + r * lq, acc, cnt, err); }
+        }
+      } break;
+      case IID_STUDENTT: {                                    // StudentT.bl:13-33
+        const double nu = th[0], mu = th[1], sigma = th[2];
+        const bool bad = nu <= 0.0 || sigma <= 0.0;
+        if (all) par += n * (-0.5 * log(3.14159265358979323846));
+        if (all || k == 2) { if (sigma <= 0.0) pc += n; else par += n * (-log(sigma)); }
+        if (all || k == 0) { if (nu <= 0.0) pc += n; else par += n * (lgamma((nu + 1.0) / 2.0) - 0.5 * log(nu) - lgamma(nu / 2.0)); }
+        if (bad) pc += n;
+        else {
+          const double h = -((nu + 1.0) / 2.0), w = (1.0 / nu) * (1.0 / (sigma * sigma));
+          for (int i = rr.lo + t0; i < rr.hi; i += tn) {
+            const double dy = d.y[i] - mu;
+            acc_term(h * log(1.0 + w * (dy * dy)), acc, cnt, err);
+          }
+        }
+      } break;
+      case IID_GEOMETRIC: {                                   // Geometric.bl:10-16
+        const double p = th[0];
+        const bool bad = p <= 0.0 || p >= 1.0;
+        if (bad) pc += n;
+        else {
+          const double lq = log(1.0 - p), lp = log(p);
+          for (int i = rr.lo + t0; i < rr.hi; i += tn) {
+            const double y = d.y[i];
+            if (y < 0.0) cnt++; else acc += y * lq + lp;
+          }
+        }
+      } break;
+      default: {                                              // Laplace.bl:12-17
+        const double loc = th[0], scale = th[1];
+        if (scale <= 0.0) pc += n;
+        else {
+          const double l2 = -log(2.0 * scale);
+          for (int i = rr.lo + t0; i < rr.hi; i += tn) acc_term(l2 - fabs(d.y[i] - loc) / scale, acc, cnt, err);
+        }
+      } break;
+    }
+    red.reduce(acc, cnt);
+    s = acc + par; c = cnt + pc;
+  }
+  BPT_D void annealed(int k, double x, int, GroupReducer& red, double& s, int& c) const {
+    double th[3] = {P[0], d.n_params > 1 ? P[1] : 0.0, d.n_params > 2 ? P[2] : 0.0};
+    th[k] = x;
+    factors(k, th, red, s, c);
+  }
+  BPT_D void commit(int k, double x, int) { P[k] = x; }
+  BPT_D void refresh() {}
+  BPT_D void full(GroupReducer& red, double& loglik, int& noos, double& logprior) const {
+    const double th[3] = {P[0], d.n_params > 1 ? P[1] : 0.0, d.n_params > 2 ? P[2] : 0.0};
+    factors(-1, th, red, loglik, noos);
+    double lp = 0.0;
+    for (int j = 0; j < d.n_params; j++) lp += fixed_constants(j) + fixed(j, P[j], 0);
+    logprior = lp;
+  }
+  BPT_D void forward(Rng& rng) {   // declaration order
+    for (int j = 0; j < d.n_params; j++) {
+      const double a = d.prior_a[j], b = d.prior_b[j];
+      double v;
+      switch (d.prior_kind[j]) {
+        case PRIOR_NORMAL: v = gen_normal(rng, a, b); break;
+        case PRIOR_GAMMA: v = gen_gamma(rng, a, b); break;
+        case PRIOR_EXPONENTIAL: v = gen_exponential(rng, a); break;
+        case PRIOR_BETA: v = gen_beta(rng, a, b); break;
+        default: v = gen_uniform(rng, a, b); break;
+      }
+      P[j] = v;
+    }
+  }
+};
+
+// ===========================================================================
 // C2  Bayesian logistic regression.  P = w[0..p)
 //     per-chain cache eta_i = s_i * (x_i . w) in HBM, s_i = +1 if y_i = 1 else -1 (the rows of
 //     the device copy of X are sign-folded once at set_model, which is exact); a move of w_k

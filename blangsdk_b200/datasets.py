@@ -62,3 +62,38 @@ def beta_binomial_batch(n_replicas=4096, groups=32, trials=50, seed=SEED_C5):
     ys = np.stack([beta_binomial(r, groups, trials, seed)["y"] for r in range(n_replicas)])
     return dict(family="betabinomial", hyper=dict(rate=0.1), y=ys,
                 ntrials=np.full((n_replicas, groups), trials, dtype=np.int32))
+
+
+SEED_IID = 20240006
+
+
+def iid_observations(dist="poisson", n=2000, seed=SEED_IID):
+    """Family "iid" (SURVEY 8(f)-4): y_i ~ Dist(theta) i.i.d. with one prior per parameter.  Parameters in the
+    reference's declaration order: poisson (mean), binomial (p; trials are data), negbinomial (r, p),
+    studentt (nu, mu, sigma), geometric (p), laplace (location, scale)."""
+    rng = np.random.default_rng(seed + sum(map(ord, dist)))
+    spec = dict(family="iid", trials=None)
+    if dist == "poisson":
+        spec["y"] = rng.poisson(4.2, n).astype(np.float64)
+        priors = [("exponential", 0.1)]
+    elif dist == "binomial":
+        tr = rng.integers(1, 40, n)
+        spec["y"] = rng.binomial(tr, 0.3).astype(np.float64)
+        spec["trials"] = tr.astype(np.float64)
+        priors = [("beta", 2.0, 3.0)]
+    elif dist == "negbinomial":
+        spec["y"] = rng.negative_binomial(3.0, 0.4, n).astype(np.float64)   # numpy counts failures with success prob 0.4
+        priors = [("gamma", 2.0, 0.5), ("uniform", 0.0, 1.0)]
+    elif dist == "studentt":
+        spec["y"] = 1.0 + 2.0 * rng.standard_t(4.0, n)
+        priors = [("exponential", 0.1), ("normal", 0.0, 100.0), ("exponential", 0.5)]
+    elif dist == "geometric":
+        spec["y"] = (rng.geometric(0.25, n) - 1).astype(np.float64)          # failures before the first success
+        priors = [("uniform", 0.0, 1.0)]
+    elif dist == "laplace":
+        spec["y"] = rng.laplace(-0.5, 1.5, n)
+        priors = [("normal", 0.0, 25.0), ("gamma", 2.0, 1.0)]
+    else:
+        raise ValueError(dist)
+    spec["hyper"] = dict(dist=dist, priors=priors)
+    return spec

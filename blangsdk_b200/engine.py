@@ -20,7 +20,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libblangpt.so")
 
-FAMILIES = {"normal": 1, "logistic": 2, "mixture": 3, "ising": 4, "betabinomial": 5}
+FAMILIES = {"normal": 1, "logistic": 2, "mixture": 3, "ising": 4, "betabinomial": 5, "iid": 6}
+# family "iid" (include/blangpt.h BLANGPT_IID_* / BLANGPT_PRIOR_*): observation laws and priors
+IID_DISTS = {"poisson": 1, "binomial": 2, "negbinomial": 3, "studentt": 4, "geometric": 5, "laplace": 6}
+IID_PRIORS = {"normal": 0, "gamma": 1, "exponential": 2, "beta": 3, "uniform": 4}
 INIT = {"COPIES": 0, "FORWARD": 1, "SCM": 2}
 
 _dp = C.POINTER(C.c_double)
@@ -268,6 +271,17 @@ class Engine:
             arrays, hyper = [], [float(h["N"]), h["coupling"], h["moment"]]
         elif fam == "betabinomial":
             arrays, hyper = [arr(spec["y"], 1), arr(spec["ntrials"], 1)], [h["rate"]]
+        elif fam == "iid":
+            if h["dist"] not in IID_DISTS:
+                raise BlangPTError("iid: unsupported distribution %r" % (h["dist"],))
+            arrays = [arr(spec["y"], 0)]
+            if h["dist"] == "binomial":
+                arrays.append(arr(spec["trials"], 0))
+            hyper = [float(IID_DISTS[h["dist"]])]
+            for p in h["priors"]:       # (kind, a[, b]) per parameter, declaration order
+                if p[0] not in IID_PRIORS:
+                    raise BlangPTError("iid: unsupported prior %r" % (p[0],))
+                hyper += [float(IID_PRIORS[p[0]]), float(p[1]), float(p[2]) if len(p) > 2 else 0.0]
         else:
             raise BlangPTError("unsupported model family %r (closed catalogue; no CPU fallback)" % fam)
         ca = (Array * max(1, len(arrays)))(*arrays)

@@ -30,6 +30,11 @@ VARIABLES = {
     "betabinomial": [("alpha", None, 0, 1), ("beta", None, 1, 1)],
     "ising": [("vertices", "index_0", 0, None)],
 }
+# family "iid": the latent parameters of each observation law, named as in R/distributions/<Name>.bl
+IID_VARIABLES = {
+    "poisson": ["mean"], "binomial": ["probabilityOfSuccess"], "negbinomial": ["r", "p"],
+    "studentt": ["nu", "mu", "sigma"], "geometric": ["p"], "laplace": ["location", "scale"],
+}
 
 
 def _fmt(v):
@@ -119,6 +124,9 @@ class PTResultsWriter:
         self.thinning = thinning
         self.estimator = logNormalizationEstimator
         self.K = int(hyper["K"]) if hyper and "K" in hyper else None
+        self.variables = VARIABLES.get(family)
+        if family == "iid":
+            self.variables = [(name, None, j, 1) for j, name in enumerate(IID_VARIABLES[hyper["dist"]])]
 
     def _resolve(self, v, n_reals):
         if v is None:
@@ -147,7 +155,7 @@ class PTResultsWriter:
         if "samples" in out or "intSamples" in out:
             vals = out["samples"][:, 0, :] if "samples" in out else out["intSamples"][:, 0, :]
             n_reals = vals.shape[1]
-            for name, index_col, start, count in VARIABLES[self.family]:
+            for name, index_col, start, count in self.variables:
                 a = self._resolve(start, n_reals)
                 c = self._resolve(count, n_reals) if count is not None else n_reals - a
                 block = vals[keep, a:a + c]

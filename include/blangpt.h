@@ -46,7 +46,23 @@ enum {
   BLANGPT_FAM_LOGISTIC = 2,     /* data: x[n*p] f64 row-major, y[n] i32. hyper: v0       */
   BLANGPT_FAM_MIXTURE = 3,      /* data: y[n] f64. hyper: K, m0, v0, gshape, grate, conc */
   BLANGPT_FAM_ISING = 4,        /* no data.       hyper: N, coupling, moment             */
-  BLANGPT_FAM_BETABINOMIAL = 5  /* data: y[R*n] i32, ntrials[R*n] i32. hyper: rate       */
+  BLANGPT_FAM_BETABINOMIAL = 5, /* data: y[R*n] i32, ntrials[R*n] i32. hyper: rate       */
+  BLANGPT_FAM_IID = 6           /* y_i ~ Dist(theta) i.i.d., theta_j ~ prior_j.  data: y[n] f64 (+ trials[n] f64 for
+                                   BINOMIAL).  hyper: dist, then (prior kind, a, b) for each parameter            */
+};
+/* family 6: observation laws (R/distributions/<Name>.bl) and their latent parameters, in this order */
+enum {
+  BLANGPT_IID_POISSON = 1,      /* mean                 */
+  BLANGPT_IID_BINOMIAL = 2,     /* p                    */
+  BLANGPT_IID_NEGBINOMIAL = 3,  /* r, p                 */
+  BLANGPT_IID_STUDENTT = 4,     /* nu, mu, sigma        */
+  BLANGPT_IID_GEOMETRIC = 5,    /* p                    */
+  BLANGPT_IID_LAPLACE = 6       /* location, scale      */
+};
+/* family 6: priors; (a, b) = (mean, variance) | (shape, rate) | (rate, unused) | (alpha, beta) | (min, max) */
+enum {
+  BLANGPT_PRIOR_NORMAL = 0, BLANGPT_PRIOR_GAMMA = 1, BLANGPT_PRIOR_EXPONENTIAL = 2, BLANGPT_PRIOR_BETA = 3,
+  BLANGPT_PRIOR_UNIFORM = 4
 };
 
 /* PT.InitType (R/engines/internals/factories/PT.java:267) */

@@ -147,6 +147,17 @@ static double gen_gamma(Rng* r, double shape, double rate) {
   if (result == 0.0) result = ZERO_PLUS_EPS;
   return result;
 }
+/* Generators.beta :143-152.  commons-math3's BetaDistribution.sample() is Cheng's BB/BC rejection sampler; the
+ * draw stream is unpinned against the JVM anyway, so the restatement uses the two-gamma identity
+ * X / (X + Y), X ~ Gamma(alpha, 1), Y ~ Gamma(beta, 1), and keeps the reference's end-point guards. */
+static double gen_beta(Rng* r, double alpha, double beta) {
+  double x = gen_gamma(r, alpha, 1.0);
+  double y = gen_gamma(r, beta, 1.0);
+  double result = x / (x + y);
+  if (result == 0.0) result = ZERO_PLUS_EPS;
+  if (result == 1.0) result = ONE_MINUS_EPS;
+  return result;
+}
 
 /* ------------------------------------------------------------------ */
 /* bayonet.math (third party, restated from published definitions)      */
@@ -198,7 +209,16 @@ enum {
   F_DIRICHLET_A,      /* Dirichlet.bl:13-22 conc = c0 (symmetric), simplex = reals i0..i0+i1-1 */
   F_ISING_EDGE,       /* F/Ising.bl:15-24  spins i0,i1, coupling c0                      */
   F_BERN_NODE,        /* F/Ising.bl:27-29 -> Bernoulli.bl -> Categorical.bl; spin i0, p=c0 */
-  F_BETABINOM         /* BetaBinomial.bl:17-30 group i0, alpha = real i1, beta = real i2 */
+  F_BETABINOM,        /* BetaBinomial.bl:17-30 group i0, alpha = real i1, beta = real i2 */
+  /* family 6 (iid observations y[i0], optional trials x[i0], parameters = reals 0..2 in the order below) */
+  F_POIS_1, F_POIS_2, F_POIS_3,            /* Poisson.bl:11-26            reals: mean                */
+  F_BINOM_1, F_BINOM_2,                    /* Binomial.bl:14-27           reals: p; trials in x[]    */
+  F_NEGBIN_1, F_NEGBIN_2,                  /* NegativeBinomial.bl:14-28   reals: r, p                */
+  F_STUD_2, F_STUD_3, F_STUD_4,            /* StudentT.bl:13-33           reals: nu, mu, sigma       */
+  F_GEOM_1,                                /* Geometric.bl:10-16          reals: p                   */
+  F_LAPLACE_1,                             /* Laplace.bl:12-17            reals: location, scale     */
+  F_BETA_A, F_BETA_B,                      /* Beta.bl:14-27 prior on real i0, alpha = c0, beta = c1  */
+  F_UNIF_B                                 /* ContinuousUniform.bl:16-19 prior on real i0, [c0, c1]  */
 };
 
 typedef struct {
@@ -217,7 +237,7 @@ typedef struct {
   int32_t *fixed_idx, *ann_idx;   /* sampler2sparseUpdate{Fixed,Annealed}, SampledModel.java:67-69 */
 } Sampler;
 
-enum { FW_NORMAL = 0, FW_EXPONENTIAL, FW_GAMMA, FW_DIRICHLET_SYM, FW_BERNOULLI_INT };
+enum { FW_NORMAL = 0, FW_EXPONENTIAL, FW_GAMMA, FW_DIRICHLET_SYM, FW_BERNOULLI_INT, FW_BETA, FW_UNIFORM };
 typedef struct { int32_t kind, var, K; double a, b; } Forward;
 
 struct orc_model {
@@ -308,6 +328,92 @@ static double factor_eval(const orc_model* m, const Factor* f, const double* re,
       if (prob < 0.0 || prob > 1.0) return NEG_INF;
       return log(s == 1 ? prob : 1.0 - prob);
     }
+    case F_POIS_1: {
+      double mean = re[0], y = m->y[f->i0];
+      if (mean <= 0) return NEG_INF;
+      if (y < 0) return NEG_INF;
+      return y * log(mean);
+    }
+    case F_POIS_2: {
+      double mean = re[0];
+      if (mean <= 0) return NEG_INF;
+      return -mean;
+    }
+    case F_POIS_3: {
+      double y = m->y[f->i0];
+      if (y < 0) return NEG_INF;
+      return -orc_lngamma(y + 1);                      /* StaticUtils.logFactorial :156-158 */
+    }
+    case F_BINOM_1: {
+      double p = re[0], k = m->y[f->i0], n = m->x[f->i0];
+      if (p < 0.0 || p > 1.0) return NEG_INF;
+      if (k < 0) return NEG_INF;
+      if (n <= 0 || k > n) return NEG_INF;
+      return k * log(p) + (n - k) * log(1.0 - p);
+    }
+    case F_BINOM_2: {
+      double k = m->y[f->i0], n = m->x[f->i0];
+      if (k < 0) return NEG_INF;
+      if (n <= 0 || k > n) return NEG_INF;
+      return orc_lngamma(n + 1) - orc_lngamma(k + 1) - orc_lngamma(n - k + 1);   /* logBinomial :160-162 */
+    }
+    case F_NEGBIN_1: {
+      double r = re[0], k = m->y[f->i0];
+      if (r <= 0 || k < 0) return NEG_INF;
+      double nn = k + r - 1.0;
+      double result = orc_lngamma(nn + 1) - orc_lngamma(k + 1) - orc_lngamma(nn - k + 1);
+      if (result != result) return NEG_INF;
+      return result;
+    }
+    case F_NEGBIN_2: {
+      double r = re[0], p = re[1], k = m->y[f->i0];
+      if (p <= 0.0 || p >= 1.0) return NEG_INF;
+      if (r <= 0 || k < 0) return NEG_INF;
+      return k * log(p) + r * log(1.0 - p);
+    }
+    case F_STUD_2: {
+      double sigma = re[2];
+      if (sigma <= 0.0) return NEG_INF;
+      return -log(sigma);
+    }
+    case F_STUD_3: {
+      double nu = re[0];
+      if (nu <= 0.0) return NEG_INF;
+      return orc_lngamma((nu + 1.0) / 2.0) - 0.5 * log(nu) - orc_lngamma(nu / 2.0);
+    }
+    case F_STUD_4: {
+      double nu = re[0], mu = re[1], sigma = re[2], y = m->y[f->i0];
+      if (nu <= 0.0 || sigma <= 0.0) return NEG_INF;
+      return -((nu + 1.0) / 2.0) * log(1.0 + (1.0 / nu) * (1.0 / (pow(sigma, 2))) * pow((y - mu), 2));
+    }
+    case F_GEOM_1: {
+      double p = re[0], y = m->y[f->i0];
+      if (p <= 0 || p >= 1) return NEG_INF;
+      if (y < 0) return NEG_INF;
+      return y * log(1 - p) + log(p);
+    }
+    case F_LAPLACE_1: {
+      double loc = re[0], scale = re[1], y = m->y[f->i0];
+      if (scale <= 0) return NEG_INF;
+      return -log(2 * scale) - fabs(y - loc) / scale;
+    }
+    case F_BETA_A: {
+      double alpha = f->c0, x = re[f->i0];
+      if (x <= 0.0 || x >= 1.0) return NEG_INF;
+      if (alpha <= 0.0) return NEG_INF;
+      return (alpha - 1.0) * log(x);
+    }
+    case F_BETA_B: {
+      double beta = f->c1, x = re[f->i0];
+      if (x <= 0.0 || x >= 1.0) return NEG_INF;
+      if (beta <= 0.0) return NEG_INF;
+      return (beta - 1.0) * log1p(-x);
+    }
+    case F_UNIF_B: {
+      double x = re[f->i0];
+      if (f->c0 <= x && x <= f->c1) return 0.0;
+      return NEG_INF;
+    }
     case F_BETABINOM: {
       double alpha = re[f->i1], beta = re[f->i2];
       double x = (double)m->yi[f->i0], n = (double)m->ntrials[f->i0];
@@ -389,6 +495,83 @@ static void b_gamma_prior(Builder* b, int sampler, int var, double shape, double
   b_factor(b, F_CONST, 0, 0, 0, 0, shape <= 0.0 ? NEG_INF : -orc_lngamma(shape), 0);
   b_factor(b, F_CONST, 0, 0, 0, 0, rate <= 0.0 ? NEG_INF : log(rate), 0);
   b_forward(b->m, as_exponential ? FW_EXPONENTIAL : FW_GAMMA, var, 0, shape, rate);
+}
+
+/* `x ~ Beta(alpha, beta)` with constant parameters: five factors (Beta.bl:14-41) */
+static void b_beta_prior(Builder* b, int sampler, int var, double alpha, double beta) {
+  b_connect(b, sampler, b_factor(b, F_BETA_A, 0, var, 0, 0, alpha, beta));
+  b_connect(b, sampler, b_factor(b, F_BETA_B, 0, var, 0, 0, alpha, beta));
+  b_factor(b, F_CONST, 0, 0, 0, 0, (alpha <= 0.0 || beta <= 0.0) ? NEG_INF : orc_lngamma(alpha + beta), 0);
+  b_factor(b, F_CONST, 0, 0, 0, 0, alpha <= 0.0 ? NEG_INF : -orc_lngamma(alpha), 0);
+  b_factor(b, F_CONST, 0, 0, 0, 0, beta <= 0.0 ? NEG_INF : -orc_lngamma(beta), 0);
+  b_forward(b->m, FW_BETA, var, 0, alpha, beta);
+}
+/* `x ~ ContinuousUniform(min, max)`: two factors (ContinuousUniform.bl:12-19) */
+static void b_uniform_prior(Builder* b, int sampler, int var, double mn, double mx) {
+  b_factor(b, F_CONST, 0, 0, 0, 0, (mx - mn <= 0.0) ? NEG_INF : -log(mx - mn), 0);
+  b_connect(b, sampler, b_factor(b, F_UNIF_B, 0, var, 0, 0, mn, mx));
+  b_forward(b->m, FW_UNIFORM, var, 0, mn, mx);
+}
+
+/* family 6: y_i | theta ~ Dist(theta) i.i.d., all observed (annealed); theta_j ~ prior_j.  One real slice sampler
+ * per parameter, in declaration order.  Every law of the distribution is one factor PER OBSERVATION, also the
+ * laws that read only parameters (Poisson's -mean, Student's -log sigma ...): that is what instantiating
+ * `y.get(i) | theta ~ Dist(theta)` n times produces, and it is what nOutOfSupport counts. */
+orc_model* orc_model_iid(int dist, const double* y, const double* trials, int n, const int32_t* prior_kind,
+                         const double* prior_a, const double* prior_b) {
+  static const int n_params[] = {0, 1, 1, 2, 3, 1, 2};
+  if (dist < ORC_IID_POISSON || dist > ORC_IID_LAPLACE) return NULL;
+  const int P = n_params[dist];
+  Builder b = b_begin(ORC_FAM_IID, P, 0, P);
+  orc_model* m = b.m;
+  m->n_obs = n; m->K = dist;
+  m->y = (double*)malloc(sizeof(double) * (n > 0 ? n : 1)); memcpy(m->y, y, sizeof(double) * n);
+  m->x = (double*)calloc(n > 0 ? n : 1, sizeof(double));
+  if (trials) memcpy(m->x, trials, sizeof(double) * n);
+  for (int j = 0; j < P; j++) {
+    m->samplers[j].type = S_REAL_SLICE; m->samplers[j].var = j;
+    switch (prior_kind[j]) {
+      case ORC_PRIOR_NORMAL: b_normal_prior(&b, j, j, prior_a[j], prior_b[j]); break;
+      case ORC_PRIOR_GAMMA: b_gamma_prior(&b, j, j, prior_a[j], prior_b[j], 0); break;
+      case ORC_PRIOR_EXPONENTIAL: b_gamma_prior(&b, j, j, 1.0, prior_a[j], 1); break;
+      case ORC_PRIOR_BETA: b_beta_prior(&b, j, j, prior_a[j], prior_b[j]); break;
+      default: b_uniform_prior(&b, j, j, prior_a[j], prior_b[j]); break;
+    }
+  }
+  for (int i = 0; i < n; i++) {
+    int f1, f2;
+    switch (dist) {
+      case ORC_IID_POISSON:
+        b_connect(&b, 0, b_factor(&b, F_POIS_1, 1, i, 0, 0, 0, 0));
+        b_connect(&b, 0, b_factor(&b, F_POIS_2, 1, i, 0, 0, 0, 0));
+        b_factor(&b, F_POIS_3, 1, i, 0, 0, 0, 0);
+        break;
+      case ORC_IID_BINOMIAL:
+        b_connect(&b, 0, b_factor(&b, F_BINOM_1, 1, i, 0, 0, 0, 0));
+        b_factor(&b, F_BINOM_2, 1, i, 0, 0, 0, 0);
+        break;
+      case ORC_IID_NEGBINOMIAL:
+        b_connect(&b, 0, b_factor(&b, F_NEGBIN_1, 1, i, 0, 0, 0, 0));
+        f2 = b_factor(&b, F_NEGBIN_2, 1, i, 0, 0, 0, 0);
+        b_connect(&b, 0, f2); b_connect(&b, 1, f2);
+        break;
+      case ORC_IID_STUDENTT:
+        b_factor(&b, F_CONST, 1, 0, 0, 0, -0.5 * log(M_PI), 0);
+        b_connect(&b, 2, b_factor(&b, F_STUD_2, 1, i, 0, 0, 0, 0));
+        b_connect(&b, 0, b_factor(&b, F_STUD_3, 1, i, 0, 0, 0, 0));
+        f1 = b_factor(&b, F_STUD_4, 1, i, 0, 0, 0, 0);
+        b_connect(&b, 0, f1); b_connect(&b, 1, f1); b_connect(&b, 2, f1);
+        break;
+      case ORC_IID_GEOMETRIC:
+        b_connect(&b, 0, b_factor(&b, F_GEOM_1, 1, i, 0, 0, 0, 0));
+        break;
+      default:
+        f1 = b_factor(&b, F_LAPLACE_1, 1, i, 0, 0, 0, 0);
+        b_connect(&b, 0, f1); b_connect(&b, 1, f1);
+        break;
+    }
+  }
+  return b_end(&b);
 }
 
 orc_model* orc_model_normal(const double* y, int n, double m0, double v0, double rate) {
@@ -625,6 +808,8 @@ static void sm_forward_sample(SampledModel* s, Rng* r) {
       case FW_EXPONENTIAL: s->reals[f->var] = gen_exponential(r, f->b); break;
       case FW_GAMMA: s->reals[f->var] = gen_gamma(r, f->a, f->b); break;
       case FW_BERNOULLI_INT: s->ints[f->var] = rng_bernoulli(r, f->a) ? 1 : 0; break;
+      case FW_BETA: s->reals[f->var] = gen_beta(r, f->a, f->b); break;
+      case FW_UNIFORM: s->reals[f->var] = f->a + rng_double(r) * (f->b - f->a); break;   /* Generators.uniform :197-202 */
       case FW_DIRICHLET_SYM: {   /* Generators.dirichletInPlace :233-272 */
         double* out = s->reals + f->var; int K = f->K; double conc = f->a;
         if (conc < 1.0) {

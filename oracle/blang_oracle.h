@@ -38,8 +38,20 @@ enum {
   ORC_FAM_LOGISTIC = 2,     /* C2: w_j ~ Normal(0,v0), y_i ~ Bernoulli(logistic(x_i.w))           */
   ORC_FAM_MIXTURE = 3,      /* C3: marginalised K-component Gaussian mixture                       */
   ORC_FAM_ISING = 4,        /* C4: F/Ising.bl                                                      */
-  ORC_FAM_BETABINOMIAL = 5  /* C5: a,b ~ Exponential(rate), y_g ~ BetaBinomial(n_g,a,b)            */
+  ORC_FAM_BETABINOMIAL = 5, /* C5: a,b ~ Exponential(rate), y_g ~ BetaBinomial(n_g,a,b)            */
+  ORC_FAM_IID = 6           /* y_i ~ Dist(theta) i.i.d., theta_j ~ prior_j          */
 };
+/* observation laws of family 6 and their parameters (reals, in this order) */
+enum {
+  ORC_IID_POISSON = 1,      /* mean                  Poisson.bl          */
+  ORC_IID_BINOMIAL = 2,     /* p (trials are data)   Binomial.bl         */
+  ORC_IID_NEGBINOMIAL = 3,  /* r, p                  NegativeBinomial.bl */
+  ORC_IID_STUDENTT = 4,     /* nu, mu, sigma         StudentT.bl         */
+  ORC_IID_GEOMETRIC = 5,    /* p                     Geometric.bl        */
+  ORC_IID_LAPLACE = 6       /* location, scale       Laplace.bl          */
+};
+/* priors of family 6: (a, b) = (mean, variance) | (shape, rate) | (rate, -) | (alpha, beta) | (min, max) */
+enum { ORC_PRIOR_NORMAL = 0, ORC_PRIOR_GAMMA = 1, ORC_PRIOR_EXPONENTIAL = 2, ORC_PRIOR_BETA = 3, ORC_PRIOR_UNIFORM = 4 };
 
 enum { ORC_INIT_COPIES = 0, ORC_INIT_FORWARD = 1 };
 enum { ORC_ORDER_REFERENCE = 0, ORC_ORDER_CHECKERBOARD = 1 };
@@ -64,6 +76,9 @@ orc_model* orc_model_mixture(const double* y, int n, int K, double m0, double v0
                              double gshape, double grate, double conc);
 orc_model* orc_model_ising(int N, double coupling, double moment);
 orc_model* orc_model_betabinomial(const int32_t* y, const int32_t* ntrials, int n, double rate);
+/* family 6; trials may be NULL unless dist == ORC_IID_BINOMIAL; one (kind, a, b) per parameter */
+orc_model* orc_model_iid(int dist, const double* y, const double* trials, int n, const int32_t* prior_kind,
+                         const double* prior_a, const double* prior_b);
 void orc_model_free(orc_model*);
 int orc_model_n_reals(const orc_model*);
 int orc_model_n_ints(const orc_model*);

@@ -75,6 +75,8 @@ def lib():
     L.orc_model_ising.argtypes = [C.c_int, C.c_double, C.c_double]
     L.orc_model_betabinomial.restype = vp
     L.orc_model_betabinomial.argtypes = [_ip, _ip, C.c_int, C.c_double]
+    L.orc_model_iid.restype = vp
+    L.orc_model_iid.argtypes = [C.c_int, _dp, _dp, C.c_int, _ip, _dp, _dp]
     L.orc_model_free.argtypes = [vp]
     for f in ("orc_model_n_reals", "orc_model_n_ints", "orc_model_n_samplers", "orc_model_n_factors"):
         getattr(L, f).argtypes = [vp]
@@ -157,8 +159,12 @@ def adapt_ladder(betas_asc, accept_asc):
     return out, cum
 
 
+IID_DISTS = dict(poisson=1, binomial=2, negbinomial=3, studentt=4, geometric=5, laplace=6)
+IID_PRIORS = dict(normal=0, gamma=1, exponential=2, beta=3, uniform=4)
+
+
 class Model:
-    """One of the five catalogue families, built from a blangsdk_b200.datasets spec dict."""
+    """One of the catalogue families, built from a blangsdk_b200.datasets spec dict."""
 
     def __init__(self, spec):
         L = lib()
@@ -181,6 +187,15 @@ class Model:
             y = np.ascontiguousarray(spec["y"], dtype=np.int32)
             nt = np.ascontiguousarray(spec["ntrials"], dtype=np.int32)
             self.h = L.orc_model_betabinomial(_i(y), _i(nt), len(y), h["rate"])
+        elif fam == "iid":
+            y = np.ascontiguousarray(spec["y"], dtype=np.float64)
+            tr = np.ascontiguousarray(spec["trials"], dtype=np.float64) if spec.get("trials") is not None else None
+            kinds = np.array([IID_PRIORS[p[0]] for p in h["priors"]], dtype=np.int32)
+            pa = np.array([float(p[1]) for p in h["priors"]], dtype=np.float64)
+            pb = np.array([float(p[2]) if len(p) > 2 else 0.0 for p in h["priors"]], dtype=np.float64)
+            self.h = L.orc_model_iid(IID_DISTS[h["dist"]], _d(y), _d(tr), len(y), _i(kinds), _d(pa), _d(pb))
+            if not self.h:
+                raise ValueError("iid: unknown distribution")
         else:
             raise ValueError(fam)
         self.n_reals = L.orc_model_n_reals(self.h)

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _case(D, rng):
-    fam = ["normal", "logistic", "mixture", "betabinomial", "ising"][rng.integers(0, 5)]
+    fam = ["normal", "logistic", "mixture", "betabinomial", "ising", "iid"][rng.integers(0, 6)]
     if fam == "normal":
         spec = D.normal_meanvar(n=int(rng.integers(1, 3000)), seed=int(rng.integers(1, 1 << 30)))
     elif fam == "logistic":
@@ -20,6 +20,9 @@ def _case(D, rng):
         spec = D.gaussian_mixture(int(rng.integers(1, 4000)), seed=int(rng.integers(1, 1 << 30)))
     elif fam == "betabinomial":
         spec = D.beta_binomial(int(rng.integers(0, 1000)), groups=int(rng.integers(1, 70)), trials=int(rng.integers(1, 80)))
+    elif fam == "iid":
+        dist = ["poisson", "binomial", "negbinomial", "studentt", "geometric", "laplace"][rng.integers(0, 6)]
+        spec = D.iid_observations(dist, int(rng.integers(1, 3000)), seed=int(rng.integers(1, 1 << 30)))
     else:
         # the checkerboard sweep needs an even lattice side
         spec = D.ising(2 * int(rng.integers(1, 7)), moment=float(rng.choice([0.0, 0.1, -0.3])))
@@ -29,7 +32,7 @@ def _case(D, rng):
     return fam, spec, int(rng.integers(1, 14)), int(rng.integers(1, 1 << 20)), ctas, opts
 
 
-@pytest.mark.parametrize("case", range(40))
+@pytest.mark.parametrize("case", range(60))
 def test_random_configuration(oracle, datasets, case):
     rng = np.random.default_rng(9000 + case)
     fam, spec, n_chains, seed, ctas, opts = _case(datasets, rng)

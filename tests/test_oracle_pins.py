@@ -77,6 +77,48 @@ def test_density_normalisation(oracle, datasets):
     assert abs(sum(p) - 1.0) < 1e-12
 
 
+def _iid_loglik(oracle, dist, y, theta, trials=None):
+    priors = {"poisson": [("exponential", 0.1)], "binomial": [("beta", 2.0, 3.0)],
+              "negbinomial": [("gamma", 2.0, 0.5), ("uniform", 0.0, 1.0)],
+              "studentt": [("exponential", 0.1), ("normal", 0.0, 100.0), ("exponential", 0.5)],
+              "geometric": [("uniform", 0.0, 1.0)], "laplace": [("normal", 0.0, 25.0), ("gamma", 2.0, 1.0)]}[dist]
+    spec = dict(family="iid", hyper=dict(dist=dist, priors=priors), y=np.array([float(y)]),
+                trials=None if trials is None else np.array([float(trials)]))
+    return oracle.Model(spec).log_density(theta)
+
+
+def test_iid_laws_normalise(oracle):
+    """T/TestSDKNormalizations.java:20-45 for the laws of family 6: every pmf sums, every pdf integrates, to
+    1 +- 1e-6 (the reference's own tolerance), priors included."""
+    tot = sum(math.exp(_iid_loglik(oracle, "poisson", y, [3.7])["loglik"]) for y in range(0, 80))
+    assert abs(tot - 1.0) < 1e-9
+    tot = sum(math.exp(_iid_loglik(oracle, "binomial", y, [0.37], trials=17)["loglik"]) for y in range(0, 18))
+    assert abs(tot - 1.0) < 1e-9
+    tot = sum(math.exp(_iid_loglik(oracle, "negbinomial", y, [2.6, 0.45])["loglik"]) for y in range(0, 400))
+    assert abs(tot - 1.0) < 1e-9
+    tot = sum(math.exp(_iid_loglik(oracle, "geometric", y, [0.2])["loglik"]) for y in range(0, 400))
+    assert abs(tot - 1.0) < 1e-9
+    lap = lambda ys: np.array([math.exp(_iid_loglik(oracle, "laplace", y, [-0.5, 1.3])["loglik"]) for y in ys])
+    assert abs(_simpson(lap, -0.5 - 60, -0.5, 3000) + _simpson(lap, -0.5, -0.5 + 60, 3000) - 1.0) < 1e-6
+    # Student t: heavy tails, integrate on a finite window and add the exact tail mass of t_5 beyond 400 scale units
+    stu = lambda ys: np.array([math.exp(_iid_loglik(oracle, "studentt", y, [5.0, 1.0, 2.0])["loglik"]) for y in ys])
+    assert abs(_simpson(stu, 1.0 - 800.0, 1.0 + 800.0, 40000) - 1.0) < 1e-6
+    # out-of-support parameters: every law that reads them is -inf, one count per observation and law
+    assert _iid_loglik(oracle, "poisson", 3, [-1.0])["noos"] == 2
+    assert _iid_loglik(oracle, "studentt", 0.3, [-1.0, 0.0, 1.0])["noos"] == 2      # nu: its own law and the joint one
+    assert _iid_loglik(oracle, "studentt", 0.3, [3.0, 0.0, -1.0])["noos"] == 2      # sigma
+    assert _iid_loglik(oracle, "negbinomial", 2, [1.5, 1.5])["noos"] == 1
+    assert _iid_loglik(oracle, "binomial", 9, [0.5], trials=4)["noos"] == 2         # k > n: both laws
+    # priors: Beta(2,3) and Uniform(0,1) integrate to one, Gamma(2, 0.5) too
+    base = _iid_loglik(oracle, "binomial", 3, [0.4], trials=10)
+    beta_pdf = lambda xs: np.array([math.exp(_iid_loglik(oracle, "binomial", 3, [x], trials=10)["fixed"]) for x in xs])
+    assert abs(_simpson(beta_pdf, 1e-9, 1 - 1e-9, 2000) - 1.0) < 1e-6
+    assert abs(math.exp(base["fixed"]) - 12.0 * 0.4 * 0.6 ** 2) < 1e-12              # Beta(2,3) pdf = 12 x (1-x)^2
+    joint = lambda xs: np.array([math.exp(_iid_loglik(oracle, "negbinomial", 1, [x, 0.3])["fixed"]) for x in xs])
+    assert abs(_simpson(joint, 1e-12, 120.0, 12000) - 1.0) < 1e-6                    # Gamma(2,0.5) x Uniform(0,1) at p = 0.3
+    assert _iid_loglik(oracle, "negbinomial", 1, [1.0, 1.2])["fixed"] == -math.inf
+
+
 def test_lngamma_choice(oracle):
     """libm lgamma (the documented choice) vs the Pike & Hill series bayonet is believed to use:
     the discrepancy class is < 3e-10 absolute, inside the 1e-9 relative bar for C5."""
