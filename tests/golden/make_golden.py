@@ -18,8 +18,8 @@ from oracle import oracle as O  # noqa: E402
 
 def spec_to_json(spec):
     out = {"family": spec["family"], "hyper": spec["hyper"]}
-    for k in ("y", "x", "ntrials"):
-        if k in spec:
+    for k in ("y", "x", "ntrials", "trials"):
+        if spec.get(k) is not None:
             out[k] = np.asarray(spec[k]).tolist()
     return out
 
@@ -32,6 +32,13 @@ def main():
         "betabinomial": D.beta_binomial(1, groups=8),
         "ising": D.ising(4),
     }
+    # family 6 (appended after the first five so that their random states, and so their vectors, are unchanged)
+    iid_state = {"poisson": lambda r: [r.gamma(2.0, 2.0)], "binomial": lambda r: [r.uniform(0.05, 0.95)],
+                 "negbinomial": lambda r: [r.gamma(2.0, 1.5), r.uniform(0.05, 0.95)],
+                 "studentt": lambda r: [r.gamma(2.0, 2.0), r.normal(1.0, 2.0), r.gamma(2.0, 1.0)],
+                 "geometric": lambda r: [r.uniform(0.05, 0.95)], "laplace": lambda r: [r.normal(0.0, 2.0), r.gamma(2.0, 1.0)]}
+    for dist in iid_state:
+        specs["iid_" + dist] = D.iid_observations(dist, 45)
     rng = np.random.default_rng(20240600)
     cases = []
     for name, spec in specs.items():
@@ -46,6 +53,8 @@ def main():
                 it = None
             elif name == "logistic":
                 re, it = rng.normal(0, 1.5, m.n_reals).tolist(), None
+            elif name.startswith("iid_"):
+                re, it = [float(v) for v in iid_state[name[4:]](rng)], None
             else:
                 re, it = rng.gamma(2.0, 1.0, m.n_reals).tolist(), None
             d = m.log_density(re, it, beta=beta)

@@ -17,9 +17,12 @@ def _cases():
 
 def _spec(c):
     s = dict(c["spec"])
-    for k in ("y", "x", "ntrials"):
+    for k in ("y", "x", "ntrials", "trials"):
         if k in s:
             s[k] = np.array(s[k])
+    if s["family"] == "iid":
+        s["hyper"] = dict(s["hyper"], priors=[tuple(p) for p in s["hyper"]["priors"]])
+        s.setdefault("trials", None)
     return s
 
 
