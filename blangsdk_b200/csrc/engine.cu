@@ -361,10 +361,9 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
       h->n_reals = 2; h->n_samplers = 2; rows = n;
     } break;
     case BLANGPT_FAM_IID: {
-      static const int n_params_of[] = {0, 1, 1, 2, 3, 1, 2};
       const int dist = nh >= 1 ? (int)hyper[0] : 0;
-      if (dist < IID_POISSON || dist > IID_LAPLACE) FAIL(h, BLANGPT_EUNSUPPORTED, "iid: unknown distribution code %d", dist);
-      const int P = n_params_of[dist];
+      if (dist < IID_POISSON || dist >= IID_N_DISTS) FAIL(h, BLANGPT_EUNSUPPORTED, "iid: unknown distribution code %d", dist);
+      const int P = iid_shape(dist).n_params;
       if (nh != 1 + 3 * P) FAIL(h, BLANGPT_EINVAL, "iid: hyper must be (dist, then kind, a, b for each of the %d parameters)", P);
       const int want_arrays = dist == IID_BINOMIAL ? 2 : 1;
       if (na != want_arrays || a[0].dtype != BLANGPT_F64 || (na == 2 && (a[1].dtype != BLANGPT_F64 || a[1].n_elem != a[0].n_elem)))

@@ -501,8 +501,137 @@ struct NormalFam {
 // more of R/distributions/*.bl).  Every law of the distribution is one factor PER OBSERVATION, also the laws that
 // read only parameters (Poisson's -mean, Student's -log sigma ...): n of them, and n out-of-support counts.
 // ===========================================================================
-enum { IID_POISSON = 1, IID_BINOMIAL = 2, IID_NEGBINOMIAL = 3, IID_STUDENTT = 4, IID_GEOMETRIC = 5, IID_LAPLACE = 6 };
+enum {
+  IID_POISSON = 1, IID_BINOMIAL, IID_NEGBINOMIAL, IID_STUDENTT, IID_GEOMETRIC, IID_LAPLACE, IID_EXPONENTIAL, IID_GAMMA,
+  IID_WEIBULL, IID_GUMBEL, IID_LOGISTICDIST, IID_HALFSTUDENTT, IID_LOGLOGISTIC, IID_GOMPERTZ, IID_YULESIMON,
+  IID_N_DISTS
+};
 enum { PRIOR_NORMAL = 0, PRIOR_GAMMA = 1, PRIOR_EXPONENTIAL = 2, PRIOR_BETA = 3, PRIOR_UNIFORM = 4 };
+
+// Per distribution: number of parameters, number of laws (`logf` blocks, file order), and per law which
+// parameters its signature names (bit j = parameter j) and whether it names the realization.
+struct IidShape { int n_params, n_laws; unsigned char mask[4], reads_y[4]; };
+BPT_HD IidShape iid_shape(int dist) {
+  switch (dist) {
+    case IID_POISSON:      return {1, 3, {1, 1, 0, 0}, {1, 0, 1, 0}};   // mean
+    case IID_BINOMIAL:     return {1, 2, {1, 0, 0, 0}, {1, 1, 0, 0}};   // p (trials are data)
+    case IID_NEGBINOMIAL:  return {2, 2, {1, 3, 0, 0}, {1, 1, 0, 0}};   // r, p
+    case IID_STUDENTT:     return {3, 4, {0, 4, 1, 7}, {0, 0, 0, 1}};   // nu, mu, sigma
+    case IID_GEOMETRIC:    return {1, 1, {1, 0, 0, 0}, {1, 0, 0, 0}};   // p
+    case IID_LAPLACE:      return {2, 1, {3, 0, 0, 0}, {1, 0, 0, 0}};   // location, scale
+    case IID_EXPONENTIAL:  return {1, 4, {1, 1, 0, 1}, {1, 1, 0, 0}};   // rate (-> Gamma(1.0, rate))
+    case IID_GAMMA:        return {2, 4, {3, 2, 1, 2}, {1, 1, 0, 0}};   // shape, rate
+    case IID_WEIBULL:      return {2, 3, {3, 3, 3, 0}, {0, 1, 1, 0}};   // scale, shape
+    case IID_GUMBEL:       return {2, 2, {3, 3, 0, 0}, {0, 1, 0, 0}};   // location, scale
+    case IID_LOGISTICDIST: return {2, 3, {2, 3, 3, 0}, {0, 1, 1, 0}};   // location, scale
+    case IID_HALFSTUDENTT: return {2, 3, {1, 2, 3, 0}, {0, 0, 1, 0}};   // nu, sigma
+    case IID_LOGLOGISTIC:  return {2, 3, {3, 3, 3, 0}, {0, 1, 1, 0}};   // scale, shape
+    case IID_GOMPERTZ:     return {2, 2, {3, 3, 0, 0}, {0, 1, 0, 0}};   // shape, scale
+    case IID_YULESIMON:    return {1, 1, {1, 0, 0, 0}, {1, 0, 0, 0}};   // rho
+  }
+  return {0, 0, {0, 0, 0, 0}, {0, 0, 0, 0}};
+}
+BPT_D double iid_gamma_law(int law, double shape, double rate, double y) {   // Gamma.bl:14-31
+  switch (law) {
+    case 0: return (shape <= 0.0 || rate <= 0.0 || y <= 0.0) ? BPT_NEG_INF : (shape - 1.0) * log(y * rate);
+    case 1: return (rate <= 0.0 || y <= 0.0) ? BPT_NEG_INF : -y * rate;
+    case 2: return shape <= 0.0 ? BPT_NEG_INF : -lgamma(shape);
+    default: return rate <= 0.0 ? BPT_NEG_INF : log(rate);
+  }
+}
+// one `logf` block of R/distributions/<Name>.bl; th = parameters, y = realization, x = trials (Binomial)
+BPT_D double iid_law(int dist, int law, const double* th, double y, double x) {
+  const double ninf = BPT_NEG_INF;
+  switch (dist) {
+    case IID_POISSON: {                                   // Poisson.bl:11-26
+      const double mean = th[0];
+      if (law == 0) return (mean <= 0.0 || y < 0.0) ? ninf : y * log(mean);
+      if (law == 1) return mean <= 0.0 ? ninf : -mean;
+      return y < 0.0 ? ninf : -lgamma(y + 1.0);
+    }
+    case IID_BINOMIAL: {                                  // Binomial.bl:14-27
+      const double p = th[0];
+      if (y < 0.0 || x <= 0.0 || y > x) return ninf;
+      if (law == 0) return (p < 0.0 || p > 1.0) ? ninf : y * log(p) + (x - y) * log(1.0 - p);
+      return lgamma(x + 1.0) - lgamma(y + 1.0) - lgamma(x - y + 1.0);
+    }
+    case IID_NEGBINOMIAL: {                               // NegativeBinomial.bl:14-28
+      const double r = th[0], p = th[1];
+      if (r <= 0.0 || y < 0.0) return ninf;
+      if (law == 0) {
+        const double nn = y + r - 1.0;
+        const double t = lgamma(nn + 1.0) - lgamma(y + 1.0) - lgamma(nn - y + 1.0);
+        return t != t ? ninf : t;
+      }
+      return (p <= 0.0 || p >= 1.0) ? ninf : y * log(p) + r * log(1.0 - p);
+    }
+    case IID_STUDENTT: {                                  // StudentT.bl:13-33
+      const double nu = th[0], mu = th[1], sigma = th[2];
+      if (law == 0) return -0.5 * log(3.14159265358979323846);
+      if (law == 1) return sigma <= 0.0 ? ninf : -log(sigma);
+      if (law == 2) return nu <= 0.0 ? ninf : lgamma((nu + 1.0) / 2.0) - 0.5 * log(nu) - lgamma(nu / 2.0);
+      if (nu <= 0.0 || sigma <= 0.0) return ninf;
+      const double dy = y - mu;
+      return -((nu + 1.0) / 2.0) * log(1.0 + (1.0 / nu) * (1.0 / (sigma * sigma)) * (dy * dy));
+    }
+    case IID_GEOMETRIC: {                                 // Geometric.bl:10-16
+      const double p = th[0];
+      return (p <= 0.0 || p >= 1.0 || y < 0.0) ? ninf : y * log(1.0 - p) + log(p);
+    }
+    case IID_LAPLACE: {                                   // Laplace.bl:12-17
+      const double loc = th[0], scale = th[1];
+      return scale <= 0.0 ? ninf : -log(2.0 * scale) - fabs(y - loc) / scale;
+    }
+    case IID_EXPONENTIAL: return iid_gamma_law(law, 1.0, th[0], y);   // Exponential.bl:11
+    case IID_GAMMA: return iid_gamma_law(law, th[0], th[1], y);
+    case IID_WEIBULL: {                                   // Weibull.bl:14-33
+      const double scale = th[0], shape = th[1];
+      if (scale <= 0.0 || shape <= 0.0) return ninf;
+      if (law == 0) return log(shape) - (shape * log(scale));
+      if (y <= 0.0) return ninf;
+      return law == 1 ? (shape - 1.0) * log(y) : -pow(y / scale, shape);
+    }
+    case IID_GUMBEL: {                                    // Gumbel.bl:13-22
+      const double loc = th[0], scale = th[1];
+      if (scale <= 0.0) return ninf;
+      if (law == 0) return -log(scale);
+      const double z = (loc - y) / scale;
+      return -exp(z) + z;
+    }
+    case IID_LOGISTICDIST: {                              // Logistic.bl:13-26
+      const double loc = th[0], scale = th[1];
+      if (scale <= 0.0) return ninf;
+      if (law == 0) return -log(scale);
+      const double z = (loc - y) / scale;
+      return law == 1 ? z : -2.0 * log(1.0 + exp(z));
+    }
+    case IID_HALFSTUDENTT: {                              // HalfStudentT.bl:12-28
+      const double nu = th[0], sigma = th[1];
+      if (law == 0) return nu <= 0.0 ? ninf : log(2.0) + lgamma((nu + 1.0) / 2.0) - lgamma(nu / 2.0) - 0.5 * log(nu * 3.14159265358979323846);
+      if (law == 1) return sigma <= 0.0 ? ninf : -log(sigma);
+      if (y < 0.0 || sigma <= 0.0 || nu <= 0.0) return ninf;
+      const double q = y / sigma;
+      return -((nu + 1.0) / 2.0) * log(1.0 + 1.0 / nu * (q * q));
+    }
+    case IID_LOGLOGISTIC: {                               // LogLogistic.bl:14-33
+      const double scale = th[0], shape = th[1];
+      if (law == 0) return (scale <= 0.0 || shape <= 0.0) ? ninf : log(shape) - (shape * log(scale));
+      if (y < 0.0 || scale <= 0.0 || shape <= 0.0) return ninf;
+      return law == 1 ? shape * log(y) - log(y) : -2.0 * log(1.0 + pow(y / scale, shape));
+    }
+    case IID_GOMPERTZ: {                                  // Gompertz.bl:13-25
+      const double shape = th[0], scale = th[1];
+      if (law == 0) return (shape <= 0.0 || scale <= 0.0) ? ninf : log(shape / scale);
+      if (y < 0.0 || scale <= 0.0 || shape <= 0.0) return ninf;
+      return (y / scale) - (shape * (exp(y / scale) - 1.0));
+    }
+    default: {                                            // YuleSimon.bl:10-16
+      const double rho = th[0];
+      if (rho <= 0.0 || y < 0.0) return ninf;
+      return log(rho) + (lgamma(1.0 + y) + lgamma(rho + 1.0) - lgamma(1.0 + y + (rho + 1.0)));
+    }
+  }
+}
 
 struct IidFam {
   struct Data {
@@ -551,90 +680,22 @@ struct IidFam {
     }
   }
   // Sum and out-of-support count of the annealed factors connected to parameter k (k < 0: of all of them),
-  // at parameters th.  Parameter-only laws are evaluated once and counted n times.
+  // at parameters th.  Laws that do not read the realization are evaluated once and counted n times.
   BPT_D void factors(int k, const double* th, GroupReducer& red, double& s, int& c) const {
     const int n = d.n;
+    const IidShape sh = iid_shape(d.dist);
     double acc = 0.0, par = 0.0; int cnt = 0, pc = 0;
-    const bool all = k < 0;
-    switch (d.dist) {
-      case IID_POISSON: {                                     // Poisson.bl:11-26
-        const double mean = th[0];
-        const bool bad = mean <= 0.0;
-        const double L = bad ? 0.0 : log(mean);
-        if (bad) pc += 2 * n; else par += n * (-mean);
-        for (int i = rr.lo + t0; i < rr.hi; i += tn) {
-          const double y = d.y[i];
-          if (!bad) { if (y < 0.0) cnt++; else acc += y * L; }
-          if (all) { if (y < 0.0) cnt++; else acc += -lgamma(y + 1.0); }
-        }
-      } break;
-      case IID_BINOMIAL: {                                    // Binomial.bl:14-27
-        const double p = th[0];
-        const bool bad = p < 0.0 || p > 1.0;
-        const double lp = log(p), lq = log(1.0 - p);
-        if (bad) pc += n;
-        for (int i = rr.lo + t0; i < rr.hi; i += tn) {
-          const double y = d.y[i], m = d.trials[i];
-          const bool bad_row = y < 0.0 || m <= 0.0 || y > m;
-          if (!bad) { if (bad_row) cnt++; else acc_term(y * lp + (m - y) * lq, acc, cnt, err); }   // p = 0 or 1: -inf / NaN as in Java
-          if (all) { if (bad_row) cnt++; else acc += lgamma(m + 1.0) - lgamma(y + 1.0) - lgamma(m - y + 1.0); }
-        }
-      } break;
-      case IID_NEGBINOMIAL: {                                 // NegativeBinomial.bl:14-28
-        const double r = th[0], p = th[1];
-        const bool bad_r = r <= 0.0, bad_p = p <= 0.0 || p >= 1.0;
-        const double lp = log(p), lq = log(1.0 - p);
-        const bool f1 = all || k == 0;                        // logBinomial(k + r - 1, k): reads r
-        if (f1 && bad_r) pc += n;
-        if (bad_p || bad_r) pc += n;
-        for (int i = rr.lo + t0; i < rr.hi; i += tn) {
-          const double y = d.y[i];
-          if (f1 && !bad_r) {
-            if (y < 0.0) cnt++;
-            else {
-              const double nn = y + r - 1.0;
-              const double t = lgamma(nn + 1.0) - lgamma(y + 1.0) - lgamma(nn - y + 1.0);
-              if (t != t) cnt++; else acc_term(t, acc, cnt, err);
-            }
-          }
-          if (!(bad_p || bad_r)) { if (y < 0.0) cnt++; else acc_term(y * lp + r * lq, acc, cnt, err); }
-        }
-      } break;
-      case IID_STUDENTT: {                                    // StudentT.bl:13-33
-        const double nu = th[0], mu = th[1], sigma = th[2];
-        const bool bad = nu <= 0.0 || sigma <= 0.0;
-        if (all) par += n * (-0.5 * log(3.14159265358979323846));
-        if (all || k == 2) { if (sigma <= 0.0) pc += n; else par += n * (-log(sigma)); }
-        if (all || k == 0) { if (nu <= 0.0) pc += n; else par += n * (lgamma((nu + 1.0) / 2.0) - 0.5 * log(nu) - lgamma(nu / 2.0)); }
-        if (bad) pc += n;
-        else {
-          const double h = -((nu + 1.0) / 2.0), w = (1.0 / nu) * (1.0 / (sigma * sigma));
-          for (int i = rr.lo + t0; i < rr.hi; i += tn) {
-            const double dy = d.y[i] - mu;
-            acc_term(h * log(1.0 + w * (dy * dy)), acc, cnt, err);
-          }
-        }
-      } break;
-      case IID_GEOMETRIC: {                                   // Geometric.bl:10-16
-        const double p = th[0];
-        const bool bad = p <= 0.0 || p >= 1.0;
-        if (bad) pc += n;
-        else {
-          const double lq = log(1.0 - p), lp = log(p);
-          for (int i = rr.lo + t0; i < rr.hi; i += tn) {
-            const double y = d.y[i];
-            if (y < 0.0) cnt++; else acc += y * lq + lp;
-          }
-        }
-      } break;
-      default: {                                              // Laplace.bl:12-17
-        const double loc = th[0], scale = th[1];
-        if (scale <= 0.0) pc += n;
-        else {
-          const double l2 = -log(2.0 * scale);
-          for (int i = rr.lo + t0; i < rr.hi; i += tn) acc_term(l2 - fabs(d.y[i] - loc) / scale, acc, cnt, err);
-        }
-      } break;
+    for (int l = 0; l < sh.n_laws; l++) {
+      if (k >= 0 && !((sh.mask[l] >> k) & 1)) continue;
+      if (!sh.reads_y[l]) {
+        const double v = iid_law(d.dist, l, th, 0.0, 0.0);
+        if (v > BPT_NEG_INF) par += n * v;
+        else if (v != v) atomicOr(err, ERR_NAN);
+        else pc += n;
+      } else {
+        for (int i = rr.lo + t0; i < rr.hi; i += tn)
+          acc_term(iid_law(d.dist, l, th, d.y[i], d.trials ? d.trials[i] : 0.0), acc, cnt, err);
+      }
     }
     red.reduce(acc, cnt);
     s = acc + par; c = cnt + pc;

@@ -70,7 +70,9 @@ SEED_IID = 20240006
 def iid_observations(dist="poisson", n=2000, seed=SEED_IID):
     """Family "iid" (SURVEY 8(f)-4): y_i ~ Dist(theta) i.i.d. with one prior per parameter.  Parameters in the
     reference's declaration order: poisson (mean), binomial (p; trials are data), negbinomial (r, p),
-    studentt (nu, mu, sigma), geometric (p), laplace (location, scale)."""
+    studentt (nu, mu, sigma), geometric (p), laplace (location, scale), exponential (rate), gamma (shape, rate),
+    weibull (scale, shape), gumbel (location, scale), logisticdist (location, scale), halfstudentt (nu, sigma),
+    loglogistic (scale, shape), gompertz (shape, scale), yulesimon (rho)."""
     rng = np.random.default_rng(seed + sum(map(ord, dist)))
     spec = dict(family="iid", trials=None)
     if dist == "poisson":
@@ -93,7 +95,42 @@ def iid_observations(dist="poisson", n=2000, seed=SEED_IID):
     elif dist == "laplace":
         spec["y"] = rng.laplace(-0.5, 1.5, n)
         priors = [("normal", 0.0, 25.0), ("gamma", 2.0, 1.0)]
+    elif dist == "exponential":
+        spec["y"] = rng.exponential(1.0 / 1.7, n)
+        priors = [("gamma", 2.0, 1.0)]
+    elif dist == "gamma":
+        spec["y"] = rng.gamma(2.5, 1.0 / 1.2, n)
+        priors = [("exponential", 0.5), ("exponential", 0.5)]
+    elif dist == "weibull":
+        spec["y"] = 2.0 * rng.weibull(1.5, n)
+        priors = [("exponential", 0.3), ("exponential", 0.3)]
+    elif dist == "gumbel":
+        spec["y"] = rng.gumbel(0.5, 1.2, n)
+        priors = [("normal", 0.0, 25.0), ("exponential", 0.5)]
+    elif dist == "logisticdist":
+        spec["y"] = rng.logistic(1.0, 0.8, n)
+        priors = [("normal", 0.0, 25.0), ("exponential", 0.5)]
+    elif dist == "halfstudentt":
+        spec["y"] = np.abs(1.5 * rng.standard_t(4.0, n))
+        priors = [("exponential", 0.1), ("exponential", 0.5)]
+    elif dist == "loglogistic":
+        u = rng.uniform(1e-6, 1 - 1e-6, n)
+        spec["y"] = 2.0 * (u / (1.0 - u)) ** (1.0 / 3.0)
+        priors = [("exponential", 0.3), ("exponential", 0.3)]
+    elif dist == "gompertz":
+        u = rng.uniform(0.0, 1 - 1e-9, n)
+        spec["y"] = 1.5 * np.log(1.0 - np.log(1.0 - u) / 0.8)
+        priors = [("exponential", 0.5), ("exponential", 0.5)]
+    elif dist == "yulesimon":
+        w = rng.exponential(1.0 / 2.5, n)
+        spec["y"] = (rng.geometric(np.exp(-w)) - 1).astype(np.float64)
+        priors = [("exponential", 0.3)]
     else:
         raise ValueError(dist)
     spec["hyper"] = dict(dist=dist, priors=priors)
+    # the generating parameters, in declaration order (a well-conditioned place to start chains from)
+    spec["truth"] = dict(poisson=[4.2], binomial=[0.3], negbinomial=[3.0, 0.6], studentt=[4.0, 1.0, 2.0], geometric=[0.25],
+                         laplace=[-0.5, 1.5], exponential=[1.7], gamma=[2.5, 1.2], weibull=[2.0, 1.5], gumbel=[0.5, 1.2],
+                         logisticdist=[1.0, 0.8], halfstudentt=[4.0, 1.5], loglogistic=[2.0, 3.0], gompertz=[0.8, 1.5],
+                         yulesimon=[2.5])[dist]
     return spec

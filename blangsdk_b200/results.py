@@ -34,6 +34,9 @@ VARIABLES = {
 IID_VARIABLES = {
     "poisson": ["mean"], "binomial": ["probabilityOfSuccess"], "negbinomial": ["r", "p"],
     "studentt": ["nu", "mu", "sigma"], "geometric": ["p"], "laplace": ["location", "scale"],
+    "exponential": ["rate"], "gamma": ["shape", "rate"], "weibull": ["scale", "shape"], "gumbel": ["location", "scale"],
+    "logisticdist": ["location", "scale"], "halfstudentt": ["nu", "sigma"], "loglogistic": ["scale", "shape"],
+    "gompertz": ["shape", "scale"], "yulesimon": ["rho"],
 }
 
 

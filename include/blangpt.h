@@ -57,7 +57,16 @@ enum {
   BLANGPT_IID_NEGBINOMIAL = 3,  /* r, p                 */
   BLANGPT_IID_STUDENTT = 4,     /* nu, mu, sigma        */
   BLANGPT_IID_GEOMETRIC = 5,    /* p                    */
-  BLANGPT_IID_LAPLACE = 6       /* location, scale      */
+  BLANGPT_IID_LAPLACE = 6,      /* location, scale      */
+  BLANGPT_IID_EXPONENTIAL = 7,  /* rate                 */
+  BLANGPT_IID_GAMMA = 8,        /* shape, rate          */
+  BLANGPT_IID_WEIBULL = 9,      /* scale, shape         */
+  BLANGPT_IID_GUMBEL = 10,      /* location, scale      */
+  BLANGPT_IID_LOGISTIC = 11,    /* location, scale      (Logistic.bl, the distribution) */
+  BLANGPT_IID_HALFSTUDENTT = 12,/* nu, sigma            */
+  BLANGPT_IID_LOGLOGISTIC = 13, /* scale, shape         */
+  BLANGPT_IID_GOMPERTZ = 14,    /* shape, scale         */
+  BLANGPT_IID_YULESIMON = 15    /* rho                  */
 };
 /* family 6: priors; (a, b) = (mean, variance) | (shape, rate) | (rate, unused) | (alpha, beta) | (min, max) */
 enum {

@@ -210,13 +210,7 @@ enum {
   F_ISING_EDGE,       /* F/Ising.bl:15-24  spins i0,i1, coupling c0                      */
   F_BERN_NODE,        /* F/Ising.bl:27-29 -> Bernoulli.bl -> Categorical.bl; spin i0, p=c0 */
   F_BETABINOM,        /* BetaBinomial.bl:17-30 group i0, alpha = real i1, beta = real i2 */
-  /* family 6 (iid observations y[i0], optional trials x[i0], parameters = reals 0..2 in the order below) */
-  F_POIS_1, F_POIS_2, F_POIS_3,            /* Poisson.bl:11-26            reals: mean                */
-  F_BINOM_1, F_BINOM_2,                    /* Binomial.bl:14-27           reals: p; trials in x[]    */
-  F_NEGBIN_1, F_NEGBIN_2,                  /* NegativeBinomial.bl:14-28   reals: r, p                */
-  F_STUD_2, F_STUD_3, F_STUD_4,            /* StudentT.bl:13-33           reals: nu, mu, sigma       */
-  F_GEOM_1,                                /* Geometric.bl:10-16          reals: p                   */
-  F_LAPLACE_1,                             /* Laplace.bl:12-17            reals: location, scale     */
+  F_IID_LAW,          /* family 6: law i1 of the observation distribution, observation i0 (iid_law below) */
   F_BETA_A, F_BETA_B,                      /* Beta.bl:14-27 prior on real i0, alpha = c0, beta = c1  */
   F_UNIF_B                                 /* ContinuousUniform.bl:16-19 prior on real i0, [c0, c1]  */
 };
@@ -255,6 +249,141 @@ struct orc_model {
 
 /* --- factor bodies ---------------------------------------------------- */
 #define LOG_2PI 1.8378770664093454835606594728112
+
+/* ---- family 6: the laws of R/distributions/<Name>.bl, one C case per `logf` block, in file order ----
+ * th = the distribution's parameters (reals, declaration order), y = realization, x = trials (Binomial).
+ * IID_MASK[d][l] = which parameters the block's signature names (bit j = parameter j): the samplers of those
+ * parameters see the factor; IID_READS_Y = whether it names the realization. */
+#define IID_MAX_LAWS 4
+static const int IID_NPARAMS[16] = {0, 1, 1, 2, 3, 1, 2, 1, 2, 2, 2, 2, 2, 2, 2, 1};
+static const int IID_NLAWS[16]   = {0, 3, 2, 2, 4, 1, 1, 4, 4, 3, 2, 3, 3, 3, 2, 1};
+static const int IID_MASK[16][IID_MAX_LAWS] = {
+  {0}, {1, 1, 0}, {1, 0}, {1, 3}, {0, 4, 1, 7}, {1}, {3}, {1, 1, 0, 1}, {3, 2, 1, 2}, {3, 3, 3}, {3, 3},
+  {2, 3, 3}, {1, 2, 3}, {3, 3, 3}, {3, 3}, {1}};
+static const int IID_READS_Y[16][IID_MAX_LAWS] = {
+  {0}, {1, 0, 1}, {1, 1}, {1, 1}, {0, 0, 0, 1}, {1}, {1}, {1, 1, 0, 0}, {1, 1, 0, 0}, {0, 1, 1}, {0, 1},
+  {0, 1, 1}, {0, 0, 1}, {0, 1, 1}, {0, 1}, {1}};
+
+static double gamma_law(int law, double shape, double rate, double y) {   /* Gamma.bl:14-31 */
+  switch (law) {
+    case 0: if (shape <= 0.0 || rate <= 0) return NEG_INF; if (y <= 0.0) return NEG_INF; return (shape - 1.0) * log(y * rate);
+    case 1: if (rate <= 0) return NEG_INF; if (y <= 0.0) return NEG_INF; return -y * rate;
+    case 2: if (shape <= 0.0) return NEG_INF; return -orc_lngamma(shape);
+    default: if (rate <= 0.0) return NEG_INF; return log(rate);
+  }
+}
+static double iid_law(int dist, int law, const double* th, double y, double x) {
+  switch (dist) {
+    case ORC_IID_POISSON: {                       /* Poisson.bl:11-26 */
+      double mean = th[0];
+      if (law == 0) { if (mean <= 0) return NEG_INF; if (y < 0) return NEG_INF; return y * log(mean); }
+      if (law == 1) { if (mean <= 0) return NEG_INF; return -mean; }
+      if (y < 0) return NEG_INF;
+      return -orc_lngamma(y + 1);                 /* StaticUtils.logFactorial :156-158 */
+    }
+    case ORC_IID_BINOMIAL: {                      /* Binomial.bl:14-27, k = y, n = x */
+      double p = th[0];
+      if (law == 0) {
+        if (p < 0.0 || p > 1.0) return NEG_INF;
+        if (y < 0) return NEG_INF;
+        if (x <= 0 || y > x) return NEG_INF;
+        return y * log(p) + (x - y) * log(1.0 - p);
+      }
+      if (y < 0) return NEG_INF;
+      if (x <= 0 || y > x) return NEG_INF;
+      return orc_lngamma(x + 1) - orc_lngamma(y + 1) - orc_lngamma(x - y + 1);   /* logBinomial :160-162 */
+    }
+    case ORC_IID_NEGBINOMIAL: {                   /* NegativeBinomial.bl:14-28 */
+      double r = th[0], p = th[1];
+      if (law == 0) {
+        if (r <= 0 || y < 0) return NEG_INF;
+        double nn = y + r - 1.0;
+        double result = orc_lngamma(nn + 1) - orc_lngamma(y + 1) - orc_lngamma(nn - y + 1);
+        if (result != result) return NEG_INF;
+        return result;
+      }
+      if (p <= 0.0 || p >= 1.0) return NEG_INF;
+      if (r <= 0 || y < 0) return NEG_INF;
+      return y * log(p) + r * log(1.0 - p);
+    }
+    case ORC_IID_STUDENTT: {                      /* StudentT.bl:13-33 */
+      double nu = th[0], mu = th[1], sigma = th[2];
+      if (law == 0) return -0.5 * log(M_PI);
+      if (law == 1) { if (sigma <= 0.0) return NEG_INF; return -log(sigma); }
+      if (law == 2) { if (nu <= 0.0) return NEG_INF; return orc_lngamma((nu + 1.0) / 2.0) - 0.5 * log(nu) - orc_lngamma(nu / 2.0); }
+      if (nu <= 0.0 || sigma <= 0.0) return NEG_INF;
+      return -((nu + 1.0) / 2.0) * log(1.0 + (1.0 / nu) * (1.0 / (pow(sigma, 2))) * pow((y - mu), 2));
+    }
+    case ORC_IID_GEOMETRIC: {                     /* Geometric.bl:10-16 */
+      double p = th[0];
+      if (p <= 0 || p >= 1) return NEG_INF;
+      if (y < 0) return NEG_INF;
+      return y * log(1 - p) + log(p);
+    }
+    case ORC_IID_LAPLACE: {                       /* Laplace.bl:12-17 */
+      double loc = th[0], scale = th[1];
+      if (scale <= 0) return NEG_INF;
+      return -log(2 * scale) - fabs(y - loc) / scale;
+    }
+    case ORC_IID_EXPONENTIAL: return gamma_law(law, 1.0, th[0], y);   /* Exponential.bl:11 -> Gamma(1.0, rate) */
+    case ORC_IID_GAMMA: return gamma_law(law, th[0], th[1], y);
+    case ORC_IID_WEIBULL: {                       /* Weibull.bl:14-33 */
+      double scale = th[0], shape = th[1];
+      if (scale <= 0.0) return NEG_INF;
+      if (shape <= 0.0) return NEG_INF;
+      if (law == 0) return log(shape) - (shape * log(scale));
+      if (y <= 0.0) return NEG_INF;
+      if (law == 1) return (shape - 1) * log(y);
+      return -pow((y / scale), shape);
+    }
+    case ORC_IID_GUMBEL: {                        /* Gumbel.bl:13-22 */
+      double loc = th[0], scale = th[1];
+      if (scale <= 0.0) return NEG_INF;
+      if (law == 0) return -log(scale);
+      return -exp((loc - y) / scale) + ((loc - y) / scale);
+    }
+    case ORC_IID_LOGISTICDIST: {                  /* Logistic.bl:13-26 */
+      double loc = th[0], scale = th[1];
+      if (scale <= 0.0) return NEG_INF;
+      if (law == 0) return -log(scale);
+      if (law == 1) return (loc - y) / scale;
+      return -2 * log(1.0 + exp((loc - y) / scale));
+    }
+    case ORC_IID_HALFSTUDENTT: {                  /* HalfStudentT.bl:12-28 */
+      double nu = th[0], sigma = th[1];
+      if (law == 0) { if (nu <= 0.0) return NEG_INF; return log(2.0) + orc_lngamma((nu + 1) / 2.0) - orc_lngamma(nu / 2.0) - 0.5 * log(nu * M_PI); }
+      if (law == 1) { if (sigma <= 0.0) return NEG_INF; return -log(sigma); }
+      if (y < 0.0) return NEG_INF;
+      if (sigma <= 0.0) return NEG_INF;
+      if (nu <= 0.0) return NEG_INF;
+      return -((nu + 1.0) / 2.0) * log(1.0 + 1.0 / nu * pow(y / sigma, 2));
+    }
+    case ORC_IID_LOGLOGISTIC: {                   /* LogLogistic.bl:14-33 */
+      double scale = th[0], shape = th[1];
+      if (law == 0) { if (scale <= 0.0) return NEG_INF; if (shape <= 0.0) return NEG_INF; return log(shape) - (shape * log(scale)); }
+      if (y < 0.0) return NEG_INF;
+      if (scale <= 0.0) return NEG_INF;
+      if (shape <= 0.0) return NEG_INF;
+      if (law == 1) return shape * log(y) - log(y);
+      return -2 * log(1 + pow((y / scale), shape));
+    }
+    case ORC_IID_GOMPERTZ: {                      /* Gompertz.bl:13-25 */
+      double shape = th[0], scale = th[1];
+      if (law == 0) { if (shape <= 0.0) return NEG_INF; if (scale <= 0.0) return NEG_INF; return log(shape / scale); }
+      if (y < 0.0) return NEG_INF;
+      if (scale <= 0.0) return NEG_INF;
+      if (shape <= 0.0) return NEG_INF;
+      return (y / scale) - (shape * (exp(y / scale) - 1));
+    }
+    case ORC_IID_YULESIMON: {                     /* YuleSimon.bl:10-16, logBeta = StaticUtils :168-170 */
+      double rho = th[0];
+      if (rho <= 0) return NEG_INF;
+      if (y < 0) return NEG_INF;
+      return log(rho) + (orc_lngamma(1.0 + y) + orc_lngamma(rho + 1) - orc_lngamma(1.0 + y + (rho + 1)));
+    }
+  }
+  return NAN;
+}
 
 static double factor_eval(const orc_model* m, const Factor* f, const double* re, const int32_t* in) {
   switch (f->kind) {
@@ -328,75 +457,7 @@ static double factor_eval(const orc_model* m, const Factor* f, const double* re,
       if (prob < 0.0 || prob > 1.0) return NEG_INF;
       return log(s == 1 ? prob : 1.0 - prob);
     }
-    case F_POIS_1: {
-      double mean = re[0], y = m->y[f->i0];
-      if (mean <= 0) return NEG_INF;
-      if (y < 0) return NEG_INF;
-      return y * log(mean);
-    }
-    case F_POIS_2: {
-      double mean = re[0];
-      if (mean <= 0) return NEG_INF;
-      return -mean;
-    }
-    case F_POIS_3: {
-      double y = m->y[f->i0];
-      if (y < 0) return NEG_INF;
-      return -orc_lngamma(y + 1);                      /* StaticUtils.logFactorial :156-158 */
-    }
-    case F_BINOM_1: {
-      double p = re[0], k = m->y[f->i0], n = m->x[f->i0];
-      if (p < 0.0 || p > 1.0) return NEG_INF;
-      if (k < 0) return NEG_INF;
-      if (n <= 0 || k > n) return NEG_INF;
-      return k * log(p) + (n - k) * log(1.0 - p);
-    }
-    case F_BINOM_2: {
-      double k = m->y[f->i0], n = m->x[f->i0];
-      if (k < 0) return NEG_INF;
-      if (n <= 0 || k > n) return NEG_INF;
-      return orc_lngamma(n + 1) - orc_lngamma(k + 1) - orc_lngamma(n - k + 1);   /* logBinomial :160-162 */
-    }
-    case F_NEGBIN_1: {
-      double r = re[0], k = m->y[f->i0];
-      if (r <= 0 || k < 0) return NEG_INF;
-      double nn = k + r - 1.0;
-      double result = orc_lngamma(nn + 1) - orc_lngamma(k + 1) - orc_lngamma(nn - k + 1);
-      if (result != result) return NEG_INF;
-      return result;
-    }
-    case F_NEGBIN_2: {
-      double r = re[0], p = re[1], k = m->y[f->i0];
-      if (p <= 0.0 || p >= 1.0) return NEG_INF;
-      if (r <= 0 || k < 0) return NEG_INF;
-      return k * log(p) + r * log(1.0 - p);
-    }
-    case F_STUD_2: {
-      double sigma = re[2];
-      if (sigma <= 0.0) return NEG_INF;
-      return -log(sigma);
-    }
-    case F_STUD_3: {
-      double nu = re[0];
-      if (nu <= 0.0) return NEG_INF;
-      return orc_lngamma((nu + 1.0) / 2.0) - 0.5 * log(nu) - orc_lngamma(nu / 2.0);
-    }
-    case F_STUD_4: {
-      double nu = re[0], mu = re[1], sigma = re[2], y = m->y[f->i0];
-      if (nu <= 0.0 || sigma <= 0.0) return NEG_INF;
-      return -((nu + 1.0) / 2.0) * log(1.0 + (1.0 / nu) * (1.0 / (pow(sigma, 2))) * pow((y - mu), 2));
-    }
-    case F_GEOM_1: {
-      double p = re[0], y = m->y[f->i0];
-      if (p <= 0 || p >= 1) return NEG_INF;
-      if (y < 0) return NEG_INF;
-      return y * log(1 - p) + log(p);
-    }
-    case F_LAPLACE_1: {
-      double loc = re[0], scale = re[1], y = m->y[f->i0];
-      if (scale <= 0) return NEG_INF;
-      return -log(2 * scale) - fabs(y - loc) / scale;
-    }
+    case F_IID_LAW: return iid_law(m->K, f->i1, re, m->y[f->i0], m->x[f->i0]);
     case F_BETA_A: {
       double alpha = f->c0, x = re[f->i0];
       if (x <= 0.0 || x >= 1.0) return NEG_INF;
@@ -519,9 +580,8 @@ static void b_uniform_prior(Builder* b, int sampler, int var, double mn, double 
  * `y.get(i) | theta ~ Dist(theta)` n times produces, and it is what nOutOfSupport counts. */
 orc_model* orc_model_iid(int dist, const double* y, const double* trials, int n, const int32_t* prior_kind,
                          const double* prior_a, const double* prior_b) {
-  static const int n_params[] = {0, 1, 1, 2, 3, 1, 2};
-  if (dist < ORC_IID_POISSON || dist > ORC_IID_LAPLACE) return NULL;
-  const int P = n_params[dist];
+  if (dist < ORC_IID_POISSON || dist > ORC_IID_YULESIMON) return NULL;
+  const int P = IID_NPARAMS[dist];
   Builder b = b_begin(ORC_FAM_IID, P, 0, P);
   orc_model* m = b.m;
   m->n_obs = n; m->K = dist;
@@ -538,39 +598,11 @@ orc_model* orc_model_iid(int dist, const double* y, const double* trials, int n,
       default: b_uniform_prior(&b, j, j, prior_a[j], prior_b[j]); break;
     }
   }
-  for (int i = 0; i < n; i++) {
-    int f1, f2;
-    switch (dist) {
-      case ORC_IID_POISSON:
-        b_connect(&b, 0, b_factor(&b, F_POIS_1, 1, i, 0, 0, 0, 0));
-        b_connect(&b, 0, b_factor(&b, F_POIS_2, 1, i, 0, 0, 0, 0));
-        b_factor(&b, F_POIS_3, 1, i, 0, 0, 0, 0);
-        break;
-      case ORC_IID_BINOMIAL:
-        b_connect(&b, 0, b_factor(&b, F_BINOM_1, 1, i, 0, 0, 0, 0));
-        b_factor(&b, F_BINOM_2, 1, i, 0, 0, 0, 0);
-        break;
-      case ORC_IID_NEGBINOMIAL:
-        b_connect(&b, 0, b_factor(&b, F_NEGBIN_1, 1, i, 0, 0, 0, 0));
-        f2 = b_factor(&b, F_NEGBIN_2, 1, i, 0, 0, 0, 0);
-        b_connect(&b, 0, f2); b_connect(&b, 1, f2);
-        break;
-      case ORC_IID_STUDENTT:
-        b_factor(&b, F_CONST, 1, 0, 0, 0, -0.5 * log(M_PI), 0);
-        b_connect(&b, 2, b_factor(&b, F_STUD_2, 1, i, 0, 0, 0, 0));
-        b_connect(&b, 0, b_factor(&b, F_STUD_3, 1, i, 0, 0, 0, 0));
-        f1 = b_factor(&b, F_STUD_4, 1, i, 0, 0, 0, 0);
-        b_connect(&b, 0, f1); b_connect(&b, 1, f1); b_connect(&b, 2, f1);
-        break;
-      case ORC_IID_GEOMETRIC:
-        b_connect(&b, 0, b_factor(&b, F_GEOM_1, 1, i, 0, 0, 0, 0));
-        break;
-      default:
-        f1 = b_factor(&b, F_LAPLACE_1, 1, i, 0, 0, 0, 0);
-        b_connect(&b, 0, f1); b_connect(&b, 1, f1);
-        break;
+  for (int i = 0; i < n; i++)
+    for (int l = 0; l < IID_NLAWS[dist]; l++) {
+      int fi = b_factor(&b, F_IID_LAW, 1, i, l, 0, 0, 0);
+      for (int j = 0; j < P; j++) if (IID_MASK[dist][l] & (1 << j)) b_connect(&b, j, fi);
     }
-  }
   return b_end(&b);
 }
 

@@ -48,7 +48,16 @@ enum {
   ORC_IID_NEGBINOMIAL = 3,  /* r, p                  NegativeBinomial.bl */
   ORC_IID_STUDENTT = 4,     /* nu, mu, sigma         StudentT.bl         */
   ORC_IID_GEOMETRIC = 5,    /* p                     Geometric.bl        */
-  ORC_IID_LAPLACE = 6       /* location, scale       Laplace.bl          */
+  ORC_IID_LAPLACE = 6,      /* location, scale       Laplace.bl          */
+  ORC_IID_EXPONENTIAL = 7,  /* rate                  Exponential.bl (-> Gamma(1.0, rate)) */
+  ORC_IID_GAMMA = 8,        /* shape, rate           Gamma.bl            */
+  ORC_IID_WEIBULL = 9,      /* scale, shape          Weibull.bl          */
+  ORC_IID_GUMBEL = 10,      /* location, scale       Gumbel.bl           */
+  ORC_IID_LOGISTICDIST = 11,/* location, scale       Logistic.bl         */
+  ORC_IID_HALFSTUDENTT = 12,/* nu, sigma             HalfStudentT.bl     */
+  ORC_IID_LOGLOGISTIC = 13, /* scale, shape          LogLogistic.bl      */
+  ORC_IID_GOMPERTZ = 14,    /* shape, scale          Gompertz.bl         */
+  ORC_IID_YULESIMON = 15    /* rho                   YuleSimon.bl        */
 };
 /* priors of family 6: (a, b) = (mean, variance) | (shape, rate) | (rate, -) | (alpha, beta) | (min, max) */
 enum { ORC_PRIOR_NORMAL = 0, ORC_PRIOR_GAMMA = 1, ORC_PRIOR_EXPONENTIAL = 2, ORC_PRIOR_BETA = 3, ORC_PRIOR_UNIFORM = 4 };

@@ -18,6 +18,8 @@ from oracle import oracle as O  # noqa: E402
 
 def spec_to_json(spec):
     out = {"family": spec["family"], "hyper": spec["hyper"]}
+    if "truth" in spec:
+        out["truth"] = spec["truth"]
     for k in ("y", "x", "ntrials", "trials"):
         if spec.get(k) is not None:
             out[k] = np.asarray(spec[k]).tolist()
@@ -39,6 +41,10 @@ def main():
                  "geometric": lambda r: [r.uniform(0.05, 0.95)], "laplace": lambda r: [r.normal(0.0, 2.0), r.gamma(2.0, 1.0)]}
     for dist in iid_state:
         specs["iid_" + dist] = D.iid_observations(dist, 45)
+    # nine more laws; their runs start from the generating parameters ("start"), see tests/test_gpu_iid.py
+    more = ["exponential", "gamma", "weibull", "gumbel", "logisticdist", "halfstudentt", "loglogistic", "gompertz", "yulesimon"]
+    for dist in more:
+        specs["iid_" + dist] = D.iid_observations(dist, 45)
     rng = np.random.default_rng(20240600)
     cases = []
     for name, spec in specs.items():
@@ -53,8 +59,10 @@ def main():
                 it = None
             elif name == "logistic":
                 re, it = rng.normal(0, 1.5, m.n_reals).tolist(), None
-            elif name.startswith("iid_"):
+            elif name.startswith("iid_") and name[4:] in iid_state:
                 re, it = [float(v) for v in iid_state[name[4:]](rng)], None
+            elif name.startswith("iid_"):
+                re, it = [float(v * (1.0 + 0.2 * rng.normal())) for v in spec["truth"]], None
             else:
                 re, it = rng.gamma(2.0, 1.0, m.n_reals).tolist(), None
             d = m.log_density(re, it, beta=beta)
@@ -62,11 +70,17 @@ def main():
                              noos=d["noos"], fixed=d["fixed"]))
         pt = O.PT(m, nChains=4, seed=2024,
                   sweepOrder=O.ORDER_CHECKERBOARD if name == "ising" else O.ORDER_REFERENCE)
-        pt.initialize()
+        start = None
+        if name.startswith("iid_") and name[4:] not in iid_state:
+            start = [[float(v * (1.0 + 0.1 * rng.normal())) for v in spec["truth"]] for _ in range(4)]
+            for p, st in enumerate(start):
+                pt.set_state(p, st)
+        else:
+            pt.initialize()
         res = pt.perform_inference(40, 0.5, want_samples=False)
         st = pt.round_stats()
         cases.append(dict(name=name, spec=spec_to_json(spec), densities=dens,
-                          run=dict(nChains=4, seed=2024, nScans=40, adaptFraction=0.5,
+                          run=dict(nChains=4, seed=2024, nScans=40, adaptFraction=0.5, start=start,
                                    energies=res["energies"].tolist(), indicators=res["indicators"].tolist(),
                                    ladder=pt.get_ladder().tolist(), nEvals=pt.n_evals(),
                                    Lambda=st["Lambda"], logZ=st["log_z_stepping_stone"],

@@ -47,3 +47,11 @@ def assert_trajectory_parity(eng, ref, scans, tol=1e-9):
         assert rel(re, rr) < tol
         assert np.array_equal(it, ri)
     return out
+
+
+def start_from(eng, ref, states):
+    """the same explicit state in every chain of both engines (COPIES-style start from a given point)"""
+    for p, st in enumerate(states):
+        eng.set_state(p, st, None)
+        ref.set_state(p, st, None)
+    eng.initialize("COPIES")

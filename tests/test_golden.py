@@ -41,7 +41,11 @@ def test_oracle_reproduces_golden(oracle, case):
     r = case["run"]
     pt = oracle.PT(m, nChains=r["nChains"], seed=r["seed"],
                    sweepOrder=oracle.ORDER_CHECKERBOARD if case["name"] == "ising" else oracle.ORDER_REFERENCE)
-    pt.initialize()
+    if r.get("start"):
+        for p, st in enumerate(r["start"]):
+            pt.set_state(p, st)
+    else:
+        pt.initialize()
     res = pt.perform_inference(r["nScans"], r["adaptFraction"], want_samples=False)
     assert np.array_equal(res["indicators"], np.array(r["indicators"]))
     assert _close(res["energies"], r["energies"]) and _close(pt.get_ladder(), r["ladder"])
@@ -68,8 +72,13 @@ def test_cuda_reproduces_golden(case):
         assert _close(got["logdens"][0, p], d["logdens"])
     eng.close()
     r = case["run"]
-    pt = PT(nChains=r["nChains"], nScans=r["nScans"], adaptFraction=r["adaptFraction"], random=r["seed"], initialization="FORWARD")
+    pt = PT(nChains=r["nChains"], nScans=r["nScans"], adaptFraction=r["adaptFraction"], random=r["seed"],
+            initialization="COPIES" if r.get("start") else "FORWARD")
     pt.setSampledModel(spec)
+    if r.get("start"):
+        for p, st in enumerate(r["start"]):
+            pt.engine.set_state(p, st, None)
+        pt.engine.initialize("COPIES")
     res = pt.performInference()
     assert np.array_equal(res["swapIndicators"][:, 0, :], np.array(r["indicators"]))
     assert _close(res["energy"][:, 0, :], r["energies"]) and _close(res["ladder"][0], r["ladder"])

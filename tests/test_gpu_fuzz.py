@@ -5,7 +5,7 @@ names a reproducible case."""
 import numpy as np
 import pytest
 
-from gpu_util import assert_trajectory_parity, make_pair
+from gpu_util import assert_trajectory_parity, make_pair, start_from
 
 pytestmark = pytest.mark.gpu
 
@@ -21,7 +21,9 @@ def _case(D, rng):
     elif fam == "betabinomial":
         spec = D.beta_binomial(int(rng.integers(0, 1000)), groups=int(rng.integers(1, 70)), trials=int(rng.integers(1, 80)))
     elif fam == "iid":
-        dist = ["poisson", "binomial", "negbinomial", "studentt", "geometric", "laplace"][rng.integers(0, 6)]
+        dists = ["poisson", "binomial", "negbinomial", "studentt", "geometric", "laplace", "exponential", "gamma", "weibull",
+                 "gumbel", "logisticdist", "halfstudentt", "loglogistic", "gompertz", "yulesimon"]
+        dist = dists[rng.integers(0, len(dists))]
         spec = D.iid_observations(dist, int(rng.integers(1, 3000)), seed=int(rng.integers(1, 1 << 30)))
     else:
         # the checkerboard sweep needs an even lattice side
@@ -37,7 +39,11 @@ def test_random_configuration(oracle, datasets, case):
     rng = np.random.default_rng(9000 + case)
     fam, spec, n_chains, seed, ctas, opts = _case(datasets, rng)
     init = "FORWARD" if rng.integers(0, 3) else "COPIES"
+    if fam == "iid":      # start near the generating parameters (see test_gpu_iid.py::test_iid_trajectory_parity)
+        init = "COPIES"
     eng, ref = make_pair(oracle, spec, n_chains, seed=seed, init=init, ctas=ctas, **opts)
+    if fam == "iid":
+        start_from(eng, ref, [[v * (1.0 + 0.1 * rng.normal()) for v in spec["truth"]] for _ in range(n_chains)])
     try:
         assert_trajectory_parity(eng, ref, int(rng.integers(2, 7)))
     finally:

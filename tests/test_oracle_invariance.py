@@ -101,3 +101,50 @@ def test_ising_16_states(oracle, datasets, order):
     folded = freq + freq[::-1]
     assert np.max(np.abs(folded - (p + p[::-1]))) < 0.01
     assert np.max(np.abs(freq - p)) < 0.06
+
+
+# ---- family 6: one exact-invariance test per law, as T/TestSDKDistributions.xtend does for R/distributions ----
+N_OBS = 10              # enough data for power: with 10 observations a 30 % error in a Weibull shape fails the test
+_TRIALS = np.array([5.0, 9.0, 14.0, 3.0, 7.0, 11.0, 2.0, 20.0, 6.0, 8.0])
+
+
+def _pos(rng):          # Gamma(2, 1) draw, the prior of every positive parameter below
+    return rng.gamma(2.0, 1.0)
+
+
+_IID_EIT = {
+    # dist: (priors, prior draw, simulator of N_OBS observations)
+    "poisson": ([("gamma", 2.0, 1.0)], lambda r: [_pos(r)], lambda r, t: r.poisson(t[0], N_OBS)),
+    "binomial": ([("beta", 2.0, 3.0)], lambda r: [r.beta(2.0, 3.0)], lambda r, t: r.binomial(_TRIALS.astype(int), t[0])),
+    "negbinomial": ([("gamma", 2.0, 1.0), ("uniform", 0.0, 1.0)], lambda r: [_pos(r), r.uniform(0.0, 1.0)],
+                    lambda r, t: r.negative_binomial(t[0], 1.0 - t[1], N_OBS)),
+    "studentt": ([("gamma", 2.0, 1.0), ("normal", 0.0, 4.0), ("gamma", 2.0, 1.0)],
+                 lambda r: [_pos(r), r.normal(0.0, 2.0), _pos(r)], lambda r, t: t[1] + t[2] * r.standard_t(t[0], N_OBS)),
+    "geometric": ([("beta", 2.0, 3.0)], lambda r: [r.beta(2.0, 3.0)], lambda r, t: r.geometric(t[0], N_OBS) - 1),
+    "laplace": ([("normal", 0.0, 4.0), ("gamma", 2.0, 1.0)], lambda r: [r.normal(0.0, 2.0), _pos(r)],
+                lambda r, t: r.laplace(t[0], t[1], N_OBS)),
+    "exponential": ([("gamma", 2.0, 1.0)], lambda r: [_pos(r)], lambda r, t: r.exponential(1.0 / t[0], N_OBS)),
+    "gamma": ([("gamma", 2.0, 1.0)] * 2, lambda r: [_pos(r), _pos(r)], lambda r, t: r.gamma(t[0], 1.0 / t[1], N_OBS)),
+    "weibull": ([("gamma", 2.0, 1.0)] * 2, lambda r: [_pos(r), _pos(r)], lambda r, t: t[0] * r.weibull(t[1], N_OBS)),
+    "gumbel": ([("normal", 0.0, 4.0), ("gamma", 2.0, 1.0)], lambda r: [r.normal(0.0, 2.0), _pos(r)],
+               lambda r, t: r.gumbel(t[0], t[1], N_OBS)),
+    "logisticdist": ([("normal", 0.0, 4.0), ("gamma", 2.0, 1.0)], lambda r: [r.normal(0.0, 2.0), _pos(r)],
+                     lambda r, t: r.logistic(t[0], t[1], N_OBS)),
+    "halfstudentt": ([("gamma", 2.0, 1.0)] * 2, lambda r: [_pos(r), _pos(r)], lambda r, t: np.abs(t[1] * r.standard_t(t[0], N_OBS))),
+    "loglogistic": ([("gamma", 2.0, 1.0)] * 2, lambda r: [_pos(r), _pos(r)],
+                    lambda r, t: t[0] * (lambda u: (u / (1.0 - u)) ** (1.0 / t[1]))(r.uniform(1e-12, 1 - 1e-12, N_OBS))),
+    "gompertz": ([("gamma", 2.0, 1.0)] * 2, lambda r: [_pos(r), _pos(r)],
+                 lambda r, t: t[1] * np.log(1.0 - np.log(1.0 - r.uniform(0.0, 1 - 1e-12, N_OBS)) / t[0])),
+    "yulesimon": ([("gamma", 2.0, 1.0)], lambda r: [_pos(r)],
+                  lambda r, t: r.geometric(np.exp(-r.exponential(1.0 / t[0], N_OBS))) - 1),
+}
+
+
+@pytest.mark.parametrize("dist", sorted(_IID_EIT))
+def test_eit_iid(oracle, dist):
+    priors, draw, sim = _IID_EIT[dist]
+    trials = _TRIALS if dist == "binomial" else None
+    spec = lambda y: dict(family="iid", hyper=dict(dist=dist, priors=priors), y=np.asarray(y, dtype=float), trials=trials)
+    n_par = len(priors)
+    fns = [(lambda t, j=j: t[j]) for j in range(n_par)] + [lambda t: float(np.prod(t[:n_par]))]
+    _eit(oracle, spec, draw, sim, n_par, fns, 60 + sorted(_IID_EIT).index(dist))

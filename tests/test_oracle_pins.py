@@ -81,7 +81,11 @@ def _iid_loglik(oracle, dist, y, theta, trials=None):
     priors = {"poisson": [("exponential", 0.1)], "binomial": [("beta", 2.0, 3.0)],
               "negbinomial": [("gamma", 2.0, 0.5), ("uniform", 0.0, 1.0)],
               "studentt": [("exponential", 0.1), ("normal", 0.0, 100.0), ("exponential", 0.5)],
-              "geometric": [("uniform", 0.0, 1.0)], "laplace": [("normal", 0.0, 25.0), ("gamma", 2.0, 1.0)]}[dist]
+              "geometric": [("uniform", 0.0, 1.0)], "laplace": [("normal", 0.0, 25.0), ("gamma", 2.0, 1.0)]}.get(dist)
+    if priors is None:
+        n_par = dict(exponential=1, gamma=2, weibull=2, gumbel=2, logisticdist=2, halfstudentt=2, loglogistic=2,
+                     gompertz=2, yulesimon=1)[dist]
+        priors = [("exponential", 0.5)] * n_par
     spec = dict(family="iid", hyper=dict(dist=dist, priors=priors), y=np.array([float(y)]),
                 trials=None if trials is None else np.array([float(trials)]))
     return oracle.Model(spec).log_density(theta)
@@ -103,6 +107,23 @@ def test_iid_laws_normalise(oracle):
     # Student t: heavy tails, integrate on a finite window and add the exact tail mass of t_5 beyond 400 scale units
     stu = lambda ys: np.array([math.exp(_iid_loglik(oracle, "studentt", y, [5.0, 1.0, 2.0])["loglik"]) for y in ys])
     assert abs(_simpson(stu, 1.0 - 800.0, 1.0 + 800.0, 40000) - 1.0) < 1e-6
+    # the other continuous laws of family 6: integrate exp(loglik) over the realization
+    def pdf(dist, theta):
+        return lambda ys: np.array([math.exp(_iid_loglik(oracle, dist, y, theta)["loglik"]) for y in ys])
+    def on_log_scale(f):      # int f(y) dy = int f(e^u) e^u du: smooth even where f ~ y^(shape-1) at the origin
+        return lambda us: f(np.exp(us)) * np.exp(us)
+    assert abs(_simpson(pdf("exponential", [1.7]), 1e-12, 40.0, 4000) - 1.0) < 1e-6
+    assert abs(_simpson(pdf("gamma", [2.5, 1.2]), 1e-12, 60.0, 6000) - 1.0) < 1e-6
+    assert abs(_simpson(on_log_scale(pdf("weibull", [2.0, 1.5])), -40.0, math.log(40.0), 4000) - 1.0) < 1e-6
+    assert abs(_simpson(pdf("gumbel", [0.5, 1.2]), -12.0, 45.0, 6000) - 1.0) < 1e-6
+    assert abs(_simpson(pdf("logisticdist", [1.0, 0.8]), -30.0, 32.0, 6000) - 1.0) < 1e-6
+    assert abs(_simpson(pdf("halfstudentt", [5.0, 1.5]), 0.0, 900.0, 40000) - 1.0) < 1e-6
+    assert abs(_simpson(on_log_scale(pdf("loglogistic", [2.0, 3.0])), -30.0, 30.0, 4000) - 1.0) < 1e-6
+    assert abs(_simpson(pdf("gompertz", [0.8, 1.5]), 0.0, 12.0, 4000) - 1.0) < 1e-6
+    tot = sum(math.exp(_iid_loglik(oracle, "yulesimon", y, [2.5])["loglik"]) for y in range(0, 3000))
+    assert abs(tot - 1.0) < 1e-6      # tail ~ Gamma(3.5) k^-2.5: 3000^-2.5 * 3.3 = 7e-9
+    assert _iid_loglik(oracle, "gamma", 1.3, [-1.0, 2.0])["noos"] == 2 and _iid_loglik(oracle, "gamma", 1.3, [1.0, -2.0])["noos"] == 3
+    assert _iid_loglik(oracle, "weibull", -1.0, [1.0, 2.0])["noos"] == 2
     # out-of-support parameters: every law that reads them is -inf, one count per observation and law
     assert _iid_loglik(oracle, "poisson", 3, [-1.0])["noos"] == 2
     assert _iid_loglik(oracle, "studentt", 0.3, [-1.0, 0.0, 1.0])["noos"] == 2      # nu: its own law and the joint one
