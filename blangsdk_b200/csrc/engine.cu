@@ -42,6 +42,7 @@ struct blangpt_handle {
   // family data
   NormalFam::Data normal{};
   IidFam::Data iid{};
+  HierFam::Data hier{};
   LogisticFam::Data logistic{};
   MixtureFam<4>::Data mixture{};
   BetaBinomialFam::Data betabin{};
@@ -152,6 +153,7 @@ static int launch_explore(blangpt_handle* h, int mode) {
   switch (h->family) {
     case BLANGPT_FAM_NORMAL: return launch_explore_t<NormalFam>(h, h->normal, mode);
     case BLANGPT_FAM_IID: return launch_explore_t<IidFam>(h, h->iid, mode);
+    case BLANGPT_FAM_HIERARCHICAL: return launch_explore_t<HierFam>(h, h->hier, mode);
     case BLANGPT_FAM_LOGISTIC:
       if (h->logistic_threads == 1024) {
         LogisticFamT<1024>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
@@ -193,6 +195,7 @@ static bool use_fused(const blangpt_handle* h) {
   if (h->family == BLANGPT_FAM_BETABINOMIAL) return forced || h->cfg.nReplicas >= 8;
   if (h->family == BLANGPT_FAM_NORMAL) return h->normal.n <= 65536 && (forced || h->cfg.nReplicas >= 8);
   if (h->family == BLANGPT_FAM_IID) return h->iid.n <= 65536 && (forced || h->cfg.nReplicas >= 8);
+  if (h->family == BLANGPT_FAM_HIERARCHICAL) return forced || h->cfg.nReplicas >= 8;
   return false;
 }
 
@@ -360,6 +363,18 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
       h->normal = {y, n, hyper[0], hyper[1], hyper[2]};
       h->n_reals = 2; h->n_samplers = 2; rows = n;
     } break;
+    case BLANGPT_FAM_HIERARCHICAL: {
+      if (na != 2 || nh != 2 || a[0].dtype != BLANGPT_I32 || a[1].dtype != BLANGPT_I32 || a[0].n_elem != a[1].n_elem)
+        FAIL(h, BLANGPT_EINVAL, "hierarchical: expects failures[i32 G], launches[i32 G], hyper (rate_a, rate_b)");
+      const int G = (int)a[0].n_elem;
+      if (G < 1 || G + 2 > kMaxParams) FAIL(h, BLANGPT_EUNSUPPORTED, "hierarchical: 1 <= groups <= %d", kMaxParams - 2);
+      int *y, *nt;
+      if ((rc = dev_alloc(h, &y, G)) || (rc = dev_alloc(h, &nt, G))) return rc;
+      CUDA_OK(h, cudaMemcpyAsync(y, a[0].data, G * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(h, cudaMemcpyAsync(nt, a[1].data, G * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      h->hier = {y, nt, G, hyper[0], hyper[1]};
+      h->n_reals = G + 2; h->n_samplers = G + 2; rows = 1;
+    } break;
     case BLANGPT_FAM_IID: {
       const int dist = nh >= 1 ? (int)hyper[0] : 0;
       if (dist < IID_POISSON || dist >= IID_N_DISTS) FAIL(h, BLANGPT_EUNSUPPORTED, "iid: unknown distribution code %d", dist);
@@ -478,6 +493,7 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
   auto fill = [&](int v, double x) { for (int l = 0; l < h->E.M_local; l++) init[(size_t)v * h->E.M_local + l] = x; };
   if (family == BLANGPT_FAM_NORMAL) { fill(0, 0.0); fill(1, 1.0); }
   if (family == BLANGPT_FAM_BETABINOMIAL) { fill(0, 1.0); fill(1, 1.0); }
+  if (family == BLANGPT_FAM_HIERARCHICAL) { fill(0, 1.0); fill(1, 1.0); for (int g = 0; g < h->hier.G; g++) fill(2 + g, 0.5); }
   if (family == BLANGPT_FAM_MIXTURE) { const int K = h->mixture.K; for (int k = 0; k < K; k++) { fill(k, 0.0); fill(K + k, 1.0); fill(2 * K + k, 1.0 / K); } }
   if (h->n_reals) CUDA_OK(h, cudaMemcpyAsync(h->E.reals, init.data(), init.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
@@ -655,7 +671,7 @@ static int scm_initialize(blangpt_handle* h) {
   c->cfg.random = h->cfg.random ^ 0x53434D2D696E6974ULL;   // its own Philox key ("SCM-init")
   c->M_total = P; c->family = h->family; c->stream = h->stream; c->logistic_threads = h->logistic_threads;
   c->n_reals = h->n_reals; c->n_ints = h->n_ints; c->n_samplers = h->n_samplers;
-  c->normal = h->normal; c->iid = h->iid; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising;
+  c->normal = h->normal; c->iid = h->iid; c->hier = h->hier; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising;
   c->betabin.chains_per_replica = P;
   auto fail = [&](int code) { for (void* p : c->allocs) cudaFree(p); if (code) h->error = c->error; delete c; return code; };
   if (h->family == BLANGPT_FAM_LOGISTIC && (rc = dev_alloc(c, &c->logistic.eta, (size_t)c->logistic.npad * P))) return fail(rc);
@@ -849,6 +865,7 @@ extern "C" int blangpt_run_scans(blangpt_handle* h, int32_t n_scans, const blang
     const int threads = 32 * h->cfg.nChains;
     if (h->family == BLANGPT_FAM_NORMAL) replica_kernel<NormalFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->normal, n_scans);
     else if (h->family == BLANGPT_FAM_IID) replica_kernel<IidFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->iid, n_scans);
+    else if (h->family == BLANGPT_FAM_HIERARCHICAL) replica_kernel<HierFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->hier, n_scans);
     else replica_kernel<BetaBinomialFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->betabin, n_scans);
     CUDA_OK(h, cudaGetLastError());
     h->n_launches++;

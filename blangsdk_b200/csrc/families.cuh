@@ -731,6 +731,95 @@ struct IidFam {
 };
 
 // ===========================================================================
+// Family 7: F/HierarchicalModel.bl, not marginalised (the rocket-launch example of the Blang documentation)
+//   a ~ Exponential(rate_a), b ~ Exponential(rate_b), p_g | a, b ~ Beta(a, b), y_g | p_g ~ Binomial(n_g, p_g)
+// P = [a, b, p_0 .. p_{G-1}], one real slice sampler each.  The Beta blocks are fixed factors (p_g is latent); only
+// the Binomial blocks are annealed, and a move of p_g touches one of them: no reduction, every thread of the chain
+// group computes the same scalars.  Small by nature (G <= 62): one warp per chain, many replicas per launch.
+// ===========================================================================
+struct HierFam {
+  struct Data { const int* y; const int* n; int G; double rate_a, rate_b; };
+  static constexpr int kThreads = 32;
+  static constexpr bool kWarpCapable = true;
+  static constexpr int kFusedParams = kMaxParams;   // a, b and up to 62 group probabilities per chain
+  Data d; double* P; int* err;
+  double sum_log_p, sum_log1m_p; bool p_inside;   // over the groups, refreshed when a sampler execution begins
+
+  BPT_D static int n_reals(const Data& d) { return d.G + 2; }
+  BPT_D static int n_samplers(const Data& d) { return d.G + 2; }
+  BPT_D void init(const Data& d_, int, double* P_, int, int, int* err_) {
+    d = d_; P = P_; err = err_; sum_log_p = 0.0; sum_log1m_p = 0.0; p_inside = false;   // set by begin_execution()
+  }
+  BPT_D void set_lanes(int, int) {}
+  BPT_D int sampler_type(int) const { return S_REAL_SLICE; }
+  BPT_D int sampler_var(int k) const { return k; }
+  BPT_D int simplex_dim() const { return 0; }
+  BPT_D static void tables_init() {}
+  BPT_D void sums() {
+    double s1 = 0.0, s2 = 0.0; bool ok = true;
+    for (int g = 0; g < d.G; g++) {
+      const double p = P[2 + g];
+      if (p <= 0.0 || p >= 1.0) ok = false; else { s1 += log(p); s2 += log1p(-p); }
+    }
+    sum_log_p = s1; sum_log1m_p = s2; p_inside = ok;
+  }
+  BPT_D void begin_execution() { sums(); }
+  // Beta.bl:14-41 with latent parameters, the blocks that name variable k
+  BPT_D double fixed(int k, double x, int) const {
+    const double a = k == 0 ? x : P[0], b = k == 1 ? x : P[1];
+    if (k == 0) {        // Exponential prior + G x { (a-1) log p_g, lnGamma(a+b), -lnGamma(a) }
+      if (a <= 0.0 || !p_inside || b <= 0.0) return BPT_NEG_INF;
+      return gamma_ab(1.0, d.rate_a, a) + (a - 1.0) * sum_log_p + d.G * (lgamma(a + b) - lgamma(a));
+    }
+    if (k == 1) {        // Exponential prior + G x { (b-1) log1p(-p_g), lnGamma(a+b), -lnGamma(b) }
+      if (b <= 0.0 || !p_inside || a <= 0.0) return BPT_NEG_INF;
+      return gamma_ab(1.0, d.rate_b, b) + (b - 1.0) * sum_log1m_p + d.G * (lgamma(a + b) - lgamma(b));
+    }
+    if (x <= 0.0 || x >= 1.0 || a <= 0.0 || b <= 0.0) return BPT_NEG_INF;
+    return (a - 1.0) * log(x) + (b - 1.0) * log1p(-x);
+  }
+  BPT_D static double binomial_block(int law, double y, double n, double p) {
+    const double th[1] = {p};
+    return iid_law(IID_BINOMIAL, law, th, y, n);
+  }
+  // annealed factors connected to variable k: none for a and b, the group's first Binomial block for p_g
+  BPT_D void annealed(int k, double x, int, GroupReducer&, double& s, int& c) const {
+    s = 0.0; c = 0;
+    if (k < 2) return;
+    const int g = k - 2;
+    acc_term(binomial_block(0, (double)d.y[g], (double)d.n[g], x), s, c, err);
+  }
+  BPT_D void commit(int k, double x, int) { P[k] = x; }
+  BPT_D void refresh() {}
+  BPT_D void full(GroupReducer&, double& loglik, int& noos, double& logprior) {
+    double s = 0.0; int c = 0;
+    for (int g = 0; g < d.G; g++) {
+      acc_term(binomial_block(0, (double)d.y[g], (double)d.n[g], P[2 + g]), s, c, err);
+      acc_term(binomial_block(1, (double)d.y[g], (double)d.n[g], P[2 + g]), s, c, err);
+    }
+    loglik = s; noos = c;
+    const double a = P[0], b = P[1];
+    double lp = gamma_ab(1.0, d.rate_a, a) + gamma_cd(1.0, d.rate_a) + gamma_ab(1.0, d.rate_b, b) + gamma_cd(1.0, d.rate_b);
+    for (int g = 0; g < d.G; g++) {
+      const double p = P[2 + g];
+      const bool in = p > 0.0 && p < 1.0;
+      lp += (in && a > 0.0) ? (a - 1.0) * log(p) : BPT_NEG_INF;
+      lp += (in && b > 0.0) ? (b - 1.0) * log1p(-p) : BPT_NEG_INF;
+      lp += (a > 0.0 && b > 0.0) ? lgamma(a + b) : BPT_NEG_INF;
+      lp += a > 0.0 ? -lgamma(a) : BPT_NEG_INF;
+      lp += b > 0.0 ? -lgamma(b) : BPT_NEG_INF;
+    }
+    logprior = lp;
+  }
+  BPT_D void forward(Rng& rng) {   // topological order: a, b, then every p_g
+    const double a = gen_exponential(rng, d.rate_a);
+    const double b = gen_exponential(rng, d.rate_b);
+    P[0] = a; P[1] = b;
+    for (int g = 0; g < d.G; g++) { const double p = gen_beta(rng, a, b); P[2 + g] = p; }
+  }
+};
+
+// ===========================================================================
 // C2  Bayesian logistic regression.  P = w[0..p)
 //     per-chain cache eta_i = s_i * (x_i . w) in HBM, s_i = +1 if y_i = 1 else -1 (the rows of
 //     the device copy of X are sign-folded once at set_model, which is exact); a move of w_k

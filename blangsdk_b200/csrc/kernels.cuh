@@ -339,10 +339,14 @@ __global__ void swap_kernel(DevEngine E, DevStats St, DevOut O) { swap_replica(E
 // one CTA per replica, one WARP per chain (reductions are shuffles only), and the whole scan loop --
 // explore, record, DEO swap, index process -- runs inside the kernel, so n_scans scans cost one launch and
 // the swap pass costs two block barriers instead of two kernel launches.
+// per-chain parameter / sampler-order slots of the fused kernel: 8 unless the family states kFusedParams
+template <class Fam, class = void> struct FusedParamsOf { static constexpr int value = 8; };
+template <class Fam> struct FusedParamsOf<Fam, decltype((void)Fam::kFusedParams)> { static constexpr int value = Fam::kFusedParams; };
+
 template <class Fam>
 __global__ void __launch_bounds__(1024) replica_kernel(DevEngine E, DevStats St, DevOut O, typename Fam::Data D, int n_scans) {
-  __shared__ double Pall[32][8];
-  __shared__ int order_all[32][8];
+  __shared__ double Pall[32][FusedParamsOf<Fam>::value];
+  __shared__ int order_all[32][FusedParamsOf<Fam>::value];
   const int rep = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int l = rep * E.N + warp;              // local slot == global slot (single-process path)
   double* P = Pall[warp];

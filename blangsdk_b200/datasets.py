@@ -134,3 +134,12 @@ def iid_observations(dist="poisson", n=2000, seed=SEED_IID):
                          logisticdist=[1.0, 0.8], halfstudentt=[4.0, 1.5], loglogistic=[2.0, 3.0], gompertz=[0.8, 1.5],
                          yulesimon=[2.5])[dist]
     return spec
+
+
+def hierarchical_rockets(groups=12, seed=20240007):
+    """Family "hierarchical": F/HierarchicalModel.bl (the rocket-launch example), not marginalised."""
+    rng = np.random.default_rng(seed)
+    launches = rng.integers(1, 60, groups).astype(np.int32)
+    p = rng.beta(1.2, 6.0, groups)
+    failures = rng.binomial(launches, p).astype(np.int32)
+    return dict(family="hierarchical", hyper=dict(rate_a=1.0, rate_b=1.0), y=failures, ntrials=launches)

@@ -29,6 +29,7 @@ VARIABLES = {
     "mixture": [("means", "index_0", 0, "K"), ("variances", "index_0", "K", "K"), ("pi", "entry", "2K", "K")],
     "betabinomial": [("alpha", None, 0, 1), ("beta", None, 1, 1)],
     "ising": [("vertices", "index_0", 0, None)],
+    "hierarchical": [("a", None, 0, 1), ("b", None, 1, 1), ("failureProbabilities", "rocketType", 2, None)],
 }
 # family "iid": the latent parameters of each observation law, named as in R/distributions/<Name>.bl
 IID_VARIABLES = {

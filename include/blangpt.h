@@ -47,8 +47,11 @@ enum {
   BLANGPT_FAM_MIXTURE = 3,      /* data: y[n] f64. hyper: K, m0, v0, gshape, grate, conc */
   BLANGPT_FAM_ISING = 4,        /* no data.       hyper: N, coupling, moment             */
   BLANGPT_FAM_BETABINOMIAL = 5, /* data: y[R*n] i32, ntrials[R*n] i32. hyper: rate       */
-  BLANGPT_FAM_IID = 6           /* y_i ~ Dist(theta) i.i.d., theta_j ~ prior_j.  data: y[n] f64 (+ trials[n] f64 for
+  BLANGPT_FAM_IID = 6,          /* y_i ~ Dist(theta) i.i.d., theta_j ~ prior_j.  data: y[n] f64 (+ trials[n] f64 for
                                    BINOMIAL).  hyper: dist, then (prior kind, a, b) for each parameter            */
+  BLANGPT_FAM_HIERARCHICAL = 7  /* F/HierarchicalModel.bl, not marginalised: a, b ~ Exponential; p_g ~ Beta(a, b);
+                                   failures_g ~ Binomial(launches_g, p_g).  data: failures[G] i32, launches[G] i32.
+                                   hyper: rate_a, rate_b.  reals = a, b, p_0 .. p_{G-1}                            */
 };
 /* family 6: observation laws (R/distributions/<Name>.bl) and their latent parameters, in this order */
 enum {

@@ -211,6 +211,8 @@ enum {
   F_BERN_NODE,        /* F/Ising.bl:27-29 -> Bernoulli.bl -> Categorical.bl; spin i0, p=c0 */
   F_BETABINOM,        /* BetaBinomial.bl:17-30 group i0, alpha = real i1, beta = real i2 */
   F_IID_LAW,          /* family 6: law i1 of the observation distribution, observation i0 (iid_law below) */
+  F_HBETA,            /* family 7: block i2 of Beta.bl:14-41 with LATENT alpha = real 0, beta = real 1, realization = real i0 */
+  F_HBINOM,           /* family 7: block i1 of Binomial.bl:14-27, group i0, p = real 2 + i0 */
   F_BETA_A, F_BETA_B,                      /* Beta.bl:14-27 prior on real i0, alpha = c0, beta = c1  */
   F_UNIF_B                                 /* ContinuousUniform.bl:16-19 prior on real i0, [c0, c1]  */
 };
@@ -231,7 +233,7 @@ typedef struct {
   int32_t *fixed_idx, *ann_idx;   /* sampler2sparseUpdate{Fixed,Annealed}, SampledModel.java:67-69 */
 } Sampler;
 
-enum { FW_NORMAL = 0, FW_EXPONENTIAL, FW_GAMMA, FW_DIRICHLET_SYM, FW_BERNOULLI_INT, FW_BETA, FW_UNIFORM };
+enum { FW_NORMAL = 0, FW_EXPONENTIAL, FW_GAMMA, FW_DIRICHLET_SYM, FW_BERNOULLI_INT, FW_BETA, FW_UNIFORM, FW_BETA_LATENT };
 typedef struct { int32_t kind, var, K; double a, b; } Forward;
 
 struct orc_model {
@@ -458,6 +460,29 @@ static double factor_eval(const orc_model* m, const Factor* f, const double* re,
       return log(s == 1 ? prob : 1.0 - prob);
     }
     case F_IID_LAW: return iid_law(m->K, f->i1, re, m->y[f->i0], m->x[f->i0]);
+    case F_HBETA: {
+      double alpha = re[0], beta = re[1], x = re[f->i0];
+      switch (f->i2) {
+        case 0:
+          if (x <= 0.0 || x >= 1.0) return NEG_INF;
+          if (alpha <= 0.0) return NEG_INF;
+          return (alpha - 1.0) * log(x);
+        case 1:
+          if (x <= 0.0 || x >= 1.0) return NEG_INF;
+          if (beta <= 0.0) return NEG_INF;
+          return (beta - 1.0) * log1p(-x);
+        case 2:
+          if (alpha <= 0.0) return NEG_INF;
+          if (beta <= 0.0) return NEG_INF;
+          return orc_lngamma(alpha + beta);
+        case 3: if (alpha <= 0.0) return NEG_INF; return -orc_lngamma(alpha);
+        default: if (beta <= 0.0) return NEG_INF; return -orc_lngamma(beta);
+      }
+    }
+    case F_HBINOM: {
+      const double th[1] = {re[2 + f->i0]};
+      return iid_law(ORC_IID_BINOMIAL, f->i1, th, (double)m->yi[f->i0], (double)m->ntrials[f->i0]);
+    }
     case F_BETA_A: {
       double alpha = f->c0, x = re[f->i0];
       if (x <= 0.0 || x >= 1.0) return NEG_INF;
@@ -603,6 +628,33 @@ orc_model* orc_model_iid(int dist, const double* y, const double* trials, int n,
       int fi = b_factor(&b, F_IID_LAW, 1, i, l, 0, 0, 0);
       for (int j = 0; j < P; j++) if (IID_MASK[dist][l] & (1 << j)) b_connect(&b, j, fi);
     }
+  return b_end(&b);
+}
+
+/* family 7: F/HierarchicalModel.bl (the rocket-launch example of the Blang documentation), not marginalised:
+ *   a ~ Exponential(rate_a), b ~ Exponential(rate_b), p_g | a, b ~ Beta(a, b), failures_g | p_g ~ Binomial(launches_g, p_g).
+ * reals = [a, b, p_0 .. p_{G-1}], one real slice sampler each.  The five Beta blocks per group are FIXED factors
+ * (p_g is latent), the two Binomial blocks per group are annealed (failures are observed). */
+orc_model* orc_model_hierarchical(const int32_t* failures, const int32_t* launches, int G, double rate_a, double rate_b) {
+  Builder b = b_begin(ORC_FAM_HIERARCHICAL, G + 2, 0, G + 2);
+  orc_model* m = b.m; m->n_obs = G;
+  m->yi = (int32_t*)malloc(sizeof(int32_t) * (G > 0 ? G : 1)); memcpy(m->yi, failures, sizeof(int32_t) * G);
+  m->ntrials = (int32_t*)malloc(sizeof(int32_t) * (G > 0 ? G : 1)); memcpy(m->ntrials, launches, sizeof(int32_t) * G);
+  for (int s = 0; s < G + 2; s++) { m->samplers[s].type = S_REAL_SLICE; m->samplers[s].var = s; }
+  b_gamma_prior(&b, 0, 0, 1.0, rate_a, 1);
+  b_gamma_prior(&b, 1, 1, 1.0, rate_b, 1);
+  for (int g = 0; g < G; g++) {
+    int fa = b_factor(&b, F_HBETA, 0, 2 + g, 0, 0, 0, 0);   b_connect(&b, 0, fa); b_connect(&b, 2 + g, fa);
+    int fb = b_factor(&b, F_HBETA, 0, 2 + g, 0, 1, 0, 0);   b_connect(&b, 1, fb); b_connect(&b, 2 + g, fb);
+    int fc = b_factor(&b, F_HBETA, 0, 2 + g, 0, 2, 0, 0);   b_connect(&b, 0, fc); b_connect(&b, 1, fc);
+    b_connect(&b, 0, b_factor(&b, F_HBETA, 0, 2 + g, 0, 3, 0, 0));
+    b_connect(&b, 1, b_factor(&b, F_HBETA, 0, 2 + g, 0, 4, 0, 0));
+    b_forward(m, FW_BETA_LATENT, 2 + g, 0, 0, 0);
+    b_connect(&b, 2 + g, b_factor(&b, F_HBINOM, 1, g, 0, 0, 0, 0));
+    b_factor(&b, F_HBINOM, 1, g, 1, 0, 0, 0);
+  }
+  m->init_reals[0] = 1.0; m->init_reals[1] = 1.0;
+  for (int g = 0; g < G; g++) m->init_reals[2 + g] = 0.5;
   return b_end(&b);
 }
 
@@ -841,6 +893,7 @@ static void sm_forward_sample(SampledModel* s, Rng* r) {
       case FW_GAMMA: s->reals[f->var] = gen_gamma(r, f->a, f->b); break;
       case FW_BERNOULLI_INT: s->ints[f->var] = rng_bernoulli(r, f->a) ? 1 : 0; break;
       case FW_BETA: s->reals[f->var] = gen_beta(r, f->a, f->b); break;
+      case FW_BETA_LATENT: s->reals[f->var] = gen_beta(r, s->reals[0], s->reals[1]); break;   /* parameters drawn just before */
       case FW_UNIFORM: s->reals[f->var] = f->a + rng_double(r) * (f->b - f->a); break;   /* Generators.uniform :197-202 */
       case FW_DIRICHLET_SYM: {   /* Generators.dirichletInPlace :233-272 */
         double* out = s->reals + f->var; int K = f->K; double conc = f->a;

@@ -75,6 +75,8 @@ def lib():
     L.orc_model_ising.argtypes = [C.c_int, C.c_double, C.c_double]
     L.orc_model_betabinomial.restype = vp
     L.orc_model_betabinomial.argtypes = [_ip, _ip, C.c_int, C.c_double]
+    L.orc_model_hierarchical.restype = vp
+    L.orc_model_hierarchical.argtypes = [_ip, _ip, C.c_int, C.c_double, C.c_double]
     L.orc_model_iid.restype = vp
     L.orc_model_iid.argtypes = [C.c_int, _dp, _dp, C.c_int, _ip, _dp, _dp]
     L.orc_model_free.argtypes = [vp]
@@ -188,6 +190,10 @@ class Model:
             y = np.ascontiguousarray(spec["y"], dtype=np.int32)
             nt = np.ascontiguousarray(spec["ntrials"], dtype=np.int32)
             self.h = L.orc_model_betabinomial(_i(y), _i(nt), len(y), h["rate"])
+        elif fam == "hierarchical":
+            y = np.ascontiguousarray(spec["y"], dtype=np.int32)
+            nt = np.ascontiguousarray(spec["ntrials"], dtype=np.int32)
+            self.h = L.orc_model_hierarchical(_i(y), _i(nt), len(y), h["rate_a"], h["rate_b"])
         elif fam == "iid":
             y = np.ascontiguousarray(spec["y"], dtype=np.float64)
             tr = np.ascontiguousarray(spec["trials"], dtype=np.float64) if spec.get("trials") is not None else None

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _case(D, rng):
-    fam = ["normal", "logistic", "mixture", "betabinomial", "ising", "iid"][rng.integers(0, 6)]
+    fam = ["normal", "logistic", "mixture", "betabinomial", "ising", "iid", "hierarchical"][rng.integers(0, 7)]
     if fam == "normal":
         spec = D.normal_meanvar(n=int(rng.integers(1, 3000)), seed=int(rng.integers(1, 1 << 30)))
     elif fam == "logistic":
@@ -20,6 +20,8 @@ def _case(D, rng):
         spec = D.gaussian_mixture(int(rng.integers(1, 4000)), seed=int(rng.integers(1, 1 << 30)))
     elif fam == "betabinomial":
         spec = D.beta_binomial(int(rng.integers(0, 1000)), groups=int(rng.integers(1, 70)), trials=int(rng.integers(1, 80)))
+    elif fam == "hierarchical":
+        spec = D.hierarchical_rockets(int(rng.integers(1, 63)), seed=int(rng.integers(1, 1 << 30)))
     elif fam == "iid":
         dists = ["poisson", "binomial", "negbinomial", "studentt", "geometric", "laplace", "exponential", "gamma", "weibull",
                  "gumbel", "logisticdist", "halfstudentt", "loglogistic", "gompertz", "yulesimon"]
@@ -34,7 +36,7 @@ def _case(D, rng):
     return fam, spec, int(rng.integers(1, 14)), int(rng.integers(1, 1 << 20)), ctas, opts
 
 
-@pytest.mark.parametrize("case", range(60))
+@pytest.mark.parametrize("case", range(70))
 def test_random_configuration(oracle, datasets, case):
     rng = np.random.default_rng(9000 + case)
     fam, spec, n_chains, seed, ctas, opts = _case(datasets, rng)

@@ -148,3 +148,16 @@ def test_eit_iid(oracle, dist):
     n_par = len(priors)
     fns = [(lambda t, j=j: t[j]) for j in range(n_par)] + [lambda t: float(np.prod(t[:n_par]))]
     _eit(oracle, spec, draw, sim, n_par, fns, 60 + sorted(_IID_EIT).index(dist))
+
+
+def test_eit_hierarchical(oracle):
+    """F/HierarchicalModel.bl un-marginalised: a, b and three group probabilities"""
+    launches = np.array([6, 11, 17], dtype=np.int32)
+    def prior(rng):
+        a, b = rng.exponential(1.0), rng.exponential(1.0)
+        p = np.clip(rng.beta(a, b, 3), 1e-300, 1 - 1e-16)
+        return [a, b] + list(p)
+    def sim(rng, th):
+        return rng.binomial(launches, th[2:]).astype(np.int32)
+    spec = lambda y: dict(family="hierarchical", hyper=dict(rate_a=1.0, rate_b=1.0), y=y, ntrials=launches)
+    _eit(oracle, spec, prior, sim, 5, [lambda t: t[0], lambda t: t[1], lambda t: t[2], lambda t: t[0] / (t[0] + t[1])], 7)
