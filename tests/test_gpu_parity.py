@@ -225,17 +225,27 @@ def test_ising_spins_bit_exact(oracle, datasets):
 
 
 def test_determinism(datasets):
-    """R/validation/DeterminismTest.java:24-51: same seed => identical trace"""
+    """R/validation/DeterminismTest.java:24-51: same seed => identical trace, bit for bit, for every family, cluster
+    size and kernel variant (compute-sanitizer's racecheck is not available on the pool: an unordered shared-memory
+    or DSMEM exchange would show up here as a run-to-run difference, as the one in the C2 commit once did)"""
     from blangsdk_b200.engine import Engine
-    outs = []
-    for _ in range(2):
-        eng = Engine(nChains=8, random=77)
-        eng.set_model(datasets.logistic_regression(2000, 6))
-        eng.initialize("FORWARD")
-        outs.append(eng.run_scans(10))
-        eng.close()
-    for k in ("energy", "swapIndicators", "samples"):
-        assert np.array_equal(outs[0][k], outs[1][k])
+    cases = [(datasets.logistic_regression(5000, 6), dict(nChains=8), 0), (datasets.logistic_regression(5000, 6), dict(nChains=8), 4),
+             (datasets.gaussian_mixture(6000), dict(nChains=6), 0), (datasets.gaussian_mixture(6000), dict(nChains=6), 4),
+             (datasets.normal_meanvar(n=3000), dict(nChains=8), 2), (datasets.ising(8), dict(nChains=6), 0),
+             (datasets.beta_binomial_batch(16), dict(nChains=6, nReplicas=16), 0),
+             (datasets.iid_observations("studentt", 4000), dict(nChains=8), 2),
+             (datasets.hierarchical_rockets(20), dict(nChains=8, nReplicas=8), 0)]
+    for spec, kw, ctas in cases:
+        outs = []
+        for _ in range(3):
+            eng = Engine(random=77, ctasPerChain=ctas, **kw)
+            eng.set_model(spec)
+            eng.initialize("FORWARD")
+            want = ("energy", "swapIndicators") + (("samples",) if spec["family"] != "ising" else ("intSamples",))
+            outs.append(eng.run_scans(12, want=want))
+            eng.close()
+        for k in outs[0]:
+            assert np.array_equal(outs[0][k], outs[1][k]) and np.array_equal(outs[0][k], outs[2][k]), (spec["family"], ctas, k)
 
 
 def test_split_phase_equals_run_scans(datasets):
