@@ -43,6 +43,7 @@ struct blangpt_handle {
   NormalFam::Data normal{};
   IidFam::Data iid{};
   HierFam::Data hier{};
+  LinRegFam::Data linreg{};
   LogisticFam::Data logistic{};
   MixtureFam<4>::Data mixture{};
   BetaBinomialFam::Data betabin{};
@@ -154,6 +155,7 @@ static int launch_explore(blangpt_handle* h, int mode) {
     case BLANGPT_FAM_NORMAL: return launch_explore_t<NormalFam>(h, h->normal, mode);
     case BLANGPT_FAM_IID: return launch_explore_t<IidFam>(h, h->iid, mode);
     case BLANGPT_FAM_HIERARCHICAL: return launch_explore_t<HierFam>(h, h->hier, mode);
+    case BLANGPT_FAM_LINREG: return launch_explore_t<LinRegFam>(h, h->linreg, mode);
     case BLANGPT_FAM_LOGISTIC:
       if (h->logistic_threads == 1024) {
         LogisticFamT<1024>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
@@ -362,6 +364,32 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
       CUDA_OK(h, cudaMemcpyAsync(y, a[0].data, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
       h->normal = {y, n, hyper[0], hyper[1], hyper[2]};
       h->n_reals = 2; h->n_samplers = 2; rows = n;
+    } break;
+    case BLANGPT_FAM_LINREG: {
+      if (na != 2 || nh != 2 || a[0].dtype != BLANGPT_F64 || a[1].dtype != BLANGPT_F64) FAIL(h, BLANGPT_EINVAL, "linreg: expects x[f64 n*p], y[f64 n], hyper (v0, smax)");
+      const int n = (int)a[1].n_elem;
+      if (n <= 0 || a[0].n_elem % n != 0) FAIL(h, BLANGPT_EINVAL, "linreg: x size is not a multiple of n");
+      const int p = (int)(a[0].n_elem / n);
+      if (p + 1 > kMaxParams) FAIL(h, BLANGPT_EUNSUPPORTED, "linreg: at most %d coefficients", kMaxParams - 1);
+      const int npad = (n + 1) & ~1;
+      double *xr, *xt, *yd, *res; uint8_t* ones;
+      if ((rc = dev_alloc(h, &xr, (size_t)n * p, false))) return rc;
+      if ((rc = dev_alloc(h, &xt, (size_t)npad * p))) return rc;
+      if ((rc = dev_alloc(h, &yd, npad))) return rc;
+      if ((rc = dev_alloc(h, &ones, npad, false))) return rc;
+      const int64_t local = h->M_total / c.worldSize;
+      if ((rc = dev_alloc(h, &res, (size_t)npad * local))) return rc;
+      CUDA_OK(h, cudaMemcpyAsync(xr, a[0].data, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(h, cudaMemcpyAsync(yd, a[1].data, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(h, cudaMemsetAsync(ones, 1, npad, h->stream));        // no sign folding: every row keeps its sign
+      dim3 grid((n + 31) / 32, (p + 31) / 32), block(32, 8);
+      transpose_kernel<<<grid, block, 0, h->stream>>>(xr, ones, xt, n, p, npad);
+      CUDA_OK(h, cudaGetLastError());
+      CUDA_OK(h, cudaStreamSynchronize(h->stream));
+      CUDA_OK(h, cudaFree(xr)); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), (void*)xr));
+      CUDA_OK(h, cudaFree(ones)); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), (void*)ones));
+      h->linreg = {xt, yd, res, n, npad, p, hyper[0], hyper[1]};
+      h->n_reals = p + 1; h->n_samplers = p + 1; rows = n;
     } break;
     case BLANGPT_FAM_HIERARCHICAL: {
       if (na != 2 || nh != 2 || a[0].dtype != BLANGPT_I32 || a[1].dtype != BLANGPT_I32 || a[0].n_elem != a[1].n_elem)
@@ -671,17 +699,18 @@ static int scm_initialize(blangpt_handle* h) {
   c->cfg.random = h->cfg.random ^ 0x53434D2D696E6974ULL;   // its own Philox key ("SCM-init")
   c->M_total = P; c->family = h->family; c->stream = h->stream; c->logistic_threads = h->logistic_threads;
   c->n_reals = h->n_reals; c->n_ints = h->n_ints; c->n_samplers = h->n_samplers;
-  c->normal = h->normal; c->iid = h->iid; c->hier = h->hier; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising;
+  c->normal = h->normal; c->iid = h->iid; c->hier = h->hier; c->linreg = h->linreg; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising;
   c->betabin.chains_per_replica = P;
   auto fail = [&](int code) { for (void* p : c->allocs) cudaFree(p); if (code) h->error = c->error; delete c; return code; };
   if (h->family == BLANGPT_FAM_LOGISTIC && (rc = dev_alloc(c, &c->logistic.eta, (size_t)c->logistic.npad * P))) return fail(rc);
+  if (h->family == BLANGPT_FAM_LINREG && (rc = dev_alloc(c, &c->linreg.res, (size_t)c->linreg.npad * P))) return fail(rc);
   if (h->family == BLANGPT_FAM_ISING && (rc = dev_alloc(c, &c->ising.spins, (size_t)P * h->n_ints))) return fail(rc);
   if (h->family == BLANGPT_FAM_MIXTURE) {
     const size_t sz = (size_t)c->mixture.npad * P;
     if ((rc = dev_alloc(c, &c->mixture.rest, sz, false)) || (rc = dev_alloc(c, &c->mixture.e1, sz, false)) ||
         (rc = dev_alloc(c, &c->mixture.e2, sz, false))) return fail(rc);
   }
-  int64_t rows = h->family == BLANGPT_FAM_NORMAL ? h->normal.n : h->family == BLANGPT_FAM_IID ? h->iid.n : h->family == BLANGPT_FAM_LOGISTIC ? h->logistic.n
+  int64_t rows = h->family == BLANGPT_FAM_NORMAL ? h->normal.n : h->family == BLANGPT_FAM_LINREG ? h->linreg.n : h->family == BLANGPT_FAM_IID ? h->iid.n : h->family == BLANGPT_FAM_LOGISTIC ? h->logistic.n
                : h->family == BLANGPT_FAM_MIXTURE ? h->mixture.n : 1;
   c->G = h->family == BLANGPT_FAM_ISING || h->family == BLANGPT_FAM_BETABINOMIAL ? 1 : pick_ctas_per_chain(c, rows);
   if ((rc = alloc_engine(c))) return fail(rc);

@@ -731,6 +731,111 @@ struct IidFam {
 };
 
 // ===========================================================================
+// Family 8: F/LinRegression.bl generalised to p covariates.  P = [w_0 .. w_{p-1}, sigma]
+//   w_j ~ Normal(0, v0), sigma ~ ContinuousUniform(0, smax), y_i ~ Normal(sum_j w_j x_ij, sigma * sigma)
+// Same layout as the logistic family: column-major X and a per-chain cache in HBM, here of the residuals
+// res_i = mean_i - y_i ("mean - x" of Normal.bl:21-24), so a move of w_k streams one column and the cache.
+// ===========================================================================
+struct LinRegFam {
+  struct Data {
+    const double* xt;      // [p][npad] column-major design matrix
+    const double* y;       // [npad]
+    double* res;           // [localSlots][npad]
+    int n, npad, p;
+    double v0, smax;
+  };
+  static constexpr int kThreads = 512;
+  static constexpr bool kWarpCapable = false;
+  Data d; double* P; double* res; RowRange rr; int* err;
+
+  BPT_D static int n_reals(const Data& d) { return d.p + 1; }
+  BPT_D static int n_samplers(const Data& d) { return d.p + 1; }
+  BPT_D void init(const Data& d_, int local_slot, double* P_, int G, int crank, int* err_) {
+    d = d_; P = P_; res = d.res + (size_t)local_slot * d.npad; rr = group_rows(d.n, G, crank); err = err_;
+  }
+  BPT_D int sampler_type(int) const { return S_REAL_SLICE; }
+  BPT_D int sampler_var(int k) const { return k; }
+  BPT_D int simplex_dim() const { return 0; }
+  BPT_D void begin_execution() {}
+  BPT_D static void tables_init() {}
+  BPT_D double fixed(int k, double x, int) const {
+    if (k < d.p) return normal_f2(0.0, d.v0, x);
+    return (0.0 <= x && x <= d.smax) ? 0.0 : BPT_NEG_INF;         // ContinuousUniform.bl:16-19
+  }
+  // this CTA's share of sum_i (res_i + delta * X[i][k])^2
+  BPT_D double sum_sq(int k, double delta) const {
+    const double* col = d.xt + (size_t)k * d.npad;
+    double s = 0.0;
+    for (int i = rr.lo + 2 * threadIdx.x; i < rr.hi; i += 2 * blockDim.x) {
+      if (i + 1 < rr.hi) {
+        const double2 r = *reinterpret_cast<const double2*>(res + i);
+        const double2 xv = *reinterpret_cast<const double2*>(col + i);
+        const double a = fma(delta, xv.x, r.x), b = fma(delta, xv.y, r.y);
+        s = fma(a, a, s); s = fma(b, b, s);
+      } else { const double a = fma(delta, col[i], res[i]); s = fma(a, a, s); }
+    }
+    return s;
+  }
+  // w_k: the n third blocks of Normal.bl; sigma: the n second and the n third blocks (Normal.bl:17-24)
+  BPT_D void annealed(int k, double x, int, GroupReducer& red, double& s, int& c) const {
+    const double sigma = k == d.p ? x : P[d.p], v = sigma * sigma;
+    if (v <= 0.0) { s = 0.0; c = (k == d.p ? 2 : 1) * d.n; return; }
+    double q = k < d.p ? sum_sq(k, x - P[k]) : sum_sq(0, 0.0); int z = 0;
+    red.reduce(q, z);
+    s = -0.5 * q / v;
+    if (k == d.p) s += d.n * (-0.5 * log(v));
+    c = 0;
+  }
+  BPT_D void commit(int k, double x, int) {
+    if (k < d.p) {
+      const double delta = x - P[k];
+      const double* col = d.xt + (size_t)k * d.npad;
+      if (delta != 0.0)
+        for (int i = rr.lo + 2 * threadIdx.x; i < rr.hi; i += 2 * blockDim.x) {
+          if (i + 1 < rr.hi) {
+            double2 r = *reinterpret_cast<const double2*>(res + i);
+            const double2 xv = *reinterpret_cast<const double2*>(col + i);
+            r.x = fma(delta, xv.x, r.x); r.y = fma(delta, xv.y, r.y);
+            *reinterpret_cast<double2*>(res + i) = r;
+          } else res[i] = fma(delta, col[i], res[i]);
+        }
+    }
+    __syncthreads();   // every thread has read P[k] for its delta before anyone overwrites it
+    P[k] = x;
+  }
+  // rebuild the residuals from scratch: sum_j w_j * X[i][j], j ascending from 0.0, minus y_i
+  BPT_D void refresh() {
+    for (int i = rr.lo + threadIdx.x; i < rr.hi; i += blockDim.x) {
+      double m = 0.0;
+      for (int j = 0; j < d.p; j++) m = fma(P[j], d.xt[(size_t)j * d.npad + i], m);
+      res[i] = m - d.y[i];
+    }
+    __syncthreads();   // sum_sq reads pairs written by other threads
+  }
+  BPT_D void full(GroupReducer& red, double& loglik, int& noos, double& logprior) {
+    refresh();
+    const double sigma = P[d.p], v = sigma * sigma;
+    loglik = d.n * (-0.5 * BPT_LOG_2PI);
+    if (v <= 0.0) noos = 2 * d.n;
+    else {
+      double q = sum_sq(0, 0.0); int z = 0;
+      red.reduce(q, z);
+      loglik += d.n * (-0.5 * log(v)) + (-0.5 * q / v);
+      noos = 0;
+    }
+    double lp = 0.0;
+    const double f01 = -0.5 * BPT_LOG_2PI + (d.v0 <= 0.0 ? BPT_NEG_INF : -0.5 * log(d.v0));
+    for (int j = 0; j < d.p; j++) lp += f01 + normal_f2(0.0, d.v0, P[j]);
+    lp += (d.smax <= 0.0 ? BPT_NEG_INF : -log(d.smax)) + fixed(d.p, sigma, 0);
+    logprior = lp;
+  }
+  BPT_D void forward(Rng& rng) {
+    for (int j = 0; j < d.p; j++) { const double w = gen_normal(rng, 0.0, d.v0); P[j] = w; }
+    const double s = gen_uniform(rng, 0.0, d.smax); P[d.p] = s;
+  }
+};
+
+// ===========================================================================
 // Family 7: F/HierarchicalModel.bl, not marginalised (the rocket-launch example of the Blang documentation)
 //   a ~ Exponential(rate_a), b ~ Exponential(rate_b), p_g | a, b ~ Beta(a, b), y_g | p_g ~ Binomial(n_g, p_g)
 // P = [a, b, p_0 .. p_{G-1}], one real slice sampler each.  The Beta blocks are fixed factors (p_g is latent); only

@@ -143,3 +143,13 @@ def hierarchical_rockets(groups=12, seed=20240007):
     p = rng.beta(1.2, 6.0, groups)
     failures = rng.binomial(launches, p).astype(np.int32)
     return dict(family="hierarchical", hyper=dict(rate_a=1.0, rate_b=1.0), y=failures, ntrials=launches)
+
+
+def linear_regression(n=5000, p=3, seed=20240008):
+    """Family "linreg": F/LinRegression.bl with p covariates (last column == 1, the intercept)."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, p))
+    x[:, p - 1] = 1.0
+    w = rng.normal(0.0, 2.0, p)
+    y = x @ w + 0.7 * rng.standard_normal(n)
+    return dict(family="linreg", hyper=dict(v0=25.0, smax=10.0), x=x, y=y, truth=list(w) + [0.7])

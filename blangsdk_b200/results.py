@@ -29,6 +29,7 @@ VARIABLES = {
     "mixture": [("means", "index_0", 0, "K"), ("variances", "index_0", "K", "K"), ("pi", "entry", "2K", "K")],
     "betabinomial": [("alpha", None, 0, 1), ("beta", None, 1, 1)],
     "ising": [("vertices", "index_0", 0, None)],
+    "linreg": [("coefficients", "index_0", 0, "P"), ("sigma", None, "P", 1)],
     "hierarchical": [("a", None, 0, 1), ("b", None, 1, 1), ("failureProbabilities", "rocketType", 2, None)],
 }
 # family "iid": the latent parameters of each observation law, named as in R/distributions/<Name>.bl
@@ -136,6 +137,8 @@ class PTResultsWriter:
         if v is None:
             return n_reals
         if isinstance(v, str):
+            if v == "P":                      # linreg: the coefficients come first, sigma last
+                return n_reals - 1
             return {"K": self.K, "2K": 2 * self.K}[v]
         return v
 

@@ -49,9 +49,12 @@ enum {
   BLANGPT_FAM_BETABINOMIAL = 5, /* data: y[R*n] i32, ntrials[R*n] i32. hyper: rate       */
   BLANGPT_FAM_IID = 6,          /* y_i ~ Dist(theta) i.i.d., theta_j ~ prior_j.  data: y[n] f64 (+ trials[n] f64 for
                                    BINOMIAL).  hyper: dist, then (prior kind, a, b) for each parameter            */
-  BLANGPT_FAM_HIERARCHICAL = 7  /* F/HierarchicalModel.bl, not marginalised: a, b ~ Exponential; p_g ~ Beta(a, b);
+  BLANGPT_FAM_HIERARCHICAL = 7, /* F/HierarchicalModel.bl, not marginalised: a, b ~ Exponential; p_g ~ Beta(a, b);
                                    failures_g ~ Binomial(launches_g, p_g).  data: failures[G] i32, launches[G] i32.
                                    hyper: rate_a, rate_b.  reals = a, b, p_0 .. p_{G-1}                            */
+  BLANGPT_FAM_LINREG = 8        /* F/LinRegression.bl with p covariates: w_j ~ Normal(0, v0), sigma ~ Uniform(0, smax),
+                                   y_i ~ Normal(x_i . w, sigma^2).  data: x[n*p] f64 row-major, y[n] f64.
+                                   hyper: v0, smax.  reals = w_0 .. w_{p-1}, sigma                                 */
 };
 /* family 6: observation laws (R/distributions/<Name>.bl) and their latent parameters, in this order */
 enum {

@@ -211,6 +211,7 @@ enum {
   F_BERN_NODE,        /* F/Ising.bl:27-29 -> Bernoulli.bl -> Categorical.bl; spin i0, p=c0 */
   F_BETABINOM,        /* BetaBinomial.bl:17-30 group i0, alpha = real i1, beta = real i2 */
   F_IID_LAW,          /* family 6: law i1 of the observation distribution, observation i0 (iid_law below) */
+  F_LINREG_F1, F_LINREG_F2,   /* family 8: Normal.bl:17-24 with mean = sum_j w_j x[i0][j], variance = sigma * sigma */
   F_HBETA,            /* family 7: block i2 of Beta.bl:14-41 with LATENT alpha = real 0, beta = real 1, realization = real i0 */
   F_HBINOM,           /* family 7: block i1 of Binomial.bl:14-27, group i0, p = real 2 + i0 */
   F_BETA_A, F_BETA_B,                      /* Beta.bl:14-27 prior on real i0, alpha = c0, beta = c1  */
@@ -460,6 +461,19 @@ static double factor_eval(const orc_model* m, const Factor* f, const double* re,
       return log(s == 1 ? prob : 1.0 - prob);
     }
     case F_IID_LAW: return iid_law(m->K, f->i1, re, m->y[f->i0], m->x[f->i0]);
+    case F_LINREG_F1: {
+      double sigma = re[m->p], variance = sigma * sigma;
+      if (variance <= 0.0) return NEG_INF;
+      return -0.5 * log(variance);
+    }
+    case F_LINREG_F2: {
+      const double* row = m->x + (size_t)f->i0 * m->p;
+      double mean = 0.0;
+      for (int j = 0; j < m->p; j++) mean += re[j] * row[j];
+      double sigma = re[m->p], variance = sigma * sigma;
+      if (variance <= 0.0) return NEG_INF;
+      return -0.5 * pow(mean - m->y[f->i0], 2) / variance;
+    }
     case F_HBETA: {
       double alpha = re[0], beta = re[1], x = re[f->i0];
       switch (f->i2) {
@@ -628,6 +642,27 @@ orc_model* orc_model_iid(int dist, const double* y, const double* trials, int n,
       int fi = b_factor(&b, F_IID_LAW, 1, i, l, 0, 0, 0);
       for (int j = 0; j < P; j++) if (IID_MASK[dist][l] & (1 << j)) b_connect(&b, j, fi);
     }
+  return b_end(&b);
+}
+
+/* family 8: F/LinRegression.bl generalised to p covariates:
+ *   w_j ~ Normal(0, v0), sigma ~ ContinuousUniform(0, smax), y_i | w, sigma ~ Normal(sum_j w_j x_ij, sigma * sigma).
+ * (the fixture is p = 2 with columns (x_i, 1): beta * x_i + alpha.)  reals = [w_0..w_{p-1}, sigma]. */
+orc_model* orc_model_linreg(const double* x, const double* y, int n, int p, double v0, double smax) {
+  Builder b = b_begin(ORC_FAM_LINREG, p + 1, 0, p + 1);
+  orc_model* m = b.m;
+  m->n_obs = n; m->p = p;
+  m->x = (double*)malloc(sizeof(double) * (size_t)n * p + 8); memcpy(m->x, x, sizeof(double) * (size_t)n * p);
+  m->y = (double*)malloc(sizeof(double) * (n > 0 ? n : 1)); memcpy(m->y, y, sizeof(double) * n);
+  for (int j = 0; j <= p; j++) { m->samplers[j].type = S_REAL_SLICE; m->samplers[j].var = j; }
+  for (int j = 0; j < p; j++) b_normal_prior(&b, j, j, 0.0, v0);
+  b_uniform_prior(&b, p, p, 0.0, smax);
+  for (int i = 0; i < n; i++) {
+    b_factor(&b, F_CONST, 1, 0, 0, 0, -0.5 * log(2.0 * M_PI), 0);
+    b_connect(&b, p, b_factor(&b, F_LINREG_F1, 1, i, 0, 0, 0, 0));
+    int f2 = b_factor(&b, F_LINREG_F2, 1, i, 0, 0, 0, 0);
+    for (int j = 0; j <= p; j++) b_connect(&b, j, f2);
+  }
   return b_end(&b);
 }
 

@@ -40,7 +40,8 @@ enum {
   ORC_FAM_ISING = 4,        /* C4: F/Ising.bl                                                      */
   ORC_FAM_BETABINOMIAL = 5, /* C5: a,b ~ Exponential(rate), y_g ~ BetaBinomial(n_g,a,b)            */
   ORC_FAM_IID = 6,          /* y_i ~ Dist(theta) i.i.d., theta_j ~ prior_j          */
-  ORC_FAM_HIERARCHICAL = 7  /* F/HierarchicalModel.bl: a,b ~ Exp; p_g ~ Beta(a,b); y_g ~ Binomial(n_g,p_g) */
+  ORC_FAM_HIERARCHICAL = 7, /* F/HierarchicalModel.bl: a,b ~ Exp; p_g ~ Beta(a,b); y_g ~ Binomial(n_g,p_g) */
+  ORC_FAM_LINREG = 8        /* F/LinRegression.bl: w_j ~ Normal(0,v0), sigma ~ U(0,smax), y_i ~ Normal(x_i.w, sigma^2) */
 };
 /* observation laws of family 6 and their parameters (reals, in this order) */
 enum {
@@ -86,6 +87,8 @@ orc_model* orc_model_mixture(const double* y, int n, int K, double m0, double v0
                              double gshape, double grate, double conc);
 orc_model* orc_model_ising(int N, double coupling, double moment);
 orc_model* orc_model_betabinomial(const int32_t* y, const int32_t* ntrials, int n, double rate);
+/* family 8: reals = [w_0..w_{p-1}, sigma] */
+orc_model* orc_model_linreg(const double* x_rowmajor, const double* y, int n, int p, double v0, double smax);
 /* family 7: reals = [a, b, p_0..p_{G-1}] */
 orc_model* orc_model_hierarchical(const int32_t* failures, const int32_t* launches, int G, double rate_a, double rate_b);
 /* family 6; trials may be NULL unless dist == ORC_IID_BINOMIAL; one (kind, a, b) per parameter */

@@ -75,6 +75,8 @@ def lib():
     L.orc_model_ising.argtypes = [C.c_int, C.c_double, C.c_double]
     L.orc_model_betabinomial.restype = vp
     L.orc_model_betabinomial.argtypes = [_ip, _ip, C.c_int, C.c_double]
+    L.orc_model_linreg.restype = vp
+    L.orc_model_linreg.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_double, C.c_double]
     L.orc_model_hierarchical.restype = vp
     L.orc_model_hierarchical.argtypes = [_ip, _ip, C.c_int, C.c_double, C.c_double]
     L.orc_model_iid.restype = vp
@@ -190,6 +192,10 @@ class Model:
             y = np.ascontiguousarray(spec["y"], dtype=np.int32)
             nt = np.ascontiguousarray(spec["ntrials"], dtype=np.int32)
             self.h = L.orc_model_betabinomial(_i(y), _i(nt), len(y), h["rate"])
+        elif fam == "linreg":
+            x = np.ascontiguousarray(spec["x"], dtype=np.float64)
+            y = np.ascontiguousarray(spec["y"], dtype=np.float64)
+            self.h = L.orc_model_linreg(_d(x), _d(y), x.shape[0], x.shape[1], h["v0"], h["smax"])
         elif fam == "hierarchical":
             y = np.ascontiguousarray(spec["y"], dtype=np.int32)
             nt = np.ascontiguousarray(spec["ntrials"], dtype=np.int32)

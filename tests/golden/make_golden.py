@@ -46,6 +46,7 @@ def main():
     for dist in more:
         specs["iid_" + dist] = D.iid_observations(dist, 45)
     specs["hierarchical"] = D.hierarchical_rockets(6)
+    specs["linreg"] = D.linear_regression(50, 3)
     rng = np.random.default_rng(20240600)
     cases = []
     for name, spec in specs.items():
@@ -60,6 +61,8 @@ def main():
                 it = None
             elif name == "logistic":
                 re, it = rng.normal(0, 1.5, m.n_reals).tolist(), None
+            elif name == "linreg":
+                re, it = rng.normal(0, 2.0, m.n_reals - 1).tolist() + [float(rng.uniform(0.1, 5.0))], None
             elif name == "hierarchical":
                 re, it = rng.gamma(2.0, 1.0, 2).tolist() + rng.uniform(0.02, 0.98, m.n_reals - 2).tolist(), None
             elif name.startswith("iid_") and name[4:] in iid_state:

@@ -20,6 +20,8 @@ def _spec(c):
     for k in ("y", "x", "ntrials", "trials"):
         if k in s:
             s[k] = np.array(s[k])
+    if s["family"] == "linreg":
+        s["y"] = s["y"].astype(np.float64)
     if s["family"] == "iid":
         s["hyper"] = dict(s["hyper"], priors=[tuple(p) for p in s["hyper"]["priors"]])
         s.setdefault("trials", None)

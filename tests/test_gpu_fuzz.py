@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _case(D, rng):
-    fam = ["normal", "logistic", "mixture", "betabinomial", "ising", "iid", "hierarchical"][rng.integers(0, 7)]
+    fam = ["normal", "logistic", "mixture", "betabinomial", "ising", "iid", "hierarchical", "linreg"][rng.integers(0, 8)]
     if fam == "normal":
         spec = D.normal_meanvar(n=int(rng.integers(1, 3000)), seed=int(rng.integers(1, 1 << 30)))
     elif fam == "logistic":
@@ -20,6 +20,8 @@ def _case(D, rng):
         spec = D.gaussian_mixture(int(rng.integers(1, 4000)), seed=int(rng.integers(1, 1 << 30)))
     elif fam == "betabinomial":
         spec = D.beta_binomial(int(rng.integers(0, 1000)), groups=int(rng.integers(1, 70)), trials=int(rng.integers(1, 80)))
+    elif fam == "linreg":
+        spec = D.linear_regression(int(rng.integers(1, 5000)), int(rng.integers(1, 9)), seed=int(rng.integers(1, 1 << 30)))
     elif fam == "hierarchical":
         spec = D.hierarchical_rockets(int(rng.integers(1, 63)), seed=int(rng.integers(1, 1 << 30)))
     elif fam == "iid":
@@ -36,15 +38,21 @@ def _case(D, rng):
     return fam, spec, int(rng.integers(1, 14)), int(rng.integers(1, 1 << 20)), ctas, opts
 
 
-@pytest.mark.parametrize("case", range(70))
+@pytest.mark.parametrize("case", range(80))
 def test_random_configuration(oracle, datasets, case):
     rng = np.random.default_rng(9000 + case)
     fam, spec, n_chains, seed, ctas, opts = _case(datasets, rng)
     init = "FORWARD" if rng.integers(0, 3) else "COPIES"
-    if fam == "iid":      # start near the generating parameters (see test_gpu_iid.py::test_iid_trajectory_parity)
+    if fam in ("iid", "linreg"):      # start near the generating parameters (see test_gpu_iid.py::test_iid_trajectory_parity)
         init = "COPIES"
-    eng, ref = make_pair(oracle, spec, n_chains, seed=seed, init=init, ctas=ctas, **opts)
     if fam == "iid":
+        # With usePriorSamples = false the beta = 0 chain slice-samples the wide priors, where the exp/pow laws reach
+        # |log-likelihood| ~ 1e15; the reference's incrementally updated caches (SampledModel.java:365-395, recomputed
+        # only every 10 scans' worth of moves, :275-281) then carry ~0.1 of rounding drift in the reported energy,
+        # which the oracle reproduces and the engine (from-scratch evaluation every scan) does not.  DESIGN.md 11.
+        opts["usePriorSamples"] = True
+    eng, ref = make_pair(oracle, spec, n_chains, seed=seed, init=init, ctas=ctas, **opts)
+    if fam in ("iid", "linreg"):
         start_from(eng, ref, [[v * (1.0 + 0.1 * rng.normal()) for v in spec["truth"]] for _ in range(n_chains)])
     try:
         assert_trajectory_parity(eng, ref, int(rng.integers(2, 7)))

@@ -161,3 +161,14 @@ def test_eit_hierarchical(oracle):
         return rng.binomial(launches, th[2:]).astype(np.int32)
     spec = lambda y: dict(family="hierarchical", hyper=dict(rate_a=1.0, rate_b=1.0), y=y, ntrials=launches)
     _eit(oracle, spec, prior, sim, 5, [lambda t: t[0], lambda t: t[1], lambda t: t[2], lambda t: t[0] / (t[0] + t[1])], 7)
+
+
+def test_eit_linreg(oracle):
+    """F/LinRegression.bl: slope, intercept and sigma"""
+    x = np.column_stack([np.linspace(-2.0, 2.0, 8), np.ones(8)])
+    def prior(rng):
+        return list(rng.normal(0.0, math.sqrt(4.0), 2)) + [rng.uniform(0.0, 3.0)]
+    def sim(rng, th):
+        return x @ np.array(th[:2]) + th[2] * rng.standard_normal(8)
+    spec = lambda y: dict(family="linreg", hyper=dict(v0=4.0, smax=3.0), x=x, y=y)
+    _eit(oracle, spec, prior, sim, 3, [lambda t: t[0], lambda t: t[1], lambda t: t[2], lambda t: t[0] * t[2]], 8)
