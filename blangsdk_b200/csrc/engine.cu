@@ -134,11 +134,17 @@ extern "C" int blangpt_ctas_per_chain(const blangpt_handle* h) { return h ? h->G
 // ---------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------
+// families may size the CTA from the data (launch_threads(D) <= kThreads, the kernel's launch bound)
+template <class Fam>
+static auto threads_for(const typename Fam::Data& D, int) -> decltype(Fam::launch_threads(D)) { return Fam::launch_threads(D); }
+template <class Fam>
+static int threads_for(const typename Fam::Data&, long) { return Fam::kThreads; }
+
 template <class Fam>
 static int launch_explore_t(blangpt_handle* h, const typename Fam::Data& D, int mode) {
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3((unsigned)(h->E.M_local * h->G));
-  lc.blockDim = dim3(Fam::kThreads);
+  lc.blockDim = dim3((unsigned)threads_for<Fam>(D, 0));
   lc.dynamicSmemBytes = 0;
   lc.stream = h->stream;
   cudaLaunchAttribute at[1];

@@ -638,7 +638,8 @@ struct IidFam {
     const double* y; const double* trials; int n, dist, n_params;
     int prior_kind[3]; double prior_a[3], prior_b[3];
   };
-  static constexpr int kThreads = 128;
+  static constexpr int kThreads = 512;          // launch bound; small data sets run 128 threads per CTA
+  static int launch_threads(const Data& d) { return d.n >= 32768 ? 512 : 128; }
   static constexpr bool kWarpCapable = true;
   Data d; double* P; RowRange rr; int* err;
   int t0, tn;   // this thread's index in the chain group and the group size

@@ -13,9 +13,12 @@ from blangsdk_b200 import datasets as D  # noqa: E402
 from blangsdk_b200.engine import Engine  # noqa: E402
 
 
-def run(name, spec, nChains, nReplicas=1, init="FORWARD", warm=3, scans=10, algo_bytes=None):
+def run(name, spec, nChains, nReplicas=1, init="FORWARD", warm=3, scans=10, algo_bytes=None, start=None):
     eng = Engine(nChains=nChains, nReplicas=nReplicas, random=1)
     eng.set_model(spec)
+    if start is not None:                 # every chain from the same well-conditioned point
+        for p in range(nChains):
+            eng.set_state(p, start, None)
     eng.initialize(init)
     eng.run_scans(warm, want=())
     c0 = eng.counters()
@@ -57,3 +60,13 @@ if __name__ == "__main__":
         run("C4 ising 256x256, 128 chains (1 of 8 GPUs)", D.ising(256), 128, scans=20, warm=3, algo_bytes=None)
     if "C5" in which:
         run("C5 beta-binomial 4096 replicas x 8 chains", D.beta_binomial_batch(4096), 8, nReplicas=4096, scans=50, warm=5, algo_bytes=256)
+    # the families added for SURVEY 8(f)-4 (not BASELINE configs): the same shapes as C2 / C3 / C5
+    if "C6" in which:
+        s = D.linear_regression(100_000, 32)
+        run("C6 linreg 100k x 32, 64 chains", s, 64, init="COPIES", scans=10, algo_bytes=100_000 * (32 * 8 + 8), start=s["truth"])
+    if "C7" in which:
+        s = D.iid_observations("studentt", 1_000_000)
+        run("C7 iid Student-t 1M obs, 64 chains", s, 64, init="COPIES", scans=5, warm=2, algo_bytes=8_000_000, start=s["truth"])
+    if "C8" in which:
+        run("C8 hierarchical rockets 12 groups, 4096 replicas x 8 chains", D.hierarchical_rockets(12), 8, nReplicas=4096,
+            scans=50, warm=5, algo_bytes=12 * 8)
