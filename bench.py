@@ -130,6 +130,12 @@ def cpu_sample(spec, budget_s, n_chains=None):
     return evals / dt, min(cores, n_chains), desc, dt
 
 
+def workload(n_chains):
+    """config.workload, the same string in both arms"""
+    return ("C2 Bayesian logistic regression 100000 x 32 (seed 20240002), %d chains (64 per GPU), nPassesPerScan 3, "
+            "COPIES init from w=0; step = one NRPT scan (explore + DEO swap)" % n_chains)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -148,8 +154,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2 logistic regression 100000 x 32, CPU restatement of the reference PT engine "
-                                   "(JVM not available); each step is a bounded sample of one scan"},
+            "config": {"workload": workload(CHAINS_PER_GPU * max(1, args.gpus)),
+                       "reference": "CPU restatement of the reference PT engine (oracle/, no JVM in the image), all host "
+                                    "threads; each step is a bounded sample of one scan of this workload, see cpu_baseline.sample"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -297,9 +304,7 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "C2 Bayesian logistic regression 100000 x 32 (seed 20240002), %d chains "
-                                       "(64 per GPU), nPassesPerScan 3, COPIES init from w=0; step = one NRPT scan "
-                                       "(explore + DEO swap)" % n_chains,
+                "config": {"workload": workload(n_chains),
                            "l2": "flushed between timed steps (256 MiB write)", "ctas_per_chain": eng.ctas_per_chain,
                            "parallelism": "chain-sharded x%d" % world},
                 "scans_per_s": 1e3 * args.steps / ms_total, "evals": evals, "wall_s_timed_region": wall,
