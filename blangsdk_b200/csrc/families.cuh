@@ -57,20 +57,7 @@ BPT_D void acc_term(double t, double& s, int& c, int* err) {
 // sg < -12 (or |sg| >= 700, or NaN) -- rare, and the only place where the reference's own
 // rounding and its -inf convention are visible -- the naive arithmetic is executed literally.
 // Coefficients live in constant memory so each one is a direct DFMA operand.
-__constant__ double kExpC[12] = {   // Taylor 1/11! .. 1/0!: |r| <= ln2/2 -> relative error < 7e-15
-    2.50521083854417187751e-08, 2.75573192239858906526e-07,
-    2.75573192239858906526e-06, 2.48015873015873015873e-05, 1.98412698412698412698e-04,
-    1.38888888888888888889e-03, 8.33333333333333333333e-03, 4.16666666666666666667e-02,
-    1.66666666666666666667e-01, 0.5, 1.0, 1.0};
-__constant__ double kAtanhC[8] = {  // 1/17 .. 1/3: |f| <= 0.1716 -> absolute error < 3e-16
-    5.88235294117647058824e-02, 6.66666666666666666667e-02,
-    7.69230769230769230769e-02, 9.09090909090909090909e-02, 1.11111111111111111111e-01,
-    1.42857142857142857143e-01, 2.00000000000000000000e-01, 3.33333333333333333333e-01};
-// {-log2(e), 1.5*2^52, -ln2_hi, -ln2_lo, 1 - C, 1 + C, log(C)} with C = fl(sqrt 2)
-__constant__ double kLogitK[7] = {
-    -1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
-    -0.41421356237309514547, 2.41421356237309514547, 0.34657359027997269783};
-
+//
 // Tables for the logistic row term (tools/gen_logit_tables.py writes them, 60-digit arithmetic, rounded once).
 // exp(-a) = 2^k * 2^(j/64) * exp(r): m = round(-a * 64 log2 e) = 64 k + j, r = -a - m ln2/64, |r| <= ln2/128, so a
 // degree-5 polynomial is exact to 4e-17.  log(u) for u in (1, 2]: u = c_j (1 + rr) with c_j the centre of the
@@ -318,41 +305,10 @@ BPT_D void logit_pair(double za, double zb, const uint8_t* yp, double& s, int& c
 }
 
 // ---------------------------------------------------------------------------
-// lean fp64 exp / log for the mixture kernel (operand ranges known, see MixtureFam::obs_fast)
+// table-driven fp64 exp / log for the mixture kernel (operand ranges known, see MixtureFam::obs_term)
 // ---------------------------------------------------------------------------
-BPT_D double exp_lean(double x) {   // exp(x) for -700 <= x <= 700 (caller clamps)
-  double kd = fma(x, -kLogitK[0], kLogitK[1]);
-  const int k = __double2loint(kd);
-  kd -= kLogitK[1];
-  double r = fma(kd, kLogitK[2], x);
-  r = fma(kd, kLogitK[3], r);
-  double p = kExpC[0];
-#pragma unroll
-  for (int i = 1; i < 12; i++) p = fma(p, r, kExpC[i]);
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-}
-BPT_D double log_lean(double a) {   // log(a) for normal positive a
-  const int hi = __double2hiint(a);
-  int mh = (hi & 0x000fffff) | 0x3ff00000;          // mantissa in [1, 2)
-  const int adj = mh >= 0x3ff6a09f ? 1 : 0;          // above sqrt(2): halve
-  mh -= adj << 20;
-  const int e = (hi >> 20) - 1023 + adj;
-  const double m = __hiloint2double(mh, __double2loint(a));   // [0.7071, 1.4142)
-  const double num = m - 1.0, den = m + 1.0;
-  double rc;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(den));
-  double t = fma(-den, rc, 1.0); rc = fma(rc, t, rc);
-  t = fma(-den, rc, 1.0); rc = fma(rc, t, rc);
-  const double f = num * rc, f2 = f * f;
-  double q = kAtanhC[0];
-#pragma unroll
-  for (int i = 1; i < 8; i++) q = fma(q, f2, kAtanhC[i]);
-  const double s1 = f + f;
-  return fma((double)e, 6.93147180559945309417e-01, fma(s1 * f2, q, s1));
-}
-
-// Table-driven versions (the logistic kernel's tables, logit_table_init()): exp in 10 and log in 10 fp64
-// instructions instead of 17 and 25.  `tab` = logit_table_address().
+// The logistic kernel's tables (logit_table_init()): exp in 10 and log in 10 fp64 instructions (a degree-11
+// polynomial exp and a reciprocal + atanh-series log took 17 and 25).  `tab` = logit_table_address().
 BPT_D double exp_tab(double x, uint32_t tab) {   // exp(x) for -700 <= x <= 700 (caller clamps)
   double kd = fma(x, -kLgtK[0], kLgtK[1]);       // low word = m = round(x * 64 log2 e) = 64 k + j
   const int m = __double2loint(kd);
@@ -379,33 +335,6 @@ BPT_D double log_tab(double a, uint32_t tab) {   // log(a) for normal positive a
   for (int i = 1; i < 4; i++) q = fma(q, rr, kLgtLogC[i]);
   const double lm = fma(rr * rr, q, rr) + cj.y;
   return fma((double)e, 6.93147180559945309417e-01, lm);
-}
-
-// lean branch-free lnGamma for the beta-binomial kernel: shift by 8 and use Stirling's series at z = x + 8 >= 8
-//   lnGamma(x) = (z - 1/2) log z - z + log(2 pi)/2 + sum_j B_2j / (2j (2j-1) z^(2j-1)) - log( x (x+1) ... (x+7) )
-// (series truncated after z^-13: error < 1e-15).  All lanes execute the same instructions whatever their
-// argument, unlike the library lgamma whose range branches serialise inside a warp.  Valid for 1e-30 < x < 1e15;
-// outside, the library function is used.
-BPT_D double lgamma_lean(double x) {
-  if (!(x > 1e-30 && x < 1e15)) return lgamma(x);
-  double p = x;
-#pragma unroll
-  for (int j = 1; j < 8; j++) p *= x + (double)j;
-  const double z = x + 8.0;
-  double rz;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rz) : "d"(z));
-  double t = fma(-z, rz, 1.0); rz = fma(rz, t, rz);
-  t = fma(-z, rz, 1.0); rz = fma(rz, t, rz);
-  const double r2 = rz * rz;
-  double s = 6.41025641025641025641e-03;            //  1/156
-  s = fma(s, r2, -1.91752691752691752692e-03);      // -691/360360
-  s = fma(s, r2, 8.41750841750841750842e-04);       //  1/1188
-  s = fma(s, r2, -5.95238095238095238095e-04);      // -1/1680
-  s = fma(s, r2, 7.93650793650793650794e-04);       //  1/1260
-  s = fma(s, r2, -2.77777777777777777778e-03);      // -1/360
-  s = fma(s, r2, 8.33333333333333333333e-02);       //  1/12
-  const double body = fma(z - 0.5, log_lean(z), -z) + 9.18938533204672741780e-01;
-  return fma(s, rz, body) - log_lean(p);
 }
 
 // Normal.bl:21-24 with constant mean/variance (a prior on x)
@@ -1415,13 +1344,10 @@ struct BetaBinomialFam {
       for (int g = rr.lo + t0; g < rr.hi; g += tn) c++;
       return;
     }
-#ifndef BPT_LGAMMA
-#define BPT_LGAMMA lgamma
-#endif
-    const double ab = BPT_LGAMMA(a + b) - BPT_LGAMMA(a) - BPT_LGAMMA(b);
+    const double ab = lgamma(a + b) - lgamma(a) - lgamma(b);
     for (int g = rr.lo + t0; g < rr.hi; g += tn) {
       const double yy = (double)y[g], n = (double)nt[g];
-      const double t = cst[g] + BPT_LGAMMA(yy + a) + BPT_LGAMMA(n - yy + b) + ab - BPT_LGAMMA(n + a + b);
+      const double t = cst[g] + lgamma(yy + a) + lgamma(n - yy + b) + ab - lgamma(n + a + b);
       acc_term(t, s, c, err);
     }
   }
