@@ -21,7 +21,7 @@ namespace bpt {
 
 enum Purpose : uint32_t { P_MOVE = 0, P_SHUFFLE = 1, P_SWAP = 2, P_SWAPDIR = 3, P_FORWARD = 4, P_INIT = 5 };
 
-enum ErrBits : int { ERR_NAN = 1, ERR_SLICE_DIVERGED = 2 };
+enum ErrBits : int { ERR_NAN = 1, ERR_SLICE_DIVERGED = 2, ERR_INT_SLICE_EMPTY = 4 };
 
 BPT_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                           uint32_t out[4]) {
@@ -113,6 +113,16 @@ BPT_HD double gen_gamma(Rng& r, double shape, double rate) {
   }
   if (result == 0.0) result = 1e-300;   // ZERO_PLUS_EPS :322
   return result;
+}
+// :299-309 -> commons-math3 PoissonDistribution.sample() for mean < 40: multiply uniforms until below exp(-mean)
+BPT_HD int gen_poisson_small(Rng& r, double mean) {
+  const double p = exp(-mean);
+  long n = 0; double prod = 1.0;
+  while (n < 1000 * mean) {
+    prod *= r.next_double();
+    if (prod >= p) n++; else return (int)n;
+  }
+  return (int)n;
 }
 // :143-152.  commons-math3's BetaDistribution.sample() is Cheng's BB/BC rejection sampler; the draw stream is
 // unpinned against the JVM anyway, so this uses the two-gamma identity X / (X + Y) and keeps the end-point guards

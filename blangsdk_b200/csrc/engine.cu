@@ -44,6 +44,7 @@ struct blangpt_handle {
   IidFam::Data iid{};
   HierFam::Data hier{};
   LinRegFam::Data linreg{};
+  RocketsLatentFam::Data rockets{};
   LogisticFam::Data logistic{};
   MixtureFam<4>::Data mixture{};
   BetaBinomialFam::Data betabin{};
@@ -162,6 +163,7 @@ static int launch_explore(blangpt_handle* h, int mode) {
     case BLANGPT_FAM_IID: return launch_explore_t<IidFam>(h, h->iid, mode);
     case BLANGPT_FAM_HIERARCHICAL: return launch_explore_t<HierFam>(h, h->hier, mode);
     case BLANGPT_FAM_LINREG: return launch_explore_t<LinRegFam>(h, h->linreg, mode);
+    case BLANGPT_FAM_ROCKETS_LATENT: return launch_explore_t<RocketsLatentFam>(h, h->rockets, mode);
     case BLANGPT_FAM_LOGISTIC:
       if (h->logistic_threads == 1024) {
         LogisticFamT<1024>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
@@ -203,7 +205,7 @@ static bool use_fused(const blangpt_handle* h) {
   if (h->family == BLANGPT_FAM_BETABINOMIAL) return forced || h->cfg.nReplicas >= 8;
   if (h->family == BLANGPT_FAM_NORMAL) return h->normal.n <= 65536 && (forced || h->cfg.nReplicas >= 8);
   if (h->family == BLANGPT_FAM_IID) return h->iid.n <= 65536 && (forced || h->cfg.nReplicas >= 8);
-  if (h->family == BLANGPT_FAM_HIERARCHICAL) return forced || h->cfg.nReplicas >= 8;
+  if (h->family == BLANGPT_FAM_HIERARCHICAL || h->family == BLANGPT_FAM_ROCKETS_LATENT) return forced || h->cfg.nReplicas >= 8;
   return false;
 }
 
@@ -221,6 +223,8 @@ static int check_device_errors(blangpt_handle* h) {
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
   if (err & ERR_SLICE_DIVERGED)
     FAIL(h, BLANGPT_ENUMERIC, "Slice diverged to infinity. Possible cause is that a variable has no distribution attached to it, i.e. the model is improper.");
+  if (err & ERR_INT_SLICE_EMPTY)
+    FAIL(h, BLANGPT_ENUMERIC, "Invalid arguments: the integer slice sampler found no point of non-zero density in its window (the state it started from has zero density; Generators.discreteUniform throws in the reference). Initialise with SCM or from a feasible state.");
   if ((err & ERR_NAN) && !h->cfg.treatNaNAsNegativeInfinity)
     FAIL(h, BLANGPT_ENUMERIC, "Factors should not return NaN. Use NEGATIVE_INFINITY to forbid configurations. If you are sure this NaN is OK, you can use the option 'treatNaNAsNegativeInfinity'.");
   return 0;
@@ -370,6 +374,17 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
       CUDA_OK(h, cudaMemcpyAsync(y, a[0].data, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
       h->normal = {y, n, hyper[0], hyper[1], hyper[2]};
       h->n_reals = 2; h->n_samplers = 2; rows = n;
+    } break;
+    case BLANGPT_FAM_ROCKETS_LATENT: {
+      if (na != 1 || nh != 3 || a[0].dtype != BLANGPT_I32) FAIL(h, BLANGPT_EINVAL, "rockets_latent: expects failures[i32 G], hyper (rate_a, rate_b, pois_mean)");
+      const int G = (int)a[0].n_elem;
+      if (G < 1 || 2 * G + 2 > kMaxParams) FAIL(h, BLANGPT_EUNSUPPORTED, "rockets_latent: 1 <= groups <= %d", (kMaxParams - 2) / 2);
+      if (!(hyper[2] > 0.0 && hyper[2] < 40.0)) FAIL(h, BLANGPT_EUNSUPPORTED, "rockets_latent: 0 < pois_mean < 40");
+      int* y;
+      if ((rc = dev_alloc(h, &y, G))) return rc;
+      CUDA_OK(h, cudaMemcpyAsync(y, a[0].data, G * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      h->rockets = {y, G, hyper[0], hyper[1], hyper[2]};
+      h->n_reals = 2 * G + 2; h->n_samplers = 2 * G + 2; rows = 1;
     } break;
     case BLANGPT_FAM_LINREG: {
       if (na != 2 || nh != 2 || a[0].dtype != BLANGPT_F64 || a[1].dtype != BLANGPT_F64) FAIL(h, BLANGPT_EINVAL, "linreg: expects x[f64 n*p], y[f64 n], hyper (v0, smax)");
@@ -528,6 +543,7 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
   if (family == BLANGPT_FAM_NORMAL) { fill(0, 0.0); fill(1, 1.0); }
   if (family == BLANGPT_FAM_BETABINOMIAL) { fill(0, 1.0); fill(1, 1.0); }
   if (family == BLANGPT_FAM_HIERARCHICAL) { fill(0, 1.0); fill(1, 1.0); for (int g = 0; g < h->hier.G; g++) fill(2 + g, 0.5); }
+  if (family == BLANGPT_FAM_ROCKETS_LATENT) { fill(0, 1.0); fill(1, 1.0); for (int g = 0; g < h->rockets.G; g++) fill(2 + g, 0.5); }
   if (family == BLANGPT_FAM_MIXTURE) { const int K = h->mixture.K; for (int k = 0; k < K; k++) { fill(k, 0.0); fill(K + k, 1.0); fill(2 * K + k, 1.0 / K); } }
   if (h->n_reals) CUDA_OK(h, cudaMemcpyAsync(h->E.reals, init.data(), init.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
@@ -705,7 +721,7 @@ static int scm_initialize(blangpt_handle* h) {
   c->cfg.random = h->cfg.random ^ 0x53434D2D696E6974ULL;   // its own Philox key ("SCM-init")
   c->M_total = P; c->family = h->family; c->stream = h->stream; c->logistic_threads = h->logistic_threads;
   c->n_reals = h->n_reals; c->n_ints = h->n_ints; c->n_samplers = h->n_samplers;
-  c->normal = h->normal; c->iid = h->iid; c->hier = h->hier; c->linreg = h->linreg; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising;
+  c->normal = h->normal; c->iid = h->iid; c->hier = h->hier; c->linreg = h->linreg; c->rockets = h->rockets; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising;
   c->betabin.chains_per_replica = P;
   auto fail = [&](int code) { for (void* p : c->allocs) cudaFree(p); if (code) h->error = c->error; delete c; return code; };
   if (h->family == BLANGPT_FAM_LOGISTIC && (rc = dev_alloc(c, &c->logistic.eta, (size_t)c->logistic.npad * P))) return fail(rc);
@@ -901,6 +917,7 @@ extern "C" int blangpt_run_scans(blangpt_handle* h, int32_t n_scans, const blang
     if (h->family == BLANGPT_FAM_NORMAL) replica_kernel<NormalFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->normal, n_scans);
     else if (h->family == BLANGPT_FAM_IID) replica_kernel<IidFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->iid, n_scans);
     else if (h->family == BLANGPT_FAM_HIERARCHICAL) replica_kernel<HierFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->hier, n_scans);
+    else if (h->family == BLANGPT_FAM_ROCKETS_LATENT) replica_kernel<RocketsLatentFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->rockets, n_scans);
     else replica_kernel<BetaBinomialFam><<<R, threads, 0, h->stream>>>(h->E, h->St, O, h->betabin, n_scans);
     CUDA_OK(h, cudaGetLastError());
     h->n_launches++;

@@ -25,7 +25,7 @@ namespace bpt {
 constexpr int kMaxParams = 64;    // latent reals per chain held in shared memory
 constexpr int kMaxSamplers = 65;
 
-enum SamplerType : int { S_REAL_SLICE = 0, S_SIMPLEX = 1 };
+enum SamplerType : int { S_REAL_SLICE = 0, S_SIMPLEX = 1, S_INT_SLICE = 3 };
 
 // rows [lo, hi) of this CTA inside the chain group; lo is even
 struct RowRange { int lo, hi; };
@@ -851,6 +851,107 @@ struct HierFam {
     const double b = gen_exponential(rng, d.rate_b);
     P[0] = a; P[1] = b;
     for (int g = 0; g < d.G; g++) { const double p = gen_beta(rng, a, b); P[2 + g] = p; }
+  }
+};
+
+// ===========================================================================
+// Family 9: F/SimpleHierarchicalModel.bl -- family 7 with LATENT launch counts, updated by the integer slice
+// sampler with stepping out (IntSliceSampler.java:53-132):
+//   a, b ~ Exponential; p_g | a, b ~ Beta(a + 0.5, b + 0.5); L_g ~ Poisson(mean); failures_g ~ Binomial(1 + L_g, p_g)
+// P = [a, b, p_0 .. p_{G-1}, L_0 .. L_{G-1}]; the integers are held as exact doubles (G <= 31).
+// ===========================================================================
+struct RocketsLatentFam {
+  struct Data { const int* y; int G; double rate_a, rate_b, pois_mean; };
+  static constexpr int kThreads = 32;
+  static constexpr bool kWarpCapable = true;
+  static constexpr bool kHasIntSlice = true;
+  static constexpr int kFusedParams = kMaxParams;
+  Data d; double* P; int* err;
+  double sum_log_p, sum_log1m_p; bool p_inside;   // over the groups, refreshed when a sampler execution begins
+
+  BPT_D static int n_reals(const Data& d) { return 2 * d.G + 2; }
+  BPT_D static int n_samplers(const Data& d) { return 2 * d.G + 2; }
+  BPT_D void init(const Data& d_, int, double* P_, int, int, int* err_) {
+    d = d_; P = P_; err = err_; sum_log_p = 0.0; sum_log1m_p = 0.0; p_inside = false;   // set by begin_execution()
+  }
+  BPT_D void set_lanes(int, int) {}
+  BPT_D int sampler_type(int k) const { return k < d.G + 2 ? S_REAL_SLICE : S_INT_SLICE; }
+  BPT_D int sampler_var(int k) const { return k; }
+  BPT_D int simplex_dim() const { return 0; }
+  BPT_D static void tables_init() {}
+  BPT_D void begin_execution() {
+    double s1 = 0.0, s2 = 0.0; bool ok = true;
+    for (int g = 0; g < d.G; g++) {
+      const double p = P[2 + g];
+      if (p <= 0.0 || p >= 1.0) ok = false; else { s1 += log(p); s2 += log1p(-p); }
+    }
+    sum_log_p = s1; sum_log1m_p = s2; p_inside = ok;
+  }
+  BPT_D double poisson_block(int law, double L) const { const double th[1] = {d.pois_mean}; return iid_law(IID_POISSON, law, th, L, 0.0); }
+  BPT_D static double binomial_block(int law, double y, double n, double p) { const double th[1] = {p}; return iid_law(IID_BINOMIAL, law, th, y, n); }
+  BPT_D double fixed(int k, double x, int) const {
+    const int G = d.G;
+    if (k >= G + 2) return poisson_block(0, x) + poisson_block(2, x);        // Poisson.bl: the blocks that name the realization
+    const double a = (k == 0 ? x : P[0]), b = (k == 1 ? x : P[1]);
+    const double al = a + 0.5, be = b + 0.5;                                   // Beta(a + 0.5, b + 0.5)
+    if (k == 0) {
+      if (al <= 0.0 || be <= 0.0 || !p_inside) return BPT_NEG_INF;
+      return gamma_ab(1.0, d.rate_a, a) + (al - 1.0) * sum_log_p + G * (lgamma(al + be) - lgamma(al));
+    }
+    if (k == 1) {
+      if (al <= 0.0 || be <= 0.0 || !p_inside) return BPT_NEG_INF;
+      return gamma_ab(1.0, d.rate_b, b) + (be - 1.0) * sum_log1m_p + G * (lgamma(al + be) - lgamma(be));
+    }
+    if (x <= 0.0 || x >= 1.0 || al <= 0.0 || be <= 0.0) return BPT_NEG_INF;
+    return (al - 1.0) * log(x) + (be - 1.0) * log1p(-x);
+  }
+  // annealed: p_g sees the group's first Binomial block; L_g sees both (the number of trials is 1 + L_g)
+  BPT_D void annealed(int k, double x, int, GroupReducer&, double& s, int& c) const {
+    s = 0.0; c = 0;
+    const int G = d.G;
+    if (k < 2) return;
+    if (k < G + 2) {
+      const int g = k - 2;
+      acc_term(binomial_block(0, (double)d.y[g], 1.0 + P[G + 2 + g], x), s, c, err);
+    } else {
+      const int g = k - (G + 2);
+      acc_term(binomial_block(0, (double)d.y[g], 1.0 + x, P[2 + g]), s, c, err);
+      acc_term(binomial_block(1, (double)d.y[g], 1.0 + x, P[2 + g]), s, c, err);
+    }
+  }
+  BPT_D void commit(int k, double x, int) { P[k] = x; }
+  BPT_D void refresh() {}
+  BPT_D void full(GroupReducer&, double& loglik, int& noos, double& logprior) {
+    const int G = d.G;
+    double s = 0.0; int c = 0;
+    for (int g = 0; g < G; g++) {
+      acc_term(binomial_block(0, (double)d.y[g], 1.0 + P[G + 2 + g], P[2 + g]), s, c, err);
+      acc_term(binomial_block(1, (double)d.y[g], 1.0 + P[G + 2 + g], P[2 + g]), s, c, err);
+    }
+    loglik = s; noos = c;
+    const double a = P[0], b = P[1], al = a + 0.5, be = b + 0.5;
+    double lp = gamma_ab(1.0, d.rate_a, a) + gamma_cd(1.0, d.rate_a) + gamma_ab(1.0, d.rate_b, b) + gamma_cd(1.0, d.rate_b);
+    for (int g = 0; g < G; g++) {
+      const double p = P[2 + g];
+      const bool in = p > 0.0 && p < 1.0;
+      lp += (in && al > 0.0) ? (al - 1.0) * log(p) : BPT_NEG_INF;
+      lp += (in && be > 0.0) ? (be - 1.0) * log1p(-p) : BPT_NEG_INF;
+      lp += (al > 0.0 && be > 0.0) ? lgamma(al + be) : BPT_NEG_INF;
+      lp += al > 0.0 ? -lgamma(al) : BPT_NEG_INF;
+      lp += be > 0.0 ? -lgamma(be) : BPT_NEG_INF;
+      lp += poisson_block(0, P[G + 2 + g]) + poisson_block(1, 0.0) + poisson_block(2, P[G + 2 + g]);
+    }
+    logprior = lp;
+  }
+  BPT_D void forward(Rng& rng) {   // topological order: a, b, then per group p_g and L_g
+    const double a = gen_exponential(rng, d.rate_a);
+    const double b = gen_exponential(rng, d.rate_b);
+    P[0] = a; P[1] = b;
+    for (int g = 0; g < d.G; g++) {
+      const double p = gen_beta(rng, a + 0.5, b + 0.5);
+      const int L = gen_poisson_small(rng, d.pois_mean);
+      P[2 + g] = p; P[d.G + 2 + g] = (double)L;
+    }
   }
 };
 

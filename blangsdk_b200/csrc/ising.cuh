@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(kIsingThreads) ising_kernel(DevEngine E, Ising
             return fx + bj * (double)((2 * x - 1) * nb);
           };
           const int x0 = sp[v];
-          const int xn = int_slice(lp, rng, x0, true, 0, 2);
+          int serr = 0;   // a spin window [0, 2) always holds the current state, whose density is finite
+          const int xn = int_slice(lp, rng, x0, true, 0, 2, serr);
           execs++;
           sp[v] = (uint8_t)xn;
         }

@@ -118,6 +118,10 @@ struct LogDensityCall : LogDensityBase<Fam> {
 // One chain's share of ParallelTempering.moveKernel for one scan: forward sample at beta = 0, else
 // floor(nPasses * S) sampler executions in the persistent shuffled order.  P / order are the chain's
 // parameter and sampler-order arrays (shared memory); every thread of the chain group runs this.
+// families with latent integers declare kHasIntSlice; the branch is not compiled into the other kernels
+template <class Fam, class = void> struct HasIntSlice { static constexpr bool value = false; };
+template <class Fam> struct HasIntSlice<Fam, decltype((void)Fam::kHasIntSlice)> { static constexpr bool value = Fam::kHasIntSlice; };
+
 template <class Fam, class Sync>
 BPT_D void explore_chain(const DevEngine& E, Fam& fam, GroupReducer& red, double* P, int* order, int& curpos, int S,
                          int pos, double beta, uint32_t scan, uint32_t key1, int mode, unsigned long long& evals,
@@ -155,6 +159,13 @@ BPT_D void explore_chain(const DevEngine& E, Fam& fam, GroupReducer& red, double
           const double x0 = P[fam.sampler_var(k)];
           const double xn = real_slice(lp, rng, x0, false, 0.0, 0.0, err);
           fam.commit(k, xn, 0);
+        } else if (HasIntSlice<Fam>::value && fam.sampler_type(k) == S_INT_SLICE) {
+          // IntSliceSampler on a latent IntVar (stepping out, w = 10); the state is held as an exact double
+          if constexpr (HasIntSlice<Fam>::value) {
+            const int x0 = (int)P[fam.sampler_var(k)];
+            const int xn = int_slice(lp, rng, x0, false, 0, 0, err);
+            fam.commit(k, (double)xn, 0);
+          }
         } else {   // SimplexSampler.xtend:21-28
           const int K = fam.simplex_dim();
           aux = rng.next_int(K);

@@ -80,8 +80,11 @@ BPT_D bool int_accept(LP& lp, int old_state, int new_state, double h, int left, 
 }
 
 // IntSliceSampler.execute :53-113
+// When no integer of the window is acceptable -- not even the current state, i.e. its density is -inf and the
+// stepping out did not reach the support -- the reference's shrinkage ends in Generators.discreteUniform throwing
+// "Invalid arguments" (Generators.java:205-211): reported here as ERR_INT_SLICE_EMPTY, state unchanged.
 template <class LP>
-BPT_D int int_slice(LP& lp, Rng& rng, int old_state, bool fixed_window, int fw_left, int fw_right) {
+BPT_D int int_slice(LP& lp, Rng& rng, int old_state, bool fixed_window, int fw_left, int fw_right, int& err) {
   const double h = next_log_slice_height(rng, lp(old_state));
   int left, right;
   if (fixed_window) { left = fw_left; right = fw_right; }
@@ -96,6 +99,7 @@ BPT_D int int_slice(LP& lp, Rng& rng, int old_state, bool fixed_window, int fw_l
   }
   int sl = left, sr = right;
   for (;;) {
+    if (sr <= sl) { err |= ERR_INT_SLICE_EMPTY; return old_state; }
     const int new_state = rng.next_int(sr - sl) + sl;   // Generators.discreteUniform :205-222
     if (h <= lp(new_state) && int_accept(lp, old_state, new_state, h, left, right)) return new_state;
     if (new_state < old_state) sl = new_state + 1; else sr = new_state;

@@ -153,3 +153,13 @@ def linear_regression(n=5000, p=3, seed=20240008):
     w = rng.normal(0.0, 2.0, p)
     y = x @ w + 0.7 * rng.standard_normal(n)
     return dict(family="linreg", hyper=dict(v0=25.0, smax=10.0), x=x, y=y, truth=list(w) + [0.7])
+
+
+def rockets_latent(groups=8, seed=20240009):
+    """Family "rockets_latent": F/SimpleHierarchicalModel.bl -- launch counts are latent (Poisson(2)), only failures
+    are observed.  State = a, b, the group probabilities, then the latent counts (as exact doubles)."""
+    rng = np.random.default_rng(seed)
+    launches = 1 + rng.poisson(2.0, groups)
+    p = rng.beta(1.5, 3.0, groups)
+    failures = rng.binomial(launches, p).astype(np.int32)
+    return dict(family="rockets_latent", hyper=dict(rate_a=1.0, rate_b=1.0, pois_mean=2.0), y=failures)

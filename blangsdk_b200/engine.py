@@ -20,7 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libblangpt.so")
 
-FAMILIES = {"normal": 1, "logistic": 2, "mixture": 3, "ising": 4, "betabinomial": 5, "iid": 6, "hierarchical": 7, "linreg": 8}
+FAMILIES = {"normal": 1, "logistic": 2, "mixture": 3, "ising": 4, "betabinomial": 5, "iid": 6, "hierarchical": 7, "linreg": 8, "rockets_latent": 9}
 # family "iid" (include/blangpt.h BLANGPT_IID_* / BLANGPT_PRIOR_*): observation laws and priors
 IID_DISTS = {"poisson": 1, "binomial": 2, "negbinomial": 3, "studentt": 4, "geometric": 5, "laplace": 6,
              "exponential": 7, "gamma": 8, "weibull": 9, "gumbel": 10, "logisticdist": 11, "halfstudentt": 12,
@@ -273,6 +273,8 @@ class Engine:
             arrays, hyper = [], [float(h["N"]), h["coupling"], h["moment"]]
         elif fam == "betabinomial":
             arrays, hyper = [arr(spec["y"], 1), arr(spec["ntrials"], 1)], [h["rate"]]
+        elif fam == "rockets_latent":
+            arrays, hyper = [arr(spec["y"], 1)], [h["rate_a"], h["rate_b"], h["pois_mean"]]
         elif fam == "linreg":
             arrays, hyper = [arr(spec["x"], 0), arr(spec["y"], 0)], [h["v0"], h["smax"]]
         elif fam == "hierarchical":

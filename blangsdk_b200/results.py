@@ -30,6 +30,8 @@ VARIABLES = {
     "betabinomial": [("alpha", None, 0, 1), ("beta", None, 1, 1)],
     "ising": [("vertices", "index_0", 0, None)],
     "linreg": [("coefficients", "index_0", 0, "P"), ("sigma", None, "P", 1)],
+    "rockets_latent": [("a", None, 0, 1), ("b", None, 1, 1), ("failureProbabilities", "rocketType", 2, "H"),
+                       ("numberOfLaunches", "rocketType", "H2", "H")],
     "hierarchical": [("a", None, 0, 1), ("b", None, 1, 1), ("failureProbabilities", "rocketType", 2, None)],
 }
 # family "iid": the latent parameters of each observation law, named as in R/distributions/<Name>.bl
@@ -139,6 +141,9 @@ class PTResultsWriter:
         if isinstance(v, str):
             if v == "P":                      # linreg: the coefficients come first, sigma last
                 return n_reals - 1
+            if v in ("H", "H2"):              # rockets_latent: a, b, then G probabilities, then G counts
+                G = (n_reals - 2) // 2
+                return G if v == "H" else G + 2
             return {"K": self.K, "2K": 2 * self.K}[v]
         return v
 

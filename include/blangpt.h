@@ -52,9 +52,13 @@ enum {
   BLANGPT_FAM_HIERARCHICAL = 7, /* F/HierarchicalModel.bl, not marginalised: a, b ~ Exponential; p_g ~ Beta(a, b);
                                    failures_g ~ Binomial(launches_g, p_g).  data: failures[G] i32, launches[G] i32.
                                    hyper: rate_a, rate_b.  reals = a, b, p_0 .. p_{G-1}                            */
-  BLANGPT_FAM_LINREG = 8        /* F/LinRegression.bl with p covariates: w_j ~ Normal(0, v0), sigma ~ Uniform(0, smax),
+  BLANGPT_FAM_LINREG = 8,       /* F/LinRegression.bl with p covariates: w_j ~ Normal(0, v0), sigma ~ Uniform(0, smax),
                                    y_i ~ Normal(x_i . w, sigma^2).  data: x[n*p] f64 row-major, y[n] f64.
                                    hyper: v0, smax.  reals = w_0 .. w_{p-1}, sigma                                 */
+  BLANGPT_FAM_ROCKETS_LATENT = 9/* F/SimpleHierarchicalModel.bl: family 7 with latent launch counts L_g ~ Poisson(mean),
+                                   p_g ~ Beta(a + 0.5, b + 0.5), failures_g ~ Binomial(1 + L_g, p_g); the L_g are updated
+                                   by IntSliceSampler with stepping out.  data: failures[G] i32.  hyper: rate_a, rate_b,
+                                   mean.  reals = a, b, p_0 .. p_{G-1}, L_0 .. L_{G-1} (the integers as exact doubles)   */
 };
 /* family 6: observation laws (R/distributions/<Name>.bl) and their latent parameters, in this order */
 enum {

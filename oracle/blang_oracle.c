@@ -147,6 +147,17 @@ static double gen_gamma(Rng* r, double shape, double rate) {
   if (result == 0.0) result = ZERO_PLUS_EPS;
   return result;
 }
+/* Generators.poisson :299-309 -> commons-math3 PoissonDistribution.sample() for mean < 40: multiply uniforms
+ * until the product falls below exp(-mean). */
+static int gen_poisson_small(Rng* r, double mean) {
+  const double p = exp(-mean);
+  long n = 0; double prod = 1.0;
+  while (n < 1000 * mean) {
+    prod *= rng_double(r);
+    if (prod >= p) n++; else return (int)n;
+  }
+  return (int)n;
+}
 /* Generators.beta :143-152.  commons-math3's BetaDistribution.sample() is Cheng's BB/BC rejection sampler; the
  * draw stream is unpinned against the JVM anyway, so the restatement uses the two-gamma identity
  * X / (X + Y), X ~ Gamma(alpha, 1), Y ~ Gamma(beta, 1), and keeps the reference's end-point guards. */
@@ -214,6 +225,8 @@ enum {
   F_LINREG_F1, F_LINREG_F2,   /* family 8: Normal.bl:17-24 with mean = sum_j w_j x[i0][j], variance = sigma * sigma */
   F_HBETA,            /* family 7: block i2 of Beta.bl:14-41 with LATENT alpha = real 0, beta = real 1, realization = real i0 */
   F_HBINOM,           /* family 7: block i1 of Binomial.bl:14-27, group i0, p = real 2 + i0 */
+  F_POIS_INT,         /* family 9: block i1 of Poisson.bl:11-26 on the latent int i0, mean = c0 */
+  F_HBINOM_LAT,       /* family 9: block i1 of Binomial.bl:14-27, group i0, trials = 1 + int i0, p = real 2 + i0 */
   F_BETA_A, F_BETA_B,                      /* Beta.bl:14-27 prior on real i0, alpha = c0, beta = c1  */
   F_UNIF_B                                 /* ContinuousUniform.bl:16-19 prior on real i0, [c0, c1]  */
 };
@@ -224,7 +237,7 @@ typedef struct {
   double c0, c1;
 } Factor;
 
-enum { S_REAL_SLICE = 0, S_SIMPLEX = 1, S_CATEGORICAL = 2 };
+enum { S_REAL_SLICE = 0, S_SIMPLEX = 1, S_CATEGORICAL = 2, S_INT_SLICE = 3 };
 
 typedef struct {
   int32_t type;
@@ -234,7 +247,7 @@ typedef struct {
   int32_t *fixed_idx, *ann_idx;   /* sampler2sparseUpdate{Fixed,Annealed}, SampledModel.java:67-69 */
 } Sampler;
 
-enum { FW_NORMAL = 0, FW_EXPONENTIAL, FW_GAMMA, FW_DIRICHLET_SYM, FW_BERNOULLI_INT, FW_BETA, FW_UNIFORM, FW_BETA_LATENT };
+enum { FW_NORMAL = 0, FW_EXPONENTIAL, FW_GAMMA, FW_DIRICHLET_SYM, FW_BERNOULLI_INT, FW_BETA, FW_UNIFORM, FW_BETA_LATENT, FW_POISSON_INT };
 typedef struct { int32_t kind, var, K; double a, b; } Forward;
 
 struct orc_model {
@@ -474,8 +487,16 @@ static double factor_eval(const orc_model* m, const Factor* f, const double* re,
       if (variance <= 0.0) return NEG_INF;
       return -0.5 * pow(mean - m->y[f->i0], 2) / variance;
     }
+    case F_POIS_INT: {
+      const double th[1] = {f->c0};
+      return iid_law(ORC_IID_POISSON, f->i1, th, (double)in[f->i0], 0.0);
+    }
+    case F_HBINOM_LAT: {
+      const double th[1] = {re[2 + f->i0]};
+      return iid_law(ORC_IID_BINOMIAL, f->i1, th, (double)m->yi[f->i0], (double)(1 + in[f->i0]));
+    }
     case F_HBETA: {
-      double alpha = re[0], beta = re[1], x = re[f->i0];
+      double alpha = re[0] + f->c0, beta = re[1] + f->c0, x = re[f->i0];   /* c0: 0, or the 0.5 of SimpleHierarchicalModel.bl */
       switch (f->i2) {
         case 0:
           if (x <= 0.0 || x >= 1.0) return NEG_INF;
@@ -690,6 +711,37 @@ orc_model* orc_model_hierarchical(const int32_t* failures, const int32_t* launch
   }
   m->init_reals[0] = 1.0; m->init_reals[1] = 1.0;
   for (int g = 0; g < G; g++) m->init_reals[2 + g] = 0.5;
+  return b_end(&b);
+}
+
+/* family 9: F/SimpleHierarchicalModel.bl -- family 7 with LATENT launch counts (IntSliceSampler with stepping out):
+ *   a, b ~ Exponential(rate); p_g | a, b ~ Beta(a + 0.5, b + 0.5); L_g ~ Poisson(mean); failures_g ~ Binomial(1 + L_g, p_g).
+ * reals = [a, b, p_0..p_{G-1}], ints = [L_0..L_{G-1}]; samplers: G + 2 real slice, then G int slice. */
+orc_model* orc_model_rockets_latent(const int32_t* failures, int G, double rate_a, double rate_b, double pois_mean) {
+  Builder b = b_begin(ORC_FAM_ROCKETS_LATENT, G + 2, G, 2 * G + 2);
+  orc_model* m = b.m; m->n_obs = G;
+  m->yi = (int32_t*)malloc(sizeof(int32_t) * (G > 0 ? G : 1)); memcpy(m->yi, failures, sizeof(int32_t) * G);
+  for (int s = 0; s < G + 2; s++) { m->samplers[s].type = S_REAL_SLICE; m->samplers[s].var = s; }
+  for (int g = 0; g < G; g++) { m->samplers[G + 2 + g].type = S_INT_SLICE; m->samplers[G + 2 + g].var = g; }
+  b_gamma_prior(&b, 0, 0, 1.0, rate_a, 1);
+  b_gamma_prior(&b, 1, 1, 1.0, rate_b, 1);
+  for (int g = 0; g < G; g++) {
+    const int sp = 2 + g, sl = G + 2 + g;
+    int fa = b_factor(&b, F_HBETA, 0, 2 + g, 0, 0, 0.5, 0);   b_connect(&b, 0, fa); b_connect(&b, sp, fa);
+    int fb = b_factor(&b, F_HBETA, 0, 2 + g, 0, 1, 0.5, 0);   b_connect(&b, 1, fb); b_connect(&b, sp, fb);
+    int fc = b_factor(&b, F_HBETA, 0, 2 + g, 0, 2, 0.5, 0);   b_connect(&b, 0, fc); b_connect(&b, 1, fc);
+    b_connect(&b, 0, b_factor(&b, F_HBETA, 0, 2 + g, 0, 3, 0.5, 0));
+    b_connect(&b, 1, b_factor(&b, F_HBETA, 0, 2 + g, 0, 4, 0.5, 0));
+    b_forward(m, FW_BETA_LATENT, 2 + g, 0, 0.5, 0);
+    b_connect(&b, sl, b_factor(&b, F_POIS_INT, 0, g, 0, 0, pois_mean, 0));
+    b_factor(&b, F_POIS_INT, 0, g, 1, 0, pois_mean, 0);
+    b_connect(&b, sl, b_factor(&b, F_POIS_INT, 0, g, 2, 0, pois_mean, 0));
+    b_forward(m, FW_POISSON_INT, g, 0, pois_mean, 0);
+    int l0 = b_factor(&b, F_HBINOM_LAT, 1, g, 0, 0, 0, 0);     b_connect(&b, sp, l0); b_connect(&b, sl, l0);
+    b_connect(&b, sl, b_factor(&b, F_HBINOM_LAT, 1, g, 1, 0, 0, 0));
+  }
+  m->init_reals[0] = 1.0; m->init_reals[1] = 1.0;
+  for (int g = 0; g < G; g++) { m->init_reals[2 + g] = 0.5; m->init_ints[g] = 0; }
   return b_end(&b);
 }
 
@@ -928,7 +980,8 @@ static void sm_forward_sample(SampledModel* s, Rng* r) {
       case FW_GAMMA: s->reals[f->var] = gen_gamma(r, f->a, f->b); break;
       case FW_BERNOULLI_INT: s->ints[f->var] = rng_bernoulli(r, f->a) ? 1 : 0; break;
       case FW_BETA: s->reals[f->var] = gen_beta(r, f->a, f->b); break;
-      case FW_BETA_LATENT: s->reals[f->var] = gen_beta(r, s->reals[0], s->reals[1]); break;   /* parameters drawn just before */
+      case FW_BETA_LATENT: s->reals[f->var] = gen_beta(r, s->reals[0] + f->a, s->reals[1] + f->a); break;   /* parameters drawn just before */
+      case FW_POISSON_INT: s->ints[f->var] = gen_poisson_small(r, f->a); break;
       case FW_UNIFORM: s->reals[f->var] = f->a + rng_double(r) * (f->b - f->a); break;   /* Generators.uniform :197-202 */
       case FW_DIRICHLET_SYM: {   /* Generators.dirichletInPlace :233-272 */
         double* out = s->reals + f->var; int K = f->K; double conc = f->a;
@@ -1069,6 +1122,10 @@ static void int_slice_execute(SamplerCtx* c, Rng* r, int fixed_window, int fw_le
   }
   int sl = left, sr = right;
   for (;;) {
+    if (sr <= sl) {   /* Generators.discreteUniform :205-211 throws "Invalid arguments": no point of the window is acceptable */
+      c->s->error |= ORC_ERR_INT_SLICE_EMPTY;
+      c->s->ints[c->sp->var] = old_state; return;
+    }
     const int new_state = gen_discrete_uniform(r, sl, sr);
     if (h <= int_log_density_at(c, new_state) && int_accept(c, old_state, new_state, h, left, right)) {
       c->s->ints[c->sp->var] = new_state;
@@ -1091,6 +1148,7 @@ static void sampler_execute(SampledModel* s, int k, Rng* r) {
       real_slice_execute(&c, r, 1, 0.0, sum);
     } break;
     case S_CATEGORICAL: int_slice_execute(&c, r, 1, 0, c.sp->K); break;   /* CategoricalSampler.xtend:24-28 */
+    case S_INT_SLICE: int_slice_execute(&c, r, 0, 0, 0); break;             /* IntSliceSampler on a latent IntVar */
   }
 }
 
@@ -1441,6 +1499,11 @@ void orc_pt_scan(orc_pt* pt, double* energies_out, int32_t* indicators_out) {
 uint64_t orc_pt_n_evals(const orc_pt* pt) { uint64_t t = 0; for (int i = 0; i < pt->n; i++) t += pt->states[i]->n_evals; return t; }
 uint64_t orc_pt_n_factor_evals(const orc_pt* pt) { uint64_t t = 0; for (int i = 0; i < pt->n; i++) t += pt->states[i]->n_factor_evals; return t; }
 uint64_t orc_pt_n_scans(const orc_pt* pt) { return pt->scan_index; }
+int orc_pt_error(const orc_pt* pt) {
+  int e = 0;
+  for (int i = 0; i < pt->n; i++) e |= pt->states[i]->error;
+  return e;
+}
 
 void orc_pt_round_stats(const orc_pt* pt, orc_round_stats* o) {
   int n = pt->n;

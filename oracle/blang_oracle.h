@@ -41,7 +41,8 @@ enum {
   ORC_FAM_BETABINOMIAL = 5, /* C5: a,b ~ Exponential(rate), y_g ~ BetaBinomial(n_g,a,b)            */
   ORC_FAM_IID = 6,          /* y_i ~ Dist(theta) i.i.d., theta_j ~ prior_j          */
   ORC_FAM_HIERARCHICAL = 7, /* F/HierarchicalModel.bl: a,b ~ Exp; p_g ~ Beta(a,b); y_g ~ Binomial(n_g,p_g) */
-  ORC_FAM_LINREG = 8        /* F/LinRegression.bl: w_j ~ Normal(0,v0), sigma ~ U(0,smax), y_i ~ Normal(x_i.w, sigma^2) */
+  ORC_FAM_LINREG = 8,       /* F/LinRegression.bl: w_j ~ Normal(0,v0), sigma ~ U(0,smax), y_i ~ Normal(x_i.w, sigma^2) */
+  ORC_FAM_ROCKETS_LATENT = 9/* F/SimpleHierarchicalModel.bl: family 7 with latent Poisson launch counts            */
 };
 /* observation laws of family 6 and their parameters (reals, in this order) */
 enum {
@@ -87,6 +88,8 @@ orc_model* orc_model_mixture(const double* y, int n, int K, double m0, double v0
                              double gshape, double grate, double conc);
 orc_model* orc_model_ising(int N, double coupling, double moment);
 orc_model* orc_model_betabinomial(const int32_t* y, const int32_t* ntrials, int n, double rate);
+/* family 9: reals = [a, b, p_0..p_{G-1}], ints = [L_0..L_{G-1}] */
+orc_model* orc_model_rockets_latent(const int32_t* failures, int G, double rate_a, double rate_b, double pois_mean);
 /* family 8: reals = [w_0..w_{p-1}, sigma] */
 orc_model* orc_model_linreg(const double* x_rowmajor, const double* y, int n, int p, double v0, double smax);
 /* family 7: reals = [a, b, p_0..p_{G-1}] */
@@ -148,6 +151,13 @@ void orc_pt_swap_kernel(orc_pt*, int32_t* indicators_out);
 uint64_t orc_pt_n_evals(const orc_pt*);         /* sampler logDensity() calls     */
 uint64_t orc_pt_n_factor_evals(const orc_pt*);  /* individual factor evaluations  */
 uint64_t orc_pt_n_scans(const orc_pt*);
+/* sticky conditions that throw in the Java engine: bit 1 = a factor returned NaN (ExponentiatedFactor.java:26-29),
+ * 2 = real slice diverged to infinity (RealSliceSampler.java:81-89), 4 = the integer slice sampler's window holds no
+ * acceptable point (Generators.discreteUniform "Invalid arguments", Generators.java:205-211) */
+#define ORC_ERR_NAN 1
+#define ORC_ERR_SLICE_DIVERGED 2
+#define ORC_ERR_INT_SLICE_EMPTY 4
+int orc_pt_error(const orc_pt*);
 
 typedef struct {
   int32_t n_chains;

@@ -75,6 +75,10 @@ def lib():
     L.orc_model_ising.argtypes = [C.c_int, C.c_double, C.c_double]
     L.orc_model_betabinomial.restype = vp
     L.orc_model_betabinomial.argtypes = [_ip, _ip, C.c_int, C.c_double]
+    L.orc_pt_error.restype = C.c_int
+    L.orc_pt_error.argtypes = [vp]
+    L.orc_model_rockets_latent.restype = vp
+    L.orc_model_rockets_latent.argtypes = [_ip, C.c_int, C.c_double, C.c_double, C.c_double]
     L.orc_model_linreg.restype = vp
     L.orc_model_linreg.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_double, C.c_double]
     L.orc_model_hierarchical.restype = vp
@@ -192,6 +196,9 @@ class Model:
             y = np.ascontiguousarray(spec["y"], dtype=np.int32)
             nt = np.ascontiguousarray(spec["ntrials"], dtype=np.int32)
             self.h = L.orc_model_betabinomial(_i(y), _i(nt), len(y), h["rate"])
+        elif fam == "rockets_latent":
+            y = np.ascontiguousarray(spec["y"], dtype=np.int32)
+            self.h = L.orc_model_rockets_latent(_i(y), len(y), h["rate_a"], h["rate_b"], h["pois_mean"])
         elif fam == "linreg":
             x = np.ascontiguousarray(spec["x"], dtype=np.float64)
             y = np.ascontiguousarray(spec["y"], dtype=np.float64)
@@ -300,6 +307,10 @@ class PT:
         ind = np.zeros(self.n, dtype=np.int32)
         lib().orc_pt_scan(self.h, _d(e), _i(ind))
         return e, ind
+
+    def error(self):
+        """sticky bits of conditions that throw in the Java engine (ORC_ERR_* in blang_oracle.h)"""
+        return lib().orc_pt_error(self.h)
 
     def n_evals(self):
         return int(lib().orc_pt_n_evals(self.h))

@@ -47,6 +47,7 @@ def main():
         specs["iid_" + dist] = D.iid_observations(dist, 45)
     specs["hierarchical"] = D.hierarchical_rockets(6)
     specs["linreg"] = D.linear_regression(50, 3)
+    specs["rockets_latent"] = D.rockets_latent(5)
     rng = np.random.default_rng(20240600)
     cases = []
     for name, spec in specs.items():
@@ -61,6 +62,10 @@ def main():
                 it = None
             elif name == "logistic":
                 re, it = rng.normal(0, 1.5, m.n_reals).tolist(), None
+            elif name == "rockets_latent":
+                G = m.n_ints
+                re = rng.gamma(2.0, 1.0, 2).tolist() + rng.uniform(0.02, 0.98, G).tolist()
+                it = (np.maximum(np.asarray(spec["y"]) - 1, 0) + rng.poisson(1.0, G)).tolist()
             elif name == "linreg":
                 re, it = rng.normal(0, 2.0, m.n_reals - 1).tolist() + [float(rng.uniform(0.1, 5.0))], None
             elif name == "hierarchical":
@@ -77,7 +82,15 @@ def main():
         pt = O.PT(m, nChains=4, seed=2024,
                   sweepOrder=O.ORDER_CHECKERBOARD if name == "ising" else O.ORDER_REFERENCE)
         start = None
-        if name.startswith("iid_") and name[4:] not in iid_state:
+        if name == "rockets_latent":          # a feasible start (1 + L_g >= failures_g), see tests/test_gpu_rockets_latent.py
+            G = m.n_ints
+            start = []
+            for p in range(4):
+                re = (rng.gamma(2.0, 0.5, 2) + 0.2).tolist() + rng.uniform(0.1, 0.9, G).tolist()
+                it = (np.maximum(np.asarray(spec["y"]) - 1, 0) + rng.poisson(1.0, G)).tolist()
+                pt.set_state(p, re, it)
+                start.append(re + [float(v) for v in it])      # the engine's layout: the integers after the reals
+        elif name.startswith("iid_") and name[4:] not in iid_state:
             start = [[float(v * (1.0 + 0.1 * rng.normal())) for v in spec["truth"]] for _ in range(4)]
             for p, st in enumerate(start):
                 pt.set_state(p, st)

@@ -172,3 +172,29 @@ def test_eit_linreg(oracle):
         return x @ np.array(th[:2]) + th[2] * rng.standard_normal(8)
     spec = lambda y: dict(family="linreg", hyper=dict(v0=4.0, smax=3.0), x=x, y=y)
     _eit(oracle, spec, prior, sim, 3, [lambda t: t[0], lambda t: t[1], lambda t: t[2], lambda t: t[0] * t[2]], 8)
+
+
+def test_eit_rockets_latent(oracle):
+    """F/SimpleHierarchicalModel.bl: the latent counts move by IntSliceSampler with stepping out"""
+    def prior(rng):
+        a, b = rng.exponential(1.0), rng.exponential(1.0)
+        p = np.clip(rng.beta(a + 0.5, b + 0.5, 3), 1e-300, 1 - 1e-16)
+        return ([a, b] + list(p), list(rng.poisson(2.0, 3)))
+    rng0 = np.random.default_rng(77)
+    prior_vals, post_vals = [], []
+    for rep in range(N_REP):
+        th, L = prior(rng0)
+        y = rng0.binomial(1 + np.array(L), th[2:]).astype(np.int32)
+        m = oracle.Model(dict(family="rockets_latent", hyper=dict(rate_a=1.0, rate_b=1.0, pois_mean=2.0), y=y))
+        pt = oracle.PT(m, nChains=1, seed=3000 + rep)
+        pt.set_state(0, th, L)
+        for _ in range(K_SCANS):
+            pt.scan()
+        re, it = pt.get_state(0)
+        fns = lambda r, i: [r[0], r[1], r[2], float(i[0]), float(i[1] + i[2])]
+        prior_vals.append(fns(th, L)); post_vals.append(fns(re, it))
+        assert pt.check_caches() < 1e-9
+    prior_vals, post_vals = np.array(prior_vals), np.array(post_vals)
+    for j in range(prior_vals.shape[1]):
+        p = stats.ks_2samp(prior_vals[:, j], post_vals[:, j]).pvalue
+        assert p > ALPHA / prior_vals.shape[1], "statistic %d: KS p = %.2e" % (j, p)
