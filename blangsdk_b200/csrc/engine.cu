@@ -165,17 +165,18 @@ static int launch_explore(blangpt_handle* h, int mode) {
     case BLANGPT_FAM_LINREG: return launch_explore_t<LinRegFam>(h, h->linreg, mode);
     case BLANGPT_FAM_ROCKETS_LATENT: return launch_explore_t<RocketsLatentFam>(h, h->rockets, mode);
     case BLANGPT_FAM_LOGISTIC:
-      if (h->logistic_threads == 1024) {
-        LogisticFamT<1024>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
-        return launch_explore_t<LogisticFamT<1024>>(h, d2, mode);
-      }
       if (h->logistic_threads == 256) {   // two 256-thread CTAs per SM: another chain's CTA fills this one's barrier waits
         LogisticFamT<256, 2>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
         return launch_explore_t<LogisticFamT<256, 2>>(h, d2, mode);
       }
-      if (h->logistic_l2ahead) {   // per-chain cache larger than the L2: stream it with L2 prefetch hints
-        LogisticFamT<512, 1, 3>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
-        return launch_explore_t<LogisticFamT<512, 1, 3>>(h, d2, mode);
+      if (h->logistic_l2ahead) {   // per-chain caches larger than the L2: they stream from HBM.  1024 threads per CTA
+        // (8 warps per scheduler hide the latency: 313 vs 356 ms per scan at 1024 chains) plus L2 prefetch hints
+        LogisticFamT<1024, 1, 3>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
+        return launch_explore_t<LogisticFamT<1024, 1, 3>>(h, d2, mode);
+      }
+      if (h->logistic_threads == 1024) {
+        LogisticFamT<1024>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
+        return launch_explore_t<LogisticFamT<1024>>(h, d2, mode);
       }
       if (h->logistic_threads == 768) {
         LogisticFamT<768>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
@@ -527,12 +528,17 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
   h->G = family == BLANGPT_FAM_ISING ? 1 : pick_ctas_per_chain(h, rows);
   // 256 threads x two CTAs per SM x twice the cluster was measured too (another chain's CTA fills this one's
   // barrier waits): 19.3 vs 19.8 ms per scan with a warm L2, 19.9 vs 19.5 ms under bench.py's L2 flush -> not the default
-  if (family == BLANGPT_FAM_LOGISTIC && h->logistic_threads == 0) {
-    h->logistic_threads = 512;
+  if (family == BLANGPT_FAM_LOGISTIC) {
+    // CTA shape: 512 threads when a cluster of CTAs serves the chain (C2: 2 x 512), 1024 when one CTA does (more
+    // chains than half the SMs: 128 chains 53.8 -> 46.0 ms per scan, 1024 chains 356 -> 313 ms).  When the chains'
+    // caches plus X exceed ~3/4 of the L2 they stream from HBM and the kernel also issues L2 prefetch hints three
+    // steps ahead (128 chains 46.0 -> 41.5 ms, 1024 chains 313 -> 300 ms).
+    if (h->logistic_threads == 0) h->logistic_threads = (h->G == 1 && rows >= 32768) ? 1024 : 512;
     int l2 = 0;
     cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, c.device);
     const size_t cache_bytes = (size_t)h->logistic.npad * (h->M_total / c.worldSize) * sizeof(double);
-    h->logistic_l2ahead = l2 > 0 && cache_bytes + (size_t)h->logistic.npad * h->logistic.p * sizeof(double) > (size_t)l2;
+    const size_t x_bytes = (size_t)h->logistic.npad * h->logistic.p * sizeof(double);
+    h->logistic_l2ahead = h->logistic_threads == 1024 && l2 > 0 && (cache_bytes + x_bytes) > (size_t)l2 / 4 * 3;
     if (const char* t = getenv("BLANGPT_L2AHEAD")) h->logistic_l2ahead = atoi(t) != 0;
   }
   if (h->G != 1 && h->G != 2 && h->G != 4 && h->G != 8) FAIL(h, BLANGPT_EINVAL, "ctasPerChain must be 1, 2, 4 or 8");

@@ -54,6 +54,9 @@ if __name__ == "__main__":
     if "C2x1024" in which:   # north_star target regime: >= 1024 chains, eta cache (819 MB) streams from HBM
         run("C2 logistic 100k x 32, 1024 chains on one GPU", D.logistic_regression(), 1024, init="COPIES", scans=2, warm=2,
             algo_bytes=25_700_000)
+    if "C2x128" in which:    # one GPU's share of 1024 chains sharded over 8 GPUs
+        run("C2 logistic 100k x 32, 128 chains on one GPU", D.logistic_regression(), 128, init="COPIES", scans=5, warm=3,
+            algo_bytes=25_700_000)
     if "C3" in which:
         run("C3 mixture K=4 1M obs, 256 chains", D.gaussian_mixture(), 256, init="COPIES", scans=2, warm=1, algo_bytes=8_000_000)
     if "C4" in which:
