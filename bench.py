@@ -132,8 +132,8 @@ def cpu_sample(spec, budget_s, n_chains=None):
 
 def workload(n_chains):
     """config.workload, the same string in both arms"""
-    return ("C2 Bayesian logistic regression 100000 x 32 (seed 20240002), %d chains (64 per GPU), nPassesPerScan 3, "
-            "COPIES init from w=0; step = one NRPT scan (explore + DEO swap)" % n_chains)
+    return ("C2 Bayesian logistic regression 100000 x 32 (seed 20240002), %d chains (%d per GPU), nPassesPerScan 3, "
+            "COPIES init from w=0; step = one NRPT scan (explore + DEO swap)" % (n_chains, CHAINS_PER_GPU))
 
 
 def run_reference(args):
@@ -317,15 +317,21 @@ def run_gpu(args):
 
 
 def main():
+    global CHAINS_PER_GPU, METRIC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft")
     ap.add_argument("--ctas", type=int, default=0, help="CTAs per chain (0 = auto)")
+    ap.add_argument("--chains-per-gpu", type=int, default=CHAINS_PER_GPU,
+                    help="default 64 = BASELINE config 1; 128 = the north-star shape (1024 chains on 8 GPUs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.chains_per_gpu != CHAINS_PER_GPU:
+        CHAINS_PER_GPU = args.chains_per_gpu
+        METRIC = METRIC.replace("64 chains/GPU", "%d chains/GPU" % CHAINS_PER_GPU)
     args.warmup = max(3, args.warmup) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         run_reference(args)
