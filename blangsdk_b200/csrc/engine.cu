@@ -32,7 +32,7 @@ struct blangpt_handle {
   int n_reals = 0, n_ints = 0, n_samplers = 0;
   int G = 1;                      // CTAs per chain
   bool logistic_l2ahead = false;  // eta cache > L2: use the kernel variant with L2 prefetch hints
-  int logistic_threads = 0;       // CTA size of the C2 kernel: 0 = choose in set_model, or BLANGPT_LOGISTIC_THREADS=256|512|768|1024
+  int logistic_threads = 0;       // CTA size of the C2 kernel: 0 = choose in set_model, or BLANGPT_LOGISTIC_THREADS=512|1024
   bool model_set = false, tables_valid = false;
   cudaStream_t stream = nullptr;  // nullptr = legacy default stream
   bool own_stream = false;
@@ -112,7 +112,7 @@ extern "C" int blangpt_create(const blangpt_config* cfg, blangpt_handle** out) {
   if (prop.major < 10) { set_error(nullptr, "device sm_%d%d is not Blackwell (kernels are built for sm_100a only)", prop.major, prop.minor); return BLANGPT_ECUDA; }
   blangpt_handle* h = new blangpt_handle();
   h->cfg = *cfg;
-  if (const char* t = getenv("BLANGPT_LOGISTIC_THREADS")) { const int v = atoi(t); h->logistic_threads = (v == 256 || v == 768 || v == 1024) ? v : 512; }
+  if (const char* t = getenv("BLANGPT_LOGISTIC_THREADS")) h->logistic_threads = atoi(t) == 1024 ? 1024 : 512;
   h->M_total = (int64_t)cfg->nReplicas * cfg->nChains;
   *out = h;
   return BLANGPT_OK;
@@ -165,10 +165,6 @@ static int launch_explore(blangpt_handle* h, int mode) {
     case BLANGPT_FAM_LINREG: return launch_explore_t<LinRegFam>(h, h->linreg, mode);
     case BLANGPT_FAM_ROCKETS_LATENT: return launch_explore_t<RocketsLatentFam>(h, h->rockets, mode);
     case BLANGPT_FAM_LOGISTIC:
-      if (h->logistic_threads == 256) {   // two 256-thread CTAs per SM: another chain's CTA fills this one's barrier waits
-        LogisticFamT<256, 2>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
-        return launch_explore_t<LogisticFamT<256, 2>>(h, d2, mode);
-      }
       if (h->logistic_l2ahead) {   // per-chain caches larger than the L2: they stream from HBM.  1024 threads per CTA
         // (8 warps per scheduler hide the latency: 313 vs 356 ms per scan at 1024 chains) plus L2 prefetch hints
         LogisticFamT<1024, 1, 3>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
@@ -177,10 +173,6 @@ static int launch_explore(blangpt_handle* h, int mode) {
       if (h->logistic_threads == 1024) {
         LogisticFamT<1024>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
         return launch_explore_t<LogisticFamT<1024>>(h, d2, mode);
-      }
-      if (h->logistic_threads == 768) {
-        LogisticFamT<768>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
-        return launch_explore_t<LogisticFamT<768>>(h, d2, mode);
       }
       return launch_explore_t<LogisticFam>(h, h->logistic, mode);
     case BLANGPT_FAM_MIXTURE:
@@ -526,8 +518,7 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
     default: FAIL(h, BLANGPT_EUNSUPPORTED, "unknown model family %d: the engine only runs the closed catalogue (no CPU fallback)", family);
   }
   h->G = family == BLANGPT_FAM_ISING ? 1 : pick_ctas_per_chain(h, rows);
-  // 256 threads x two CTAs per SM x twice the cluster was measured too (another chain's CTA fills this one's
-  // barrier waits): 19.3 vs 19.8 ms per scan with a warm L2, 19.9 vs 19.5 ms under bench.py's L2 flush -> not the default
+  // (256 threads x two CTAs per SM x twice the cluster, and 768-thread CTAs, were measured and dropped: DESIGN.md 5.1)
   if (family == BLANGPT_FAM_LOGISTIC) {
     // CTA shape: 512 threads when a cluster of CTAs serves the chain (C2: 2 x 512), 1024 when one CTA does (more
     // chains than half the SMs: 128 chains 53.8 -> 46.0 ms per scan, 1024 chains 356 -> 313 ms).  When the chains'

@@ -114,10 +114,10 @@ def test_cluster_sizes(oracle, datasets, ctas):
         eng.close()
 
 
-@pytest.mark.parametrize("threads,ctas", [(256, 1), (256, 4), (768, 2), (1024, 2), ("l2ahead", 1), ("l2ahead", 2)])
+@pytest.mark.parametrize("threads,ctas", [(512, 1), (1024, 1), (1024, 2), ("l2ahead", 1), ("l2ahead", 2)])
 def test_logistic_cta_shapes(oracle, datasets, monkeypatch, threads, ctas):
-    """the C2 kernel's other shapes (256/768/1024-thread CTAs; the variant with L2 prefetch hints that set_model
-    picks when the per-chain caches exceed the L2) walk the same trajectory as the oracle"""
+    """the C2 kernel's shapes (512- and 1024-thread CTAs; the variant with L2 prefetch hints that set_model picks when
+    the per-chain caches outgrow the L2) walk the same trajectory as the oracle"""
     if threads == "l2ahead":
         monkeypatch.setenv("BLANGPT_L2AHEAD", "1")
     else:
