@@ -1,5 +1,7 @@
 #!/bin/sh
-# Builds libblangpt.so in-tree for sm_100a (B200).  nvcc cross-compiles without a GPU.
+# Builds libblangpt.so in-tree for sm_100a (B200).  nvcc cross-compiles without a GPU (about two minutes).
+# Do not add --split-compile: it halves the build time but changes the code generated for the C2 kernel
+# (measured: 2.78 -> 2.06 M evals/s).
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
