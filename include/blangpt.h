@@ -34,8 +34,11 @@ enum {
   BLANGPT_ECUDA = 2,        /* CUDA runtime error (message in last_error)                */
   BLANGPT_ESTATE = 3,       /* call order violated (e.g. run before set_model)           */
   BLANGPT_ENUMERIC = 4,     /* device-side condition that throws in Java: NaN factor
-                               (ExponentiatedFactor.java:26-29) or slice diverged to
-                               infinity (RealSliceSampler.java:81-82,88-89)              */
+                               (ExponentiatedFactor.java:26-29), slice diverged to
+                               infinity (RealSliceSampler.java:81-82,88-89), or no
+                               acceptable integer in the slice window ("Invalid
+                               arguments", Generators.java:205-211 via
+                               IntSliceSampler.java:93-111)                              */
   BLANGPT_EUNSUPPORTED = 5  /* model / option outside the closed catalogue               */
 };
 
