@@ -1062,6 +1062,7 @@ static int real_accept(SamplerCtx* c, int fixed_window, double old_state, double
 }
 /* RealSliceSampler.execute :53-119 */
 static void real_slice_execute(SamplerCtx* c, Rng* r, int fixed_window, double fw_left, double fw_right) {
+  if (isnan(var_get(c))) { c->s->error |= 1; return; }   /* the reference throws at the first NaN factor, ExponentiatedFactor.java:26-29 */
   const double log_slice_height = next_log_slice_height(r, sampler_log_density(c));
   const double old_state = var_get(c);
   double left, right;

@@ -333,6 +333,10 @@ def test_error_paths(datasets):
     with pytest.raises(BlangPTError) as ei:
         eng.log_density()
     assert "NaN" in str(ei.value)
+    with pytest.raises(BlangPTError) as ei:      # scans from a NaN coordinate report the error too (and terminate)
+        eng.run_scans(2)
+        eng.counters()
+    assert "NaN" in str(ei.value)
     eng.close()
     with pytest.raises(BlangPTError):
         PT(targetAccept=1.5)
