@@ -135,7 +135,12 @@ BPT_D void explore_chain(const DevEngine& E, Fam& fam, GroupReducer& red, double
       Rng rng(E.key0, key1, P_FORWARD, (uint32_t)pos, scan, 0u);
       fam.forward(rng);
     } else {
-      const int n_steps = E.steps_override > 0 ? E.steps_override : (int)floor(E.n_passes * S);
+      // A NaN coordinate (only possible through set_state) makes every factor NaN: the reference throws at the first
+      // evaluation (ExponentiatedFactor.java:26-29); here the slice sampler's shrinkage would never terminate.
+      bool nan_state = false;
+      for (int v = 0; v < Fam::n_reals(fam.d); v++) nan_state = nan_state || (P[v] != P[v]);
+      int n_steps = E.steps_override > 0 ? E.steps_override : (int)floor(E.n_passes * S);
+      if (nan_state) { err |= ERR_NAN; n_steps = 0; }
       for (int t = 0; t < n_steps; t++) {
         Sync::sync();
         if (curpos == -1) {   // Collections.shuffle(order, rnd); SampledModel.java:267-272

@@ -40,9 +40,6 @@ BPT_D bool real_accept(LP& lp, bool fixed_window, double old_state, double new_s
 template <class LP>
 BPT_D double real_slice(LP& lp, Rng& rng, double old_state, bool fixed_window, double fw_left, double fw_right,
                         int& err) {
-  // a NaN coordinate (only possible through set_state) makes every factor NaN: the reference throws at the first
-  // evaluation (ExponentiatedFactor.java:26-29); here the shrinkage below would never terminate
-  if (old_state != old_state) { err |= ERR_NAN; return old_state; }
   const double h = next_log_slice_height(rng, lp(old_state));
   double left, right;
   if (fixed_window) { left = fw_left; right = fw_right; }
