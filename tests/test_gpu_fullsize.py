@@ -156,3 +156,49 @@ def test_ising_gpu_statistics_against_enumeration(oracle, datasets):
     se = bm.std(ddof=1) / math.sqrt(nb)
     assert abs(e.mean() - dlogz) < 5 * se + 0.05
     pt.engine.close()
+
+
+def test_c1_reference_config_against_quadrature(datasets):
+    """BASELINE config 0 exactly as the reference would run it (1 000 observations, 8 chains, nScans = 1000 => 1001
+    scans, adaptFraction 0.5, nPassesPerScan 3, SCM initialisation, five seeds): posterior means and variances of
+    (mu, sigma^2) and log Z against 2-D quadrature, gated by batch-means Monte Carlo errors."""
+    import math
+    from blangsdk_b200.engine import PT
+    spec = datasets.normal_meanvar()
+    y = spec["y"]; n = len(y)
+    assert n == 1000
+    mu = np.linspace(y.mean() - 0.5, y.mean() + 0.5, 1001)
+    s2 = np.linspace(2.8, 5.6, 1401)
+    ybar, S = y.mean(), ((y - y.mean()) ** 2).sum()
+    MU, S2 = np.meshgrid(mu, s2, indexing="ij")
+    ll = -0.5 * n * np.log(2 * np.pi * S2) - 0.5 * (S + n * (MU - ybar) ** 2) / S2
+    lp = -0.5 * np.log(2 * np.pi * 100.0) - 0.5 * MU ** 2 / 100.0 + np.log(0.1) - 0.1 * S2
+    w = np.exp(ll + lp - (ll + lp).max())
+    dA = (mu[1] - mu[0]) * (s2[1] - s2[0])
+    truth = dict(logz=math.log(w.sum() * dA) + (ll + lp).max(),
+                 m_mu=(w * MU).sum() / w.sum(), m_s2=(w * S2).sum() / w.sum())
+    truth["v_mu"] = (w * (MU - truth["m_mu"]) ** 2).sum() / w.sum()
+    truth["v_s2"] = (w * (S2 - truth["m_s2"]) ** 2).sum() / w.sum()
+
+    def batch_se(x):
+        b = int(math.sqrt(len(x)))
+        means = x[:b * (len(x) // b)].reshape(b, -1).mean(axis=1)
+        return means.std(ddof=1) / math.sqrt(b)
+
+    z = {k: [] for k in ("m_mu", "m_s2", "v_mu", "v_s2")}
+    logzs = []
+    for seed in range(1, 6):
+        pt = PT(nChains=8, nScans=1000, adaptFraction=0.5, random=seed, initialization="SCM")
+        pt.setSampledModel(spec)
+        res = pt.performInference()
+        assert sum(r["nScans"] for r in res["rounds"]) == 1001
+        s = res["samples"][-500:, 0, :]              # the final, non-adaptive round
+        for name, x, t in (("m_mu", s[:, 0], truth["m_mu"]), ("m_s2", s[:, 1], truth["m_s2"]),
+                           ("v_mu", (s[:, 0] - s[:, 0].mean()) ** 2, truth["v_mu"]),
+                           ("v_s2", (s[:, 1] - s[:, 1].mean()) ** 2, truth["v_s2"])):
+            z[name].append((x.mean() - t) / batch_se(x))
+        logzs.append(res["rounds"][-1]["logZ"][0])
+        pt.engine.close()
+    for name, zs in z.items():
+        assert np.max(np.abs(zs)) < 5.0 and abs(np.mean(zs)) < 2.5, (name, zs)
+    assert abs(np.mean(logzs) - truth["logz"]) < 4 * max(np.std(logzs, ddof=1) / math.sqrt(5), 0.02), (logzs, truth["logz"])
