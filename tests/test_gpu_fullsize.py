@@ -202,3 +202,35 @@ def test_c1_reference_config_against_quadrature(datasets):
     for name, zs in z.items():
         assert np.max(np.abs(zs)) < 5.0 and abs(np.mean(zs)) < 2.5, (name, zs)
     assert abs(np.mean(logzs) - truth["logz"]) < 4 * max(np.std(logzs, ddof=1) / math.sqrt(5), 0.02), (logzs, truth["logz"])
+
+
+def test_c2_posterior_against_laplace(datasets):
+    """The bench workload end to end (100k x 32, 64 chains): the beta = 1 chain's posterior mean and standard
+    deviations against the Gaussian (Laplace) approximation at the MAP, which is accurate to O(1/n) here --
+    MAP and Hessian by Newton's method in numpy, independent of the engine."""
+    from blangsdk_b200.engine import Engine
+    spec = datasets.logistic_regression()
+    X, yv, v0 = spec["x"], spec["y"].astype(np.float64), spec["hyper"]["v0"]
+    w = np.zeros(X.shape[1])
+    for _ in range(30):                                   # Newton on the log posterior
+        p = 1.0 / (1.0 + np.exp(-(X @ w)))
+        g = X.T @ (yv - p) - w / v0
+        H = (X * (p * (1 - p))[:, None]).T @ X + np.eye(len(w)) / v0
+        step = np.linalg.solve(H, g)
+        w = w + step
+        if np.abs(step).max() < 1e-12:
+            break
+    sd = np.sqrt(np.diag(np.linalg.inv(H)))
+    eng = Engine(nChains=64, random=3)
+    eng.set_model(spec)
+    eng.initialize("COPIES")                              # every chain from w = 0, as in bench.py
+    eng.run_scans(120, want=())                           # burn-in
+    out = eng.run_scans(260, want=("samples",))
+    s = out["samples"][:, 0, :]
+    # autocorrelated draws: gate the mean with batch means, the spread with a generous band
+    b = 13
+    means = s[:b * (len(s) // b)].reshape(b, -1, s.shape[1]).mean(axis=1)
+    se = means.std(axis=0, ddof=1) / np.sqrt(b)
+    assert np.all(np.abs(s.mean(axis=0) - w) < 5 * se + 0.1 * sd), np.max(np.abs(s.mean(axis=0) - w) / sd)
+    assert np.all(s.std(axis=0) > 0.6 * sd) and np.all(s.std(axis=0) < 1.5 * sd)
+    eng.close()
