@@ -35,6 +35,7 @@ struct blangpt_handle {
   int logistic_threads = 0;       // CTA size of the C2 kernel: 0 = choose in set_model, or BLANGPT_LOGISTIC_THREADS=512|1024
   bool model_set = false, tables_valid = false;
   cudaStream_t stream = nullptr;  // nullptr = legacy default stream
+  double* swap_out = nullptr; int* swap_out_i = nullptr;   // one scan's outputs of blangpt_swap (split-phase path)
   bool own_stream = false;
 
   DevEngine E{};
@@ -1241,12 +1242,38 @@ extern "C" int blangpt_swap(blangpt_handle* h, const blangpt_scan_outputs* out) 
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
-  (void)out;
   CUDA_OK(h, cudaMemsetAsync(h->E.batch_counter, 0, sizeof(uint32_t) * h->cfg.nReplicas, h->stream));
   DevOut O{}; O.n_reals = h->n_reals; O.reversible = h->cfg.reversible;
-  int rc = launch_swap(h, O);
-  if (rc) return rc;
+  int rc;
+  const size_t M = (size_t)h->M_total, R = (size_t)h->cfg.nReplicas;
+  if (out) {   // this scan's per-chain outputs (one scan's worth of the run_scans layout); buffers are kept in the handle
+    if (out->intSamples) FAIL(h, BLANGPT_EUNSUPPORTED, "blangpt_swap: intSamples are recorded by run_scans only");
+    if (!h->swap_out) {
+      const size_t doubles = 2 * M + R * (size_t)std::max(1, h->n_reals), ints = 2 * M;
+      if ((rc = dev_alloc(h, &h->swap_out, doubles)) || (rc = dev_alloc(h, &h->swap_out_i, ints))) return rc;
+    }
+    if (out->energy) O.energy = h->swap_out;
+    if (out->logDensity) O.logdens = h->swap_out + M;
+    if (out->samples && h->n_reals) {
+      O.samples = h->swap_out + 2 * M;     // filled by the rank that owns the beta = 1 chain of a replica; else NaN
+      std::vector<double> nan(R * h->n_reals, std::nan(""));
+      CUDA_OK(h, cudaMemcpyAsync(O.samples, nan.data(), nan.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    }
+    if (out->nOutOfSupport) O.noos = h->swap_out_i;
+    if (out->swapIndicators) O.indicators = h->swap_out_i + M;
+  }
+  if ((rc = launch_swap(h, O))) return rc;
   h->n_scans++; h->scans_in_round++;
+  if (out) {
+    auto back = [&](void* host, const void* dev, size_t bytes) { if (host && dev) cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, h->stream); };
+    back(out->energy, O.energy, M * 8);
+    back(out->logDensity, O.logdens, M * 8);
+    back(out->nOutOfSupport, O.noos, M * 4);
+    back(out->swapIndicators, O.indicators, M * 4);
+    back(out->samples, O.samples, R * h->n_reals * 8);
+    return check_device_errors(h);   // synchronises the stream
+  }
   return BLANGPT_OK;
 }
 extern "C" int blangpt_synchronize(blangpt_handle* h) {

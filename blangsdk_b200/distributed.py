@@ -94,13 +94,21 @@ class ShardedEngine:
     def exchange(self):
         self._gather()
 
-    def swap(self):
-        self.engine._check(self.engine.L.blangpt_swap(self.engine.h, None))
+    def swap(self, want=()):
+        """DEO swap pass; `want` selects this scan's outputs (as Engine.run_scans, one scan)"""
+        e = self.engine
+        if not want:
+            e._check(e.L.blangpt_swap(e.h, None))
+            return None
+        so, bufs = e._outputs(1, tuple(w for w in want if not (w == "samples" and e.n_ints)))
+        import ctypes
+        e._check(e.L.blangpt_swap(e.h, ctypes.byref(so)))
+        return {k: v[0] for k, v in bufs.items()}
 
-    def scan(self):
+    def scan(self, want=()):
         self.explore()
         self.exchange()
-        self.swap()
+        return self.swap(want)
 
     def run_scans(self, n):
         for _ in range(n):

@@ -277,6 +277,9 @@ int blangpt_explore(blangpt_handle* h);
  *        1 = local send segment [localChains][4]                              */
 void* blangpt_table_ptr(blangpt_handle* h, int32_t which);
 int64_t blangpt_local_chains(const blangpt_handle* h, int64_t* first_slot);
+/* DEO swap pass on the replicated table.  `out` (nullable): this scan's energy / logDensity / nOutOfSupport /
+ * swapIndicators [nReplicas][nChains] and samples [nReplicas][nReals]; samples are filled by the rank that owns the
+ * replica's beta = 1 chain and are NaN elsewhere.  With `out` the call synchronises; with NULL it only enqueues. */
 int blangpt_swap(blangpt_handle* h, const blangpt_scan_outputs* out_one_scan_or_null);
 int blangpt_synchronize(blangpt_handle* h);
 

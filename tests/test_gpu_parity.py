@@ -255,10 +255,17 @@ def test_split_phase_equals_run_scans(datasets):
     from blangsdk_b200.engine import Engine
     spec = datasets.normal_meanvar(n=300)
     a = Engine(nChains=8, random=3); a.set_model(spec); a.initialize("FORWARD")
-    a.run_scans(9, want=())
+    want = ("energy", "logDensity", "nOutOfSupport", "swapIndicators", "samples")
+    ref = a.run_scans(9, want=want)
     b = Engine(nChains=8, random=3); b.set_model(spec); b.initialize("FORWARD")
     sh = ShardedEngine(b)
-    sh.prepare(); sh.run_scans(9); sh.synchronize()
+    sh.prepare()
+    for s in range(9):                       # per-scan outputs of the split-phase path == run_scans' batch outputs
+        got = sh.scan(want if s % 2 == 0 else ())
+        if got is not None:
+            for k in want:
+                assert np.array_equal(got[k], ref[k][s]), (k, s)
+    sh.synchronize()
     for p in range(8):
         assert np.array_equal(a.get_state(p)[0], b.get_state(p)[0])
     assert a.counters()["evals"] == b.counters()["evals"]
