@@ -692,18 +692,33 @@ struct LinRegFam {
     if (k < d.p) return normal_f2(0.0, d.v0, x);
     return (0.0 <= x && x <= d.smax) ? 0.0 : BPT_NEG_INF;         // ContinuousUniform.bl:16-19
   }
-  // this CTA's share of sum_i (res_i + delta * X[i][k])^2
+  // this CTA's share of sum_i (res_i + delta * X[i][k])^2; eight steps' loads are issued before their FMAs (the
+  // pass is two loads and four FMAs per pair: latency-, not bandwidth-bound)
   BPT_D double sum_sq(int k, double delta) const {
     const double* col = d.xt + (size_t)k * d.npad;
-    double s = 0.0;
-    for (int i = rr.lo + 2 * threadIdx.x; i < rr.hi; i += 2 * blockDim.x) {
-      if (i + 1 < rr.hi) {
-        const double2 r = *reinterpret_cast<const double2*>(res + i);
-        const double2 xv = *reinterpret_cast<const double2*>(col + i);
-        const double a = fma(delta, xv.x, r.x), b = fma(delta, xv.y, r.y);
-        s = fma(a, a, s); s = fma(b, b, s);
-      } else { const double a = fma(delta, col[i], res[i]); s = fma(a, a, s); }
+    const int n_pairs = (rr.hi - rr.lo) >> 1;
+    const double2* pr = reinterpret_cast<const double2*>(res + rr.lo);
+    const double2* px = reinterpret_cast<const double2*>(col + rr.lo);
+    const int T = blockDim.x;
+    double s0 = 0.0, s1 = 0.0;
+    int q = threadIdx.x;
+    for (; q + 7 * T < n_pairs; q += 8 * T) {
+      double2 r[8], xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { r[u] = pr[q + u * T]; xv[u] = px[q + u * T]; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const double a = fma(delta, xv[u].x, r[u].x), b = fma(delta, xv[u].y, r[u].y);
+        s0 = fma(a, a, s0); s1 = fma(b, b, s1);
+      }
     }
+    for (; q < n_pairs; q += T) {
+      const double2 r = pr[q], xv = px[q];
+      const double a = fma(delta, xv.x, r.x), b = fma(delta, xv.y, r.y);
+      s0 = fma(a, a, s0); s1 = fma(b, b, s1);
+    }
+    double s = s0 + s1;
+    if (((rr.hi - rr.lo) & 1) && threadIdx.x == 0) { const int i = rr.hi - 1; const double a = fma(delta, col[i], res[i]); s = fma(a, a, s); }
     return s;
   }
   // w_k: the n third blocks of Normal.bl; sigma: the n second and the n third blocks (Normal.bl:17-24)
