@@ -623,7 +623,15 @@ struct IidFam {
         else if (v != v) atomicOr(err, ERR_NAN);
         else pc += n;
       } else {
-        for (int i = rr.lo + t0; i < rr.hi; i += tn)
+        int i = rr.lo + t0;
+        for (; i + 3 * tn < rr.hi; i += 4 * tn) {      // four rows' loads in flight, same summation order
+          double yv[4], xv[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) { yv[u] = d.y[i + u * tn]; xv[u] = d.trials ? d.trials[i + u * tn] : 0.0; }
+#pragma unroll
+          for (int u = 0; u < 4; u++) acc_term(iid_law(d.dist, l, th, yv[u], xv[u]), acc, cnt, err);
+        }
+        for (; i < rr.hi; i += tn)
           acc_term(iid_law(d.dist, l, th, d.y[i], d.trials ? d.trials[i] : 0.0), acc, cnt, err);
       }
     }
