@@ -14,7 +14,10 @@
  * (T/TestSDKNormalizations.java:20-45), cache == from-scratch density
  * (SampledModel.java:178-188), Ising log Z against exhaustive enumeration
  * (T/TestEndToEnd.xtend:139-167, factories/Exact.java:82-92) and the
- * Random123 Philox known-answer vectors.
+ * Random123 Philox known-answer vectors.  Families 6-9 (i.i.d. laws of R/distributions, the hierarchical rocket
+ * models of F/HierarchicalModel.bl and F/SimpleHierarchicalModel.bl, F/LinRegression.bl) are pinned the same way:
+ * every pmf sums / pdf integrates to 1 +- 1e-6, scipy's log-densities, and one exact-invariance test per law and
+ * family (T/TestSDKDistributions.xtend:12-18 -> R/validation/ExactInvarianceTest.java), tests/test_oracle_invariance.py.
  *
  * Third-party arithmetic that is NOT in /root/reference (bayonet 4.1.13,
  * build.gradle:35): lnGamma, logistic, logAdd, isClose, Random.  Restated
