@@ -198,3 +198,25 @@ def test_eit_rockets_latent(oracle):
     for j in range(prior_vals.shape[1]):
         p = stats.ks_2samp(prior_vals[:, j], post_vals[:, j]).pvalue
         assert p > ALPHA / prior_vals.shape[1], "statistic %d: KS p = %.2e" % (j, p)
+
+
+def test_scm_normalisation_estimate_is_unbiased(oracle):
+    """After T/TestSMCUnbiasness.xtend (exhaustive randomness on a two-state HMM there; Monte Carlo over seeds here): the
+    annealed-SMC estimate of Z produced by the SCM initialisation (AdaptiveJarzynski.java:91-233, adaptive temperatures,
+    stratified resampling) has expectation Z.  Model with a closed-form evidence: Poisson counts, Gamma(2, 1) prior."""
+    rng = np.random.default_rng(5)
+    y = rng.poisson(3.0, 12).astype(float)
+    a0, b0, S, n = 2.0, 1.0, y.sum(), len(y)
+    log_z = (a0 * math.log(b0) - math.lgamma(a0) + math.lgamma(a0 + S) - (a0 + S) * math.log(b0 + n)
+             - sum(math.lgamma(v + 1) for v in y))
+    spec = dict(family="iid", hyper=dict(dist="poisson", priors=[("gamma", a0, b0)]), y=y, trials=None)
+    m = oracle.Model(spec)
+    ratios = []
+    for seed in range(400):
+        pt = oracle.PT(m, nChains=2, seed=seed)
+        rs = pt.initialize_scm(nParticles=30, threshold=0.8)
+        ratios.append(math.exp(rs["logNormEstimate"] - log_z))
+    ratios = np.array(ratios)
+    se = ratios.std(ddof=1) / math.sqrt(len(ratios))
+    assert abs(ratios.mean() - 1.0) < 4 * se + 1e-3, (ratios.mean(), se)
+    assert se < 0.05                        # and it is a usable estimator, not just an unbiased one
