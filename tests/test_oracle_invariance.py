@@ -220,3 +220,37 @@ def test_scm_normalisation_estimate_is_unbiased(oracle):
     se = ratios.std(ddof=1) / math.sqrt(len(ratios))
     assert abs(ratios.mean() - 1.0) < 4 * se + 1e-3, (ratios.mean(), se)
     assert se < 0.05                        # and it is a usable estimator, not just an unbiased one
+
+
+def test_forward_generators_moments(oracle):
+    """After T/TestMoments.java:166-171 (3 sigma / sqrt(n) on i.i.d. draws): the beta = 0 chain of a PT run is an exact
+    prior draw every scan (SampledModel.forwardSample), so its states over many scans are i.i.d. from the priors; their
+    first two moments must match the closed forms of Normal, Gamma, Exponential, Beta, Uniform, Dirichlet and Poisson."""
+    n = 6000
+    def prior_draws(spec, n_chains=2):
+        pt = oracle.PT(oracle.Model(spec), nChains=n_chains, seed=17)
+        pt.initialize(oracle.INIT_FORWARD)
+        re, it = [], []
+        for _ in range(n):
+            pt.scan()
+            r, i = pt.get_state(n_chains - 1)
+            re.append(r.copy()); it.append(i.copy())
+        return np.array(re), np.array(it)
+    def check(x, mean, var, what):
+        se_m = math.sqrt(var / len(x))
+        assert abs(x.mean() - mean) < 4 * se_m, (what, x.mean(), mean)
+        assert abs(x.var() - var) < 0.12 * var + 1e-12, (what, x.var(), var)
+    y = np.array([1.0, 2.0])
+    re, _ = prior_draws(dict(family="iid", hyper=dict(dist="studentt", priors=[("gamma", 2.5, 0.7), ("normal", -1.0, 4.0), ("exponential", 0.4)]), y=y, trials=None))
+    check(re[:, 0], 2.5 / 0.7, 2.5 / 0.49, "gamma"); check(re[:, 1], -1.0, 4.0, "normal"); check(re[:, 2], 2.5, 6.25, "exponential")
+    re, _ = prior_draws(dict(family="iid", hyper=dict(dist="negbinomial", priors=[("gamma", 0.6, 1.5), ("uniform", 0.2, 0.9)]), y=y, trials=None))
+    check(re[:, 0], 0.4, 0.6 / 2.25, "gamma, shape < 1"); check(re[:, 1], 0.55, 0.49 / 12, "uniform")
+    re, _ = prior_draws(dict(family="iid", hyper=dict(dist="geometric", priors=[("beta", 2.0, 3.0)]), y=y, trials=None))
+    check(re[:, 0], 0.4, 6.0 / (25 * 6), "beta")
+    re, _ = prior_draws(dict(family="mixture", hyper=dict(K=3, m0=0.5, v0=2.0, gshape=2.0, grate=2.0, conc=1.0), y=y))
+    check(re[:, 0], 0.5, 2.0, "mixture mean"); check(re[:, 3], 1.0, 0.5, "mixture variance (gamma)")
+    check(re[:, 6], 1.0 / 3, 2.0 / (9 * 4), "dirichlet(1,1,1) coordinate")
+    assert np.allclose(re[:, 6:9].sum(axis=1), 1.0)
+    re, it = prior_draws(dict(family="rockets_latent", hyper=dict(rate_a=1.0, rate_b=1.0, pois_mean=2.0), y=np.array([0, 1])))
+    check(it[:, 0].astype(float), 2.0, 2.0, "poisson"); check(re[:, 0], 1.0, 1.0, "exponential(1)")
+    assert np.all((re[:, 2:] > 0) & (re[:, 2:] < 1))
