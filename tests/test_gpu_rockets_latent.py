@@ -194,3 +194,19 @@ def test_rockets_latent_counts_posterior(tmp_path, datasets):
             cond.append((w * Ls).sum() / w.sum())
         assert abs(L[g, h:].mean() - np.mean(cond)) < 0.2, (g, k, L[g, h:].mean(), np.mean(cond))
     pt.engine.close()
+
+
+def test_scm_zero_over_zero_ratio_is_the_references_error(oracle, datasets):
+    """After T/runtime/TestSampledModel.java: with the support not annealed, prior draws whose launch counts cannot
+    explain the failures have density zero at every beta > 0, the SCM weight update meets 0/0 and the reference throws
+    SampledModel.INVALID_LOG_RATIO; so do the oracle and the engine."""
+    from blangsdk_b200.engine import BlangPTError, Engine
+    spec = datasets.rockets_latent(13)
+    ref = oracle.PT(oracle.Model(spec), nChains=4, seed=1, annealSupport=False)
+    with pytest.raises(RuntimeError, match="Invalid logDensity ratio"):
+        ref.initialize_scm(nParticles=8, threshold=0.9)
+    eng = Engine(nChains=4, random=1, annealSupport=False)
+    eng.set_model(spec)
+    with pytest.raises(BlangPTError, match="Invalid logDensity ratio"):
+        eng.initialize("SCM", nParticles=8, threshold=0.9)
+    eng.close()
