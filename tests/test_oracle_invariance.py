@@ -254,3 +254,14 @@ def test_forward_generators_moments(oracle):
     re, it = prior_draws(dict(family="rockets_latent", hyper=dict(rate_a=1.0, rate_b=1.0, pois_mean=2.0), y=np.array([0, 1])))
     check(it[:, 0].astype(float), 2.0, 2.0, "poisson"); check(re[:, 0], 1.0, 1.0, "exponential(1)")
     assert np.all((re[:, 2:] > 0) & (re[:, 2:] < 1))
+
+
+def test_eit_has_power(oracle):
+    """After T/TestExactTest.xtend (the reference checks that its exact-invariance test rejects F/BadNormal.bl and
+    BadRealSliceSampler): the tests above must be able to fail.  A simulator that is unfaithful to the law by 30 % in
+    one parameter is rejected."""
+    priors, draw, _ = _IID_EIT["weibull"]
+    unfaithful = lambda r, t: t[0] * r.weibull(t[1] * 1.3, N_OBS)
+    spec = lambda y: dict(family="iid", hyper=dict(dist="weibull", priors=priors), y=np.asarray(y, dtype=float), trials=None)
+    with pytest.raises(AssertionError):
+        _eit(oracle, spec, draw, unfaithful, 2, [lambda t: t[0], lambda t: t[1], lambda t: t[0] * t[1]], 99)
