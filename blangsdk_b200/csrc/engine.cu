@@ -20,6 +20,7 @@
 #include "kernels.cuh"
 #include "ising.cuh"
 #include "schedule.hpp"
+#include "pool_host.hpp"
 
 using namespace bpt;
 
@@ -58,6 +59,7 @@ struct blangpt_handle {
   // SCM initialisation (PT.scmInit defaults, PT.java:68-72,507-515)
   int scm_particles = 100; double scm_threshold = 0.9, scm_resampling_ess = 0.5;
   double scm_log_norm = std::nan(""); int scm_n_temperatures = 0, scm_n_resamplings = 0;
+  PoolState* pool = nullptr;      // pool exploration kernel (pool.cuh): every SM serves every chain; null = not used
 };
 
 #define FAIL(h, code, ...) do { set_error((h), __VA_ARGS__); return (code); } while (0)
@@ -124,6 +126,7 @@ extern "C" void blangpt_destroy(blangpt_handle* h) {
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
+  pool_destroy(h->pool); h->pool = nullptr;
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -132,6 +135,7 @@ extern "C" int blangpt_n_reals(const blangpt_handle* h) { return h ? h->n_reals 
 extern "C" int blangpt_n_ints(const blangpt_handle* h) { return h ? h->n_ints : -1; }
 extern "C" int blangpt_n_samplers(const blangpt_handle* h) { return h ? h->n_samplers : -1; }
 extern "C" int blangpt_ctas_per_chain(const blangpt_handle* h) { return h ? h->G : -1; }
+extern "C" int blangpt_kernel_variant(const blangpt_handle* h) { return h ? (h->pool ? 1 : 0) : -1; }
 
 // ---------------------------------------------------------------------------
 // launches
@@ -166,6 +170,12 @@ static int launch_explore(blangpt_handle* h, int mode) {
     case BLANGPT_FAM_LINREG: return launch_explore_t<LinRegFam>(h, h->linreg, mode);
     case BLANGPT_FAM_ROCKETS_LATENT: return launch_explore_t<RocketsLatentFam>(h, h->rockets, mode);
     case BLANGPT_FAM_LOGISTIC:
+      if (h->pool) {   // persistent pool kernel: all SMs serve all chains (pool.cuh)
+        const int prc = pool_launch_logistic(h->pool, h->E, h->logistic, mode, h->stream);
+        if (prc != 0) FAIL(h, BLANGPT_ECUDA, "pool launch failed: %s", cudaGetErrorString((cudaError_t)prc));
+        h->n_launches++;
+        return 0;
+      }
       if (h->logistic_l2ahead) {   // per-chain caches larger than the L2: they stream from HBM.  1024 threads per CTA
         // (8 warps per scheduler hide the latency: 313 vs 356 ms per scan at 1024 chains) plus L2 prefetch hints
         LogisticFamT<1024, 1, 3>::Data d2; memcpy(&d2, &h->logistic, sizeof d2);
@@ -219,6 +229,8 @@ static int check_device_errors(blangpt_handle* h) {
     FAIL(h, BLANGPT_ENUMERIC, "Slice diverged to infinity. Possible cause is that a variable has no distribution attached to it, i.e. the model is improper.");
   if (err & ERR_INT_SLICE_EMPTY)
     FAIL(h, BLANGPT_ENUMERIC, "Invalid arguments: the integer slice sampler found no point of non-zero density in its window (the state it started from has zero density; Generators.discreteUniform throws in the reference). Initialise with SCM or from a feasible state.");
+  if (err & ERR_POOL_TIMEOUT)
+    FAIL(h, BLANGPT_ECUDA, "pool kernel: a wait inside the persistent exploration kernel timed out (aborted instead of hanging)");
   if ((err & ERR_NAN) && !h->cfg.treatNaNAsNegativeInfinity)
     FAIL(h, BLANGPT_ENUMERIC, "Factors should not return NaN. Use NEGATIVE_INFINITY to forbid configurations. If you are sure this NaN is OK, you can use the option 'treatNaNAsNegativeInfinity'.");
   return 0;
@@ -532,6 +544,15 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
     const size_t x_bytes = (size_t)h->logistic.npad * h->logistic.p * sizeof(double);
     h->logistic_l2ahead = h->logistic_threads == 1024 && l2 > 0 && (cache_bytes + x_bytes) > (size_t)l2 / 4 * 3;
     if (const char* t = getenv("BLANGPT_L2AHEAD")) h->logistic_l2ahead = atoi(t) != 0;
+    // Pool kernel (pool.cuh) when there are enough chains to keep every SM busy with other chains' rows while one
+    // chain's request is in flight; an explicit ctasPerChain asks for the cluster kernel.  BLANGPT_POOL=0/1 overrides.
+    const int64_t local_chains = h->M_total / c.worldSize;
+    bool want_pool = local_chains >= 24 && rows >= 16384 && c.ctasPerChain == 0;
+    if (const char* t = getenv("BLANGPT_POOL")) want_pool = atoi(t) != 0;
+    if (want_pool) {
+      const int prc = pool_create(&h->pool, (int)local_chains, c.device);
+      if (prc > 0) FAIL(h, BLANGPT_ECUDA, "pool setup failed: %s", cudaGetErrorString((cudaError_t)prc));
+    }
   }
   if (h->G != 1 && h->G != 2 && h->G != 4 && h->G != 8) FAIL(h, BLANGPT_EINVAL, "ctasPerChain must be 1, 2, 4 or 8");
   if ((rc = alloc_engine(h))) return rc;

@@ -65,11 +65,11 @@ BPT_D void acc_term(double t, double& s, int& c, int* err) {
 // (series to rr^5, truncation < 1e-17); the table holds the log of the value really multiplied by, so the
 // identity is exact up to rounding.  No division, no reciprocal; 25 fp64 instructions per row.
 // {-64 log2(e), 1.5*2^52, -ln2/64 hi (21 low bits zero: m * hi exact), -ln2/64 lo}
-__constant__ double kLgtK[4] = {-92.33248261689366, 6755399441055744.0, -0.01083042469326756, -2.9815858269852933e-12};
-__constant__ double kLgtExpC[6] = {   // 1/5! .. 1/0!
+static __constant__ double kLgtK[4] = {-92.33248261689366, 6755399441055744.0, -0.01083042469326756, -2.9815858269852933e-12};
+static __constant__ double kLgtExpC[6] = {   // 1/5! .. 1/0!
     8.33333333333333333333e-03, 4.16666666666666666667e-02, 1.66666666666666666667e-01, 0.5, 1.0, 1.0};
-__constant__ double kLgtLogC[4] = {0.2, -0.25, 3.33333333333333333333e-01, -0.5};
-__constant__ double kLgtExpTabC[64] = {
+static __constant__ double kLgtLogC[4] = {0.2, -0.25, 3.33333333333333333333e-01, -0.5};
+static __constant__ double kLgtExpTabC[64] = {
     1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
     1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
     1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
@@ -86,7 +86,7 @@ __constant__ double kLgtExpTabC[64] = {
     1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
     1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
     1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
-__constant__ double2 kLgtLogTabC[256] = {
+static __constant__ double2 kLgtLogTabC[256] = {
     {0.9980506822612085, 0.0019512201312618048}, {0.9941747572815534, 0.0058422756242284025},
     {0.9903288201160542, 0.00971824946892134}, {0.9865125240847784, 0.013579258126380866},
     {0.982725527831094, 0.01742541671385917}, {0.9789674952198852, 0.021256839025415152},

@@ -349,7 +349,7 @@ BPT_D void swap_replica(const DevEngine& E, const DevStats& St, const DevOut& O,
   }
 }
 
-__global__ void swap_kernel(DevEngine E, DevStats St, DevOut O) { swap_replica(E, St, O, blockIdx.x); }
+static __global__ void swap_kernel(DevEngine E, DevStats St, DevOut O) { swap_replica(E, St, O, blockIdx.x); }
 
 // Fused kernel for many small models (config C5: thousands of independent replicas, a few chains each):
 // one CTA per replica, one WARP per chain (reductions are shuffles only), and the whole scan loop --
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(1024) replica_kernel(DevEngine E, DevStats St,
 }
 
 // energy "before" of the next scan = current table (called after an evaluation-only pass)
-__global__ void prime_prev_kernel(DevEngine E, DevStats St) {
+static __global__ void prime_prev_kernel(DevEngine E, DevStats St) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < E.R * E.N) {
     E.prev_loglik[i] = E.table[(size_t)i * 4];
@@ -418,7 +418,7 @@ __global__ void prime_prev_kernel(DevEngine E, DevStats St) {
 }
 
 // ParallelTempering.setAnnealingParameters :197-204 + Paths.initPaths :131-139
-__global__ void reset_round_kernel(DevEngine E, DevStats St) {
+static __global__ void reset_round_kernel(DevEngine E, DevStats St) {
   const int rep = blockIdx.x, N = E.N;
   const size_t base = (size_t)rep * N;
   for (int p = threadIdx.x; p < N; p += blockDim.x) {

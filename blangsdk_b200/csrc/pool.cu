@@ -1,0 +1,107 @@
+// pool.cu -- host side of the pool exploration kernel (see pool.cuh for the design).
+#include "pool_host.hpp"
+#include "pool.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <algorithm>
+
+namespace bpt {
+
+struct PoolState {
+  PoolCtl ctl{};
+  void* control = nullptr;      // requests | result slots | finished | abort: zeroed before every launch
+  size_t control_bytes = 0;
+  void* results = nullptr;      // wbuf
+  unsigned long long* prof = nullptr; int launches = 0;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int pool_create(PoolState** out, int chains, int device) {
+  *out = nullptr;
+  int sms = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) return (int)e;
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_kernel<LogisticPool>, kPoolThreads, 0);
+  if (e != cudaSuccess) return (int)e;
+  const int n_ctrl = (chains + kPoolWarps - 1) / kPoolWarps;   // controller CTAs: one chain per warp
+  const int n_work = sms - n_ctrl;                             // worker CTAs: one slab of rows each
+  if (!coop || per_sm < 1 || n_work < sms / 2 || chains > kPoolMaxChains || n_work > 32 * kPoolMaxSlotsPerLane) return 0;
+  PoolState& ps = *new PoolState();
+  const size_t C = (size_t)chains;
+  // control block (zeroed before every launch): requests, result slots, finished counter, abort flag
+  size_t off = 0;
+  const size_t o_reqa = off; off += align_up(C * sizeof(PoolHalf), 256);
+  const size_t o_reqb = off; off += align_up(C * sizeof(PoolHalf), 256);
+  const size_t o_slot = off; off += C * n_work * sizeof(PoolHalf);
+  const size_t o_fin = off; off += sizeof(uint32_t);
+  const size_t o_abort = off; off += sizeof(int);
+  ps.control_bytes = align_up(off, 256);
+  if ((e = cudaMalloc(&ps.control, ps.control_bytes)) != cudaSuccess) { delete &ps; return (int)e; }
+  const size_t ro = align_up(C * kMaxParams * sizeof(double), 256);
+  if ((e = cudaMalloc(&ps.results, ro)) != cudaSuccess) { cudaFree(ps.control); delete &ps; return (int)e; }
+  cudaMemset(ps.results, 0, ro);
+  char* cb = (char*)ps.control;
+  PoolCtl& c = ps.ctl;
+  c.C = chains; c.n_cta = n_work; c.n_ctrl = n_ctrl;
+  c.reqa = (PoolHalf*)(cb + o_reqa); c.reqb = (PoolHalf*)(cb + o_reqb); c.slot = (PoolHalf*)(cb + o_slot);
+  c.finished = (uint32_t*)(cb + o_fin); c.abort_flag = (int*)(cb + o_abort);
+  c.wbuf = (double*)ps.results;
+  c.prof = nullptr;
+  if (getenv("BLANGPT_POOL_PROFILE")) {
+    cudaMalloc(&ps.prof, (size_t)sms * kPoolWarps * 8 * sizeof(unsigned long long));
+    cudaMemset(ps.prof, 0, (size_t)sms * kPoolWarps * 8 * sizeof(unsigned long long));
+    c.prof = ps.prof;
+  }
+  *out = &ps;
+  return 0;
+}
+
+// BLANGPT_POOL_PROFILE: where the warps' time went, summed over this handle's launches (stderr)
+static void pool_report(PoolState* ps) {
+  const int W = (ps->ctl.n_cta + ps->ctl.n_ctrl) * kPoolWarps;
+  std::vector<unsigned long long> h((size_t)W * 8);
+  cudaMemcpy(h.data(), ps->prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  double served = 0, cyc_serve = 0, cyc_total = 0, polls = 0, evals = 0, cyc_wait = 0, cyc_ctrl = 0; int n_ctrl = 0;
+  for (int w = 0; w < W; w++) {
+    const unsigned long long* q = &h[(size_t)w * 8];
+    served += q[0]; cyc_serve += q[1]; cyc_total += q[2]; polls += q[3];
+    if (q[4]) { evals += q[4]; cyc_wait += q[5]; cyc_ctrl += q[6]; n_ctrl++; }
+  }
+  fprintf(stderr, "[pool profile] launches %d  requests served %.0f  cycles/request %.0f  worker busy %.3f  polls/request %.2f\n",
+          ps->launches, served, cyc_serve / std::max(1.0, served), cyc_serve / std::max(1.0, cyc_total), polls / std::max(1.0, served));
+  fprintf(stderr, "[pool profile] controllers %d  evaluations %.0f  cycles/evaluation %.0f  of which waiting %.0f (%.3f)\n",
+          n_ctrl, evals, cyc_ctrl / std::max(1.0, evals), cyc_wait / std::max(1.0, evals), cyc_wait / std::max(1.0, cyc_ctrl));
+}
+
+void pool_destroy(PoolState* ps) {
+  if (!ps) return;
+  if (ps->prof) { pool_report(ps); cudaFree(ps->prof); }
+  if (ps->control) cudaFree(ps->control);
+  if (ps->results) cudaFree(ps->results);
+  delete ps;
+}
+
+int pool_launch_logistic(const PoolState* psp, const DevEngine& E, const LogisticFam::Data& D, int mode, cudaStream_t stream) {
+  const PoolState& ps = *psp;
+  const_cast<PoolState*>(psp)->launches++;
+  cudaError_t e = cudaMemsetAsync(ps.control, 0, ps.control_bytes, stream);
+  if (e != cudaSuccess) return (int)e;
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3((unsigned)(ps.ctl.n_cta + ps.ctl.n_ctrl));
+  lc.blockDim = dim3((unsigned)kPoolThreads);
+  lc.dynamicSmemBytes = 0;
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  e = cudaLaunchKernelEx(&lc, pool_kernel<LogisticPool>, E, D, ps.ctl, mode);
+  return (int)e;
+}
+
+}  // namespace bpt

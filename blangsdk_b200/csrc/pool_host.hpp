@@ -1,0 +1,19 @@
+// pool_host.hpp -- host interface of the pool exploration kernel (design: pool.cuh; compiled in pool.cu).
+// Deliberately free of device code so that engine.cu does not recompile when the kernel changes.
+#pragma once
+#include <cuda_runtime.h>
+#include "kernels.cuh"
+
+namespace bpt {
+
+struct PoolState;   // opaque: global-memory request / result blocks of one handle
+
+// Allocates the pool for `chains` local chains on `device`.  Returns 0 and *out != nullptr on success; 0 and
+// *out == nullptr when the pool cannot serve this shape (no cooperative launch, too many chains per SM);
+// a cudaError_t (> 0) when an allocation fails.
+int pool_create(PoolState** out, int chains, int device);
+void pool_destroy(PoolState* ps);
+// one launch = one exploration pass (mode: ExploreMode) of every local chain; returns a cudaError_t
+int pool_launch_logistic(const PoolState* ps, const DevEngine& E, const LogisticFam::Data& D, int mode, cudaStream_t stream);
+
+}  // namespace bpt

@@ -81,7 +81,7 @@ class InferenceSummary(C.Structure):
 
 EXPORTS = [
     "blangpt_default_config", "blangpt_create", "blangpt_destroy", "blangpt_last_error", "blangpt_set_model",
-    "blangpt_n_reals", "blangpt_n_ints", "blangpt_n_samplers", "blangpt_ctas_per_chain", "blangpt_set_ladder", "blangpt_get_ladder",
+    "blangpt_n_reals", "blangpt_n_ints", "blangpt_n_samplers", "blangpt_ctas_per_chain", "blangpt_kernel_variant", "blangpt_set_ladder", "blangpt_get_ladder",
     "blangpt_set_state", "blangpt_get_state", "blangpt_initialize", "blangpt_log_density", "blangpt_run_scans",
     "blangpt_get_round_stats", "blangpt_adapt", "blangpt_reset_round", "blangpt_rounds",
     "blangpt_perform_inference", "blangpt_counters", "blangpt_set_stream", "blangpt_evaluate", "blangpt_prime",
@@ -110,7 +110,7 @@ def load_library():
     L.blangpt_last_error.argtypes = [vp]
     L.blangpt_last_error.restype = C.c_char_p
     L.blangpt_set_model.argtypes = [vp, C.c_int32, C.POINTER(Array), C.c_int32, _dp, C.c_int32]
-    for f in ("blangpt_n_reals", "blangpt_n_ints", "blangpt_n_samplers", "blangpt_ctas_per_chain"):
+    for f in ("blangpt_n_reals", "blangpt_n_ints", "blangpt_n_samplers", "blangpt_ctas_per_chain", "blangpt_kernel_variant"):
         getattr(L, f).argtypes = [vp]
     L.blangpt_set_ladder.argtypes = [vp, _dp, C.c_int64]
     L.blangpt_get_ladder.argtypes = [vp, _dp, C.c_int64]
@@ -299,6 +299,7 @@ class Engine:
         self.n_ints = self.L.blangpt_n_ints(self.h)
         self.n_samplers = self.L.blangpt_n_samplers(self.h)
         self.ctas_per_chain = self.L.blangpt_ctas_per_chain(self.h)
+        self.kernel_variant = self.L.blangpt_kernel_variant(self.h)   # 0 = cluster per chain, 1 = pool
         self.family = fam
 
     def set_ladder(self, betas):

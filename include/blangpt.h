@@ -138,6 +138,10 @@ int blangpt_n_reals(const blangpt_handle* h);      /* latent reals per chain, de
 int blangpt_n_ints(const blangpt_handle* h);
 int blangpt_n_samplers(const blangpt_handle* h);   /* SampledModel.nPosteriorSamplers :155-158  */
 int blangpt_ctas_per_chain(const blangpt_handle* h); /* thread-block cluster size chosen for this model */
+/* which exploration kernel serves this model: 0 = one thread-block cluster per chain (kernels.cuh),
+ * 1 = the persistent pool kernel in which every SM serves every chain (pool.cuh; big-data families with
+ * enough chains; BLANGPT_POOL=0/1 in the environment overrides the choice at set_model time) */
+int blangpt_kernel_variant(const blangpt_handle* h);
 
 /* Ladder, descending, betas[replica][position]; position 0 is beta = 1
  * (ParallelTempering.setAnnealingParameters :183-205: sorts, requires betas[0]==1,
