@@ -26,7 +26,9 @@ int pool_create(PoolState** out, int chains, int device) {
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_kernel<LogisticPool>, kPoolThreads, 0);
+  e = cudaFuncSetAttribute(pool_kernel<LogisticPool>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolDynSmemBytes);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_kernel<LogisticPool>, kPoolThreads, kPoolDynSmemBytes);
   if (e != cudaSuccess) return (int)e;
   const int n_ctrl = (chains + kPoolWarps - 1) / kPoolWarps;   // controller CTAs: one chain per warp
   const int n_work = sms - n_ctrl;                             // worker CTAs: one slab of rows each
@@ -94,7 +96,7 @@ int pool_launch_logistic(const PoolState* psp, const DevEngine& E, const Logisti
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3((unsigned)(ps.ctl.n_cta + ps.ctl.n_ctrl));
   lc.blockDim = dim3((unsigned)kPoolThreads);
-  lc.dynamicSmemBytes = 0;
+  lc.dynamicSmemBytes = kPoolDynSmemBytes;
   lc.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeCooperative;

@@ -31,7 +31,7 @@
 
 namespace bpt {
 
-constexpr int kPoolThreads = 1024;        // 32 warps per CTA: controller warps (one per chain), one dispatcher, the rest workers
+constexpr int kPoolThreads = 768;         // 24 warps per CTA: controller warps (one per chain), one dispatcher, the rest workers
 constexpr int kPoolWarps = kPoolThreads / 32;
 constexpr int kPoolMaxChains = 1024;      // chains per GPU served by the pool (size of the per-CTA request ring; power of two)
 constexpr int kPoolMaxSlotsPerLane = 8;   // n_SM <= 256
@@ -96,6 +96,64 @@ struct PoolSmem {
   };
 };
 
+// Bank-conflict-free copies of the two lookup tables of logit_fast() (dynamic shared memory, 40 KB).  Lanes index
+// the tables with unrelated j, so the compact tables cost 5-7 shared-memory wavefronts per lookup and the LSU data
+// pipe, not the fp64 pipe, limited the kernel (ncu: l1tex data-pipe wavefronts 96 % of peak).  Here entry j is
+// replicated across a 128-byte row, and a lane always reads its own column of the row:
+//   log table: 256 rows x 8 copies of {1/c_j, -log(1/c_j)} (16 B): lanes l, l+8, l+16, l+24 share a column -> 4
+//              wavefronts, the minimum for 32 x 16 B;
+//   exp table:  64 rows x 16 copies of 2^(j/64) (8 B): lanes l, l+16 share a column -> 2 wavefronts, the minimum.
+constexpr uint32_t kPoolLogTabBytes = 256u * 128u, kPoolExpTabBytes = 64u * 128u;
+constexpr size_t kPoolDynSmemBytes = kPoolLogTabBytes + kPoolExpTabBytes;
+BPT_D void pool_tables_init(unsigned char* dyn) {
+  double2* lg = reinterpret_cast<double2*>(dyn);
+  double* ex = reinterpret_cast<double*>(dyn + kPoolLogTabBytes);
+  for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) lg[i] = kLgtLogTabC[i >> 3];
+  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) ex[i] = kLgtExpTabC[i >> 4];
+}
+// logit_fast<2>() on the replicated tables: tl / te = shared-memory address of this lane's column of the log / exp table
+BPT_D void logit_fast2_rep(double z0, double z1, double& s, uint32_t tl, uint32_t te_base) {
+  const double z[2] = {z0, z1};
+  double kd[2], r[2], p[2], te[2]; int m[2];
+#pragma unroll
+  for (int w = 0; w < 2; w++) {
+    const double a = fabs(z[w]);
+    kd[w] = fma(a, kLgtK[0], kLgtK[1]);     // magic add: low word = round(-a * 64 log2 e)
+    m[w] = __double2loint(kd[w]);
+    kd[w] -= kLgtK[1];
+    asm("ld.shared.f64 %0, [%1];" : "=d"(te[w]) : "r"(te_base + (((uint32_t)m[w] & 63u) << 7)));
+    r[w] = fma(kd[w], kLgtK[2], -a);
+    r[w] = fma(kd[w], kLgtK[3], r[w]);
+    p[w] = kLgtExpC[0];
+  }
+#pragma unroll
+  for (int i = 1; i < 6; i++)
+#pragma unroll
+    for (int w = 0; w < 2; w++) p[w] = fma(p[w], r[w], kLgtExpC[i]);
+  double q[2], rr[2], lc[2];
+#pragma unroll
+  for (int w = 0; w < 2; w++) {
+    const double tp = te[w] * p[w];
+    const double t = __hiloint2double(__double2hiint(tp) + ((m[w] >> 6) << 20), __double2loint(tp));
+    const double u = 1.0 + t;
+    const unsigned j = min(255u, (unsigned)(__double2hiint(u) - 0x3ff00000) >> 12);
+    double2 cj;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cj.x), "=d"(cj.y) : "r"(tl + (j << 7)));
+    rr[w] = fma(u, cj.x, -1.0);
+    lc[w] = cj.y;
+    q[w] = kLgtLogC[0];
+  }
+#pragma unroll
+  for (int i = 1; i < 4; i++)
+#pragma unroll
+    for (int w = 0; w < 2; w++) q[w] = fma(q[w], rr[w], kLgtLogC[i]);
+#pragma unroll
+  for (int w = 0; w < 2; w++) {
+    const double l = fma(rr[w] * rr[w], q[w], rr[w]) + lc[w];     // log1p(exp(-|z|))
+    s += fma(0.5, z[w] - fabs(z[w]), -l);                          // min(z,0) - log1p(exp(-|z|))
+  }
+}
+
 // integer form of logit_is_fast(): zs > -12 (to within one high-word step) and |zs| < 700; NaN and inf fail
 BPT_D bool logit_is_fast_bits(double zs) {
   const int hi = __double2hiint(zs);
@@ -118,9 +176,10 @@ struct LogisticPool {
   // the rare literal path of two rows (some lane of the warp has a row outside the lean range): out of line, so
   // that the hot loop stays straight-line code; results by value, so that the caller's accumulators stay in registers
   struct SlowPair { double s; int c; };
-  __device__ __noinline__ static SlowPair duo_slow(double s0, double za, double zb, const uint8_t* yp, int* err) {
+  __device__ __noinline__ static SlowPair duo_slow(double s0, double za, double zb, const uint8_t* yp, int* err, uint32_t tab) {
     SlowPair r; r.s = s0; r.c = 0;
-    logit_term(za, yp, r.s, r.c, err); logit_term(zb, yp + 1, r.s, r.c, err);
+    if (logit_is_fast_bits(za) && logit_is_fast_bits(zb)) { const double z[2] = {za, zb}; logit_fast<2>(z, r.s, tab); }   // as the hot loop
+    else { logit_term(za, yp, r.s, r.c, err); logit_term(zb, yp + 1, r.s, r.c, err); }
     return r;
   }
   template <bool FULL_WARP>
@@ -131,7 +190,7 @@ struct LogisticPool {
     logit_fast<2>(z, t, tab);
     if (__all_sync(FULL_WARP ? 0xffffffffu : __activemask(), ok)) { s = t; return; }
     if (ok) s = t;
-    else { const SlowPair r = duo_slow(s, za, zb, yp, err); s = r.s; c += r.c; }
+    else { const SlowPair r = duo_slow(s, za, zb, yp, err, tab); s = r.s; c += r.c; }
   }
 
   // PR_EVAL on rows [lo, hi) of chain c: sum_i logit_term(eta_i + delta * X[i][k]); COMMIT first applies
@@ -151,18 +210,43 @@ struct LogisticPool {
     const uint8_t* py = D.y + lo + 2 * lane;
     // loads as volatile asm: issued where they are written (the compiler otherwise sinks the prefetch to the end of
     // the step to save registers, which exposes the whole L2 latency every step)
-    auto ldg2 = [](const double2* p) { double2 v; asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p)); return v; };
+    extern __shared__ __align__(128) unsigned char pool_dyn[];
+    uint32_t tl = (uint32_t)__cvta_generic_to_shared(pool_dyn) + ((uint32_t)lane & 7u) * 16u;
+    uint32_t te = (uint32_t)__cvta_generic_to_shared(pool_dyn) + kPoolLogTabBytes + ((uint32_t)lane & 15u) * 8u;
+    asm volatile("" : "+r"(tl), "+r"(te));   // opaque: kept in registers instead of being re-derived per use
+    auto ldg2 = [](const double2* p) { return *p; };
     int j = 0;
     if (n_pairs >= 32) {
       double2 e = ldg2(pe), x = ldg2(px), q;
       if (COMMIT) q = ldg2(pp);
-      for (; j + 32 <= n_pairs; j += 32) {
-        if (COMMIT) { e.x = fma(dprev, q.x, e.x); e.y = fma(dprev, q.y, e.y); pe[j] = e; }
-        const double za = fma(delta, x.x, e.x), zb = fma(delta, x.y, e.y);
-        // e, x (and q) are dead from here on: the next step's rows are loaded into the same registers right away
-        // and have the whole step's arithmetic to arrive
-        if (j + 64 <= n_pairs) { e = ldg2(pe + j + 32); x = ldg2(px + j + 32); if (COMMIT) q = ldg2(pp + j + 32); }
-        duo<true>(za, zb, py + 2 * j, acc, cnt, err, tab);
+      // Blocks of up to 32 steps.  The inner loop is straight-line code with no branch but its own back edge and no
+      // call (so its constants stay in registers): a step whose range vote fails keeps the accumulator unchanged and
+      // sets its bit in `bad`; those steps (0.4 % on the bench) are redone out of line after the block.  The sum is
+      // therefore "lean steps in order, then literal steps in order" per block: a fixed order.
+      while (j + 32 <= n_pairs) {
+        const int j0 = j;
+        unsigned bad = 0u, bit = 1u;
+        const int j_end = min(n_pairs - 31, j0 + 32 * 32);
+        for (; j < j_end; j += 32, bit <<= 1) {
+          if (COMMIT) { e.x = fma(dprev, q.x, e.x); e.y = fma(dprev, q.y, e.y); pe[j] = e; }
+          const double za = fma(delta, x.x, e.x), zb = fma(delta, x.y, e.y);
+          // e, x (and q) are dead from here on: the next step's rows are loaded into the same registers right away
+          // and have the whole step's arithmetic to arrive
+          if (j + 64 <= n_pairs) { e = ldg2(pe + j + 32); x = ldg2(px + j + 32); if (COMMIT) q = ldg2(pp + j + 32); }
+          const bool ok = logit_is_fast_bits(za) && logit_is_fast_bits(zb);
+          double t = acc;
+          logit_fast2_rep(za, zb, t, tl, te);
+          const bool all = __all_sync(0xffffffffu, ok);
+          acc = all ? t : acc;
+          bad |= all ? 0u : bit;
+        }
+        while (bad) {
+          const int jb = j0 + 32 * (__ffs(bad) - 1);
+          bad &= bad - 1u;
+          const double2 eb = pe[jb], xb = px[jb];       // eta already holds the committed value
+          const SlowPair r = duo_slow(acc, fma(delta, xb.x, eb.x), fma(delta, xb.y, eb.y), py + 2 * jb, err, tab);
+          acc = r.s; cnt += r.c;
+        }
       }
     }
     if (j + lane < n_pairs) {     // ragged rest (last SM only)
@@ -474,6 +558,10 @@ pool_kernel(DevEngine E, typename PF::Data D, PoolCtl pc, int mode) {
   if ((int)blockIdx.x >= pc.n_ctrl) for (int i = tid; i < pc.C; i += blockDim.x) sm.seen[i] = 0;
   if (tid == 0) { sm.q.head = 0; sm.q.tail = 0; sm.q.done = 0; }
   logit_table_init();
+  {
+    extern __shared__ __align__(128) unsigned char pool_dyn[];
+    if ((int)blockIdx.x >= pc.n_ctrl) pool_tables_init(pool_dyn);
+  }
   __syncthreads();
   // The first n_ctrl CTAs only run samplers (one chain per warp), the others only serve rows: an SM that hosted
   // both was slower than its peers (one warp fewer, the sampler's code in its instruction cache), and every
