@@ -36,7 +36,12 @@ if ROOT not in sys.path:
 
 N_ROWS, N_FEATURES, CHAINS_PER_GPU = 100_000, 32, 64
 ALGO_BYTES_PER_EVAL = N_ROWS * (N_FEATURES * 8 + 1)      # one full pass over (x_i, y_i)
-KERNEL_BYTES_PER_EVAL = N_ROWS * (8 + 8 + 1)             # what the eta-cached kernel must move: eta_i, X[i][k], y_i
+KERNEL_BYTES_PER_EVAL = N_ROWS * (8 + 8)                 # what the eta-cached kernel moves per evaluation: eta_i, X[i][k]
+# fp64-pipe instructions (DFMA + DADD + DMUL [+ DSETP]) per row of one evaluation, counted in the SASS of the inner
+# loop of each exploration kernel (profiles/sass_pool_inner_loop_r02.md, tools/sass_loops.py): the kernel's roofline is
+# the fp64 pipe (one fp64 instruction per lane per 2 cycles per SM sub-partition), not HBM -- the rows come from L2.
+FP64_INSTR_PER_ROW = {1: ("pool_kernel<LogisticPool>", 22), 0: ("explore_kernel<LogisticFam>", 26)}
+NRPT_SCANS = 400                                          # scans of the adaptive NRPT run that measures round trips/s
 METRIC = "annealed log-density evals/s (NRPT, logistic 100k x 32, 64 chains/GPU)"
 UNIT = "evals/s"
 
@@ -269,37 +274,62 @@ def run_gpu(args):
                        "run_scans(%d) with per-scan outputs copied D2H + counters, wall clock, median of 3 "
                        "complete repetitions; N independent 64-chain engines when N > 1" % k_e2e}
 
+    # ---- NRPT quality of the same workload: adaptive rounds, then round trips/s of the final round ----
+    nrpt = None
+    if not args.no_nrpt and world == 1:
+        e3 = Engine(nChains=n_chains, random=5, device=local_rank, ctasPerChain=args.ctas)
+        e3.set_model(spec)
+        e3.initialize("COPIES")
+        t0 = time.perf_counter()
+        res = e3.perform_inference(args.nrpt_scans, 0.5, want=())
+        wall_nrpt = time.perf_counter() - t0
+        last = res["rounds"][-1]
+        nrpt = {"what": "PT.performInference(nScans=%d, adaptFraction=0.5), COPIES init, same workload; figures of the final "
+                        "(non-adaptive) round: round trips = Paths.nRejuvenations (ptanalysis/Paths.xtend:26-50), rate = "
+                        "count / that round's wall time (PT.java:451-461 reports the same count per scan)" % args.nrpt_scans,
+                "rounds": [r["nScans"] for r in res["rounds"]], "final_round_scans": last["nScans"],
+                "final_round_s": last["millis"] * 1e-3, "round_trips": int(last["roundTrips"][0]),
+                "round_trips_per_s": float(last["roundTrips"][0]) / (last["millis"] * 1e-3),
+                "Lambda": float(last["Lambda"][0]), "mean_swap_accept": float(last["meanAccept"][0]),
+                "min_swap_accept": float(last["minAccept"][0]), "logZ_stepping_stone": float(last["logZ"][0]),
+                "wall_s": wall_nrpt}
+        e3.close()
+
     if rank == 0:
         peak, peak_src = read_peaks()
         evals_per_launch = evals / max(1, args.steps * world)
         explore_s = ms_explore * 1e-3 / args.steps
-        achieved = evals_per_launch * ALGO_BYTES_PER_EVAL / explore_s / 1e9
-        achieved_kernel = evals_per_launch * KERNEL_BYTES_PER_EVAL / explore_s / 1e9
         try:
-            fp64_peak = microbench(0, local_rank)
-            term_peak = microbench(1, local_rank)
+            fp64_peak = microbench(0, local_rank)          # measured DFMA rate of this GPU, TFLOP/s (2 flop per FMA)
         except Exception:
-            fp64_peak = term_peak = None
-        terms_per_s = evals_per_launch * N_ROWS / explore_s
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+            fp64_peak = None
+        kernel_name, per_row = FP64_INSTR_PER_ROW[eng.kernel_variant]
+        rows_per_s = evals_per_launch * N_ROWS / explore_s
+        achieved_tf = rows_per_s * per_row * 2 / 1e12        # every fp64-pipe instruction counted as one FMA issue slot
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "traffic_r02.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        roofline = {"bound": "hbm", "kernel": "explore_kernel<LogisticFam>", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_eval": ALGO_BYTES_PER_EVAL, "evals_per_launch": evals_per_launch,
-                    "ms_per_launch": explore_s * 1e3,
-                    "note": "achieved uses SURVEY 8(d)'s 25.7 MB per evaluation (a full pass over X,y). The kernel "
-                            "keeps eta = X.w per chain, so one evaluation moves 17 B/row (kernel_bytes_per_eval) and "
-                            "X/eta stay L2-resident: frac > 1 is expected and the binding resource is the fp64 pipe "
-                            "(see compute).",
-                    "kernel_bytes_per_eval": KERNEL_BYTES_PER_EVAL, "achieved_kernel_GBps": achieved_kernel,
-                    "frac_kernel_bytes": achieved_kernel / peak,
-                    "compute": {"bound": "fp64 exp/log/div (logistic row term)", "achieved_terms_per_s": terms_per_s,
-                                "peak_terms_per_s": term_peak,
-                                "frac": (terms_per_s / term_peak) if term_peak else None,
-                                "fp64_fma_tflops_measured": fp64_peak}}
+                tj = json.load(f)
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+        algo_gbps = evals_per_launch * ALGO_BYTES_PER_EVAL / explore_s / 1e9
+        roofline = {"bound": "fp64", "kernel": kernel_name, "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": (achieved_tf / fp64_peak) if fp64_peak else None,
+                    "peak_source": "fp64 FMA rate measured on this GPU in this run (blangpt_microbench(0)); "
+                                   "MEASURED_PEAKS.json has no fp64 figure",
+                    "how": "rows/s x %d fp64-pipe instructions per row (DFMA+DADD+DMUL in the inner-loop SASS) x 2, over the "
+                           "explore kernel's CUDA-event time; ncu sm__pipe_fp64_cycles_active of the same kernel: "
+                           "profiles/pool_logistic_r02.md" % per_row,
+                    "fp64_instr_per_row": per_row, "rows_per_s": rows_per_s, "evals_per_launch": evals_per_launch,
+                    "ms_per_launch": explore_s * 1e3, "traffic": traffic, "traffic_source": traffic_src,
+                    "hbm_side": {"note": "SURVEY 8(d) counts one full pass over X,y (25.7 MB) per evaluation; the engine keeps "
+                                         "eta = X.w per chain, moves 16 B/row per evaluation from L2 and is NOT HBM-bound: the "
+                                         "8(d) figure is far above 1 x HBM peak and is reported here only as the survey asks",
+                                 "algorithmic_bytes_per_eval": ALGO_BYTES_PER_EVAL, "algorithmic_GBps": algo_gbps,
+                                 "hbm_peak_GBps": peak, "hbm_peak_source": peak_src,
+                                 "algorithmic_x_of_hbm_peak": algo_gbps / peak,
+                                 "kernel_bytes_per_eval": KERNEL_BYTES_PER_EVAL,
+                                 "kernel_L2_GBps": evals_per_launch * KERNEL_BYTES_PER_EVAL / explore_s / 1e9}}
         cpu_v, cpu_cores, cpu_desc, _ = cpu_sample(spec, 8.0) if not args.no_cpu else (None, 0, "skipped", 0)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -308,6 +338,8 @@ def run_gpu(args):
                            "l2": "flushed between timed steps (256 MiB write)", "ctas_per_chain": eng.ctas_per_chain,
                            "parallelism": "chain-sharded x%d" % world},
                 "scans_per_s": 1e3 * args.steps / ms_total, "evals": evals, "wall_s_timed_region": wall,
+                "kernel_variant": "pool" if eng.kernel_variant == 1 else "cluster",
+                "round_trips_per_s": nrpt["round_trips_per_s"] if nrpt else None, "nrpt": nrpt,
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cpu_cores, "kind": "port", "sample": cpu_desc}}
         print(json.dumps(line))
@@ -327,6 +359,8 @@ def main():
     ap.add_argument("--chains-per-gpu", type=int, default=CHAINS_PER_GPU,
                     help="default 64 = BASELINE config 1; 128 = the north-star shape (1024 chains on 8 GPUs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-nrpt", action="store_true", help="skip the adaptive NRPT run that measures round trips/s")
+    ap.add_argument("--nrpt-scans", type=int, default=NRPT_SCANS)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.chains_per_gpu != CHAINS_PER_GPU:

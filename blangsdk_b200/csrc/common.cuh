@@ -21,7 +21,7 @@ namespace bpt {
 
 enum Purpose : uint32_t { P_MOVE = 0, P_SHUFFLE = 1, P_SWAP = 2, P_SWAPDIR = 3, P_FORWARD = 4, P_INIT = 5 };
 
-enum ErrBits : int { ERR_NAN = 1, ERR_SLICE_DIVERGED = 2, ERR_INT_SLICE_EMPTY = 4, ERR_POOL_TIMEOUT = 8 };
+enum ErrBits : int { ERR_NAN = 1, ERR_SLICE_DIVERGED = 2, ERR_INT_SLICE_EMPTY = 4, ERR_POOL_TIMEOUT = 8, ERR_PEER_TIMEOUT = 16 };
 
 BPT_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                           uint32_t out[4]) {

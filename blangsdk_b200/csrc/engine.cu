@@ -59,6 +59,10 @@ struct blangpt_handle {
   // SCM initialisation (PT.scmInit defaults, PT.java:68-72,507-515)
   int scm_particles = 100; double scm_threshold = 0.9, scm_resampling_ess = 0.5;
   double scm_log_norm = std::nan(""); int scm_n_temperatures = 0, scm_n_resamplings = 0;
+  // multi-GPU exchange (kernels.cuh PeerBox): this rank's mailbox allocation and the opened peer mappings
+  void* mailbox = nullptr; size_t mailbox_bytes = 0; size_t mail_record_bytes = 0;
+  std::vector<void*> peer_maps; bool peers_ready = false;
+  bool one_view() const { return cfg.worldSize == 1 || peers_ready; }   // this process sees every chain's record
   PoolState* pool = nullptr;      // pool exploration kernel (pool.cuh): every SM serves every chain; null = not used
 };
 
@@ -98,6 +102,7 @@ extern "C" const char* blangpt_last_error(const blangpt_handle* h) {
 extern "C" int blangpt_create(const blangpt_config* cfg, blangpt_handle** out) {
   if (!cfg || !out) { set_error(nullptr, "null argument"); return BLANGPT_EINVAL; }
   if (cfg->nChains < 1) { set_error(nullptr, "Number of tempering chains must be greater than zero."); return BLANGPT_EINVAL; }
+  if (!(cfg->nPassesPerScan >= 0.0) || std::isinf(cfg->nPassesPerScan)) { set_error(nullptr, "nPassesPerScan must be a finite number >= 0"); return BLANGPT_EINVAL; }
   if (cfg->nReplicas < 1 || cfg->worldSize < 1 || cfg->rank < 0 || cfg->rank >= cfg->worldSize) { set_error(nullptr, "bad nReplicas/rank/worldSize"); return BLANGPT_EINVAL; }
   if (cfg->worldSize > 1 && cfg->nReplicas != 1) { set_error(nullptr, "chain sharding (worldSize > 1) requires nReplicas == 1; shard replicas with one handle per rank"); return BLANGPT_EINVAL; }
   if (cfg->worldSize > 1 && cfg->nChains % cfg->worldSize != 0) { set_error(nullptr, "nChains must be a multiple of worldSize"); return BLANGPT_EINVAL; }
@@ -125,6 +130,8 @@ extern "C" void blangpt_destroy(blangpt_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
+  for (void* p : h->peer_maps) if (p) cudaIpcCloseMemHandle(p);
+  if (h->mailbox) cudaFree(h->mailbox);
   for (void* p : h->allocs) cudaFree(p);
   pool_destroy(h->pool); h->pool = nullptr;
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -162,7 +169,7 @@ static int launch_explore_t(blangpt_handle* h, const typename Fam::Data& D, int 
   return 0;
 }
 
-static int launch_explore(blangpt_handle* h, int mode) {
+static int launch_explore_local(blangpt_handle* h, int mode) {
   switch (h->family) {
     case BLANGPT_FAM_NORMAL: return launch_explore_t<NormalFam>(h, h->normal, mode);
     case BLANGPT_FAM_IID: return launch_explore_t<IidFam>(h, h->iid, mode);
@@ -200,6 +207,19 @@ static int launch_explore(blangpt_handle* h, int mode) {
   FAIL(h, BLANGPT_ESTATE, "no model set");
 }
 
+// One exploration pass of the local chains; with the multi-GPU exchange on, every chain's record is published to all
+// ranks by the kernel itself and gather_kernel completes this rank's replicated table on the same stream.
+static int launch_explore(blangpt_handle* h, int mode) {
+  if (h->peers_ready) h->E.peers.xseq++;
+  int rc = launch_explore_local(h, mode);
+  if (rc || !h->peers_ready) return rc;
+  const int64_t items = h->M_total + (int64_t)h->cfg.nReplicas * h->n_reals;
+  gather_kernel<<<(unsigned)std::min<int64_t>(64, (items + 127) / 128), 128, 0, h->stream>>>(h->E);
+  CUDA_OK(h, cudaGetLastError());
+  h->n_launches++;
+  return 0;
+}
+
 // the fused replica kernel applies to warp-capable families with small data, <= 32 chains, one process
 static bool use_fused(const blangpt_handle* h) {
   if (h->cfg.worldSize != 1 || h->cfg.nChains > 32) return false;
@@ -225,10 +245,16 @@ static int check_device_errors(blangpt_handle* h) {
   int err = 0;
   CUDA_OK(h, cudaMemcpyAsync(&err, h->E.err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  if (err) {   // reported once: the handle is usable again after the caller repairs the state (set_state / initialize)
+    CUDA_OK(h, cudaMemsetAsync(h->E.err, 0, sizeof(int), h->stream));
+    h->tables_valid = false;
+  }
   if (err & ERR_SLICE_DIVERGED)
     FAIL(h, BLANGPT_ENUMERIC, "Slice diverged to infinity. Possible cause is that a variable has no distribution attached to it, i.e. the model is improper.");
   if (err & ERR_INT_SLICE_EMPTY)
     FAIL(h, BLANGPT_ENUMERIC, "Invalid arguments: the integer slice sampler found no point of non-zero density in its window (the state it started from has zero density; Generators.discreteUniform throws in the reference). Initialise with SCM or from a feasible state.");
+  if (err & ERR_PEER_TIMEOUT)
+    FAIL(h, BLANGPT_ECUDA, "multi-GPU exchange: a peer's chain records did not arrive (a rank failed, or the ranks did not make the same sequence of calls)");
   if (err & ERR_POOL_TIMEOUT)
     FAIL(h, BLANGPT_ECUDA, "pool kernel: a wait inside the persistent exploration kernel timed out (aborted instead of hanging)");
   if ((err & ERR_NAN) && !h->cfg.treatNaNAsNegativeInfinity)
@@ -240,12 +266,12 @@ static int ensure_tables(blangpt_handle* h) {
   if (h->tables_valid) return 0;
   int rc = launch_explore(h, MODE_EVAL);
   if (rc) return rc;
-  if (h->cfg.worldSize == 1) {
+  if (h->one_view()) {
     prime_prev_kernel<<<(unsigned)((h->M_total + 255) / 256), 256, 0, h->stream>>>(h->E, h->St);
     CUDA_OK(h, cudaGetLastError());
     h->n_launches++;
   }
-  h->tables_valid = h->cfg.worldSize == 1;
+  h->tables_valid = h->one_view();
   return 0;
 }
 
@@ -295,6 +321,7 @@ static int alloc_engine(blangpt_handle* h) {
   E.key0 = (uint32_t)c.random; E.key1 = (uint32_t)(c.random >> 32);
   E.replica_offset = (uint32_t)c.replicaOffset;
   E.n_passes = c.nPassesPerScan; E.use_prior = c.usePriorSamples; E.anneal_support = c.annealSupport;
+  E.nan_neginf = c.treatNaNAsNegativeInfinity;
   E.beta_override = std::nan(""); E.steps_override = 0;
   E.s_max = h->family == BLANGPT_FAM_ISING ? 1 : std::max(1, h->n_samplers);
   double* ladder; int rc;
@@ -330,6 +357,13 @@ static int alloc_engine(blangpt_handle* h) {
   if ((rc = dev_alloc(h, &S.rejuv, c.nReplicas))) return rc;
   if ((rc = dev_alloc(h, &S.total_evals, 1))) return rc;
   if ((rc = dev_alloc(h, &S.oos_seen, c.nReplicas))) return rc;
+  if (c.worldSize > 1) {   // this rank's mailbox for the multi-GPU exchange (its own allocation: it is exported through CUDA IPC)
+    h->mail_record_bytes = (size_t)2 * M * 2 * sizeof(MailHalf);
+    h->mailbox_bytes = h->mail_record_bytes + (size_t)2 * c.nReplicas * std::max(1, h->n_reals) * sizeof(MailHalf);
+    CUDA_OK(h, cudaMalloc(&h->mailbox, h->mailbox_bytes));
+    CUDA_OK(h, cudaMemsetAsync(h->mailbox, 0, h->mailbox_bytes, h->stream));
+    if ((rc = dev_alloc(h, &E.peers.sample_buf, (size_t)c.nReplicas * std::max(1, h->n_reals)))) return rc;
+  }
   init_perm_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(E, h->family == BLANGPT_FAM_ISING ? 0 : h->n_samplers);
   CUDA_OK(h, cudaGetLastError());
   // default ladder: EquallySpaced
@@ -522,6 +556,9 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
       if (nh != 3) FAIL(h, BLANGPT_EINVAL, "ising: hyper (N, coupling, moment)");
       const int N = (int)hyper[0];
       if (N < 2 || (N & 1)) FAIL(h, BLANGPT_EUNSUPPORTED, "ising: the checkerboard sweep needs an even lattice side >= 2");
+      // the reference runs floor(nPassesPerScan * N*N) single-spin steps (SampledModel.java:249-256); the checkerboard
+      // kernel runs whole sweeps, so a fractional number of passes would silently be truncated
+      if (c.nPassesPerScan != std::floor(c.nPassesPerScan)) FAIL(h, BLANGPT_EUNSUPPORTED, "ising: nPassesPerScan must be a whole number (checkerboard sweeps); got %g", c.nPassesPerScan);
       h->ising.N = N; h->ising.coupling = hyper[1]; h->ising.moment = hyper[2];
       h->ising.p1 = 1.0 / (1.0 + exp(2.0 * hyper[2]));   // logistic(-2*moment), F/Ising.bl:28
       h->n_reals = 0; h->n_ints = N * N; h->n_samplers = N * N; rows = 1;
@@ -729,7 +766,7 @@ static int scm_permute(blangpt_handle* c, const std::vector<int>& anc) {
 }
 
 static int scm_initialize(blangpt_handle* h) {
-  if (h->cfg.worldSize != 1 || h->cfg.nReplicas != 1) FAIL(h, BLANGPT_EUNSUPPORTED, "SCM initialisation is implemented for one replica on one GPU");
+  if (h->cfg.nReplicas != 1) FAIL(h, BLANGPT_EUNSUPPORTED, "SCM initialisation is implemented for one replica per handle");
   const int N = h->cfg.nChains, P = h->scm_particles, as = h->cfg.annealSupport;
   // chains at beta == 0 (and every chain before it is overwritten) start from the prior, PT.java:311-315
   int rc = blangpt_initialize(h, BLANGPT_INIT_FORWARD);
@@ -737,12 +774,16 @@ static int scm_initialize(blangpt_handle* h) {
   // ---- child engine: P particles sharing the parent's device data ----
   blangpt_handle* c = new blangpt_handle();
   c->cfg = h->cfg; c->cfg.nChains = P; c->cfg.nReplicas = 1; c->cfg.usePriorSamples = 0;
+  c->cfg.worldSize = 1; c->cfg.rank = 0;   // every rank runs the same particle system (same seed) and keeps its own chains
   c->cfg.random = h->cfg.random ^ 0x53434D2D696E6974ULL;   // its own Philox key ("SCM-init")
   c->M_total = P; c->family = h->family; c->stream = h->stream; c->logistic_threads = h->logistic_threads;
   c->n_reals = h->n_reals; c->n_ints = h->n_ints; c->n_samplers = h->n_samplers;
   c->normal = h->normal; c->iid = h->iid; c->hier = h->hier; c->linreg = h->linreg; c->rockets = h->rockets; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising;
   c->betabin.chains_per_replica = P;
   auto fail = [&](int code) { for (void* p : c->allocs) cudaFree(p); if (code) h->error = c->error; delete c; return code; };
+  // CUDA calls on the child go through fail(): the child's allocations are released and its message reaches the caller
+#define SCM_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
+    set_error(c, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); return fail(BLANGPT_ECUDA); } } while (0)
   if (h->family == BLANGPT_FAM_LOGISTIC && (rc = dev_alloc(c, &c->logistic.eta, (size_t)c->logistic.npad * P))) return fail(rc);
   if (h->family == BLANGPT_FAM_LINREG && (rc = dev_alloc(c, &c->linreg.res, (size_t)c->linreg.npad * P))) return fail(rc);
   if (h->family == BLANGPT_FAM_ISING && (rc = dev_alloc(c, &c->ising.spins, (size_t)P * h->n_ints))) return fail(rc);
@@ -762,6 +803,7 @@ static int scm_initialize(blangpt_handle* h) {
   std::vector<double> w(P, 1.0 / P);
   double log_scaling = 0.0, temperature = 0.0;
   uint32_t iter = 0, master = 0;
+  int n_stalled = 0;
   const uint32_t k0 = (uint32_t)c->cfg.random, k1 = (uint32_t)(c->cfg.random >> 32);
   auto master_double = [&]() { Rng r(k0, k1, P_MASTER, 0u, master++, 0u); return r.next_double(); };
   h->scm_n_temperatures = 0; h->scm_n_resamplings = 0;
@@ -777,9 +819,16 @@ static int scm_initialize(blangpt_handle* h) {
       double next;
       const double at_one = objective(1.0);
       if (!ok) return fail((set_error(c, "Invalid logDensity ratio (0/0): this could be caused by a generate(rand){..} block not faithful with its laws{..} block."), BLANGPT_ENUMERIC));
-      if (at_one != at_one) next = std::max(temperature, 1e-10);
-      else next = objective(target) >= 0 ? target : pegasus_solve(objective, temperature, target, 1e-16, 100);
-      if (!(next > temperature)) next = target;     // guard against a stalled search (never reached in the tests)
+      if (at_one != at_one) {
+        // every particle is out of support: the reference re-proposes at max(temperature, 1e-10) until one comes back
+        // (AdaptiveTemperatureSchedule.java:54-60); bounded here instead of looping for ever
+        next = std::max(temperature, 1e-10);
+        if (++n_stalled > 100000) return fail((set_error(c, "SCM initialisation: every particle stayed out of support for 100000 consecutive temperatures"), BLANGPT_ENUMERIC));
+      } else {
+        n_stalled = 0;
+        next = objective(target) >= 0 ? target : pegasus_solve(objective, temperature, target, 1e-16, 100);
+        if (!(next > temperature)) next = target;   // numerical stall of the root search (never reached in the tests)
+      }
       // --- resamplingNeeded :139-147 / resample :149-154 (stratified) ---
       bool need = false;
       double ess_den = 0.0;
@@ -808,8 +857,8 @@ static int scm_initialize(blangpt_handle* h) {
         lsum = log_add(lsum, lw[i]);
       }
       c->E.beta_override = next;
-      CUDA_OK(c, cudaMemcpyAsync(c->E.scan_counter, &iter, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-      CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      SCM_OK(cudaMemcpyAsync(c->E.scan_counter, &iter, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      SCM_OK(cudaStreamSynchronize(c->stream));
       if ((rc = launch_explore(c, MODE_EXPLORE))) return fail(rc);
       if ((rc = scm_read_table(c, ps))) return fail(rc);
       for (int i = 0; i < P; i++) w[i] = exp(lw[i] - lsum);   // ParticlePopulation.buildDestructivelyFromLogWeights
@@ -822,17 +871,20 @@ static int scm_initialize(blangpt_handle* h) {
     double cum = 0.0; int pick = P - 1;
     for (int i = 0; i < P; i++) { cum += w[i]; if (u < cum) { pick = i; break; } }
     std::vector<double> reals(std::max(1, h->n_reals)); std::vector<int32_t> ints(std::max(1, h->n_ints));
-    if (h->n_reals) CUDA_OK(c, cudaMemcpy2D(reals.data(), 8, c->E.reals + pick, (size_t)P * 8, 8, h->n_reals, cudaMemcpyDeviceToHost));
+    if (h->n_reals) SCM_OK(cudaMemcpy2D(reals.data(), 8, c->E.reals + pick, (size_t)P * 8, 8, h->n_reals, cudaMemcpyDeviceToHost));
     if (h->n_ints) {
       std::vector<uint8_t> b(h->n_ints);
-      CUDA_OK(c, cudaMemcpy(b.data(), c->ising.spins + (size_t)pick * h->n_ints, b.size(), cudaMemcpyDeviceToHost));
+      SCM_OK(cudaMemcpy(b.data(), c->ising.spins + (size_t)pick * h->n_ints, b.size(), cudaMemcpyDeviceToHost));
       for (int q = 0; q < h->n_ints; q++) ints[q] = b[q];
     }
+    int owner_local = 0;
+    if (slot_of(h, 0, li, &owner_local) != 0) { h->error.clear(); continue; }   // that chain lives on another rank
     if ((rc = blangpt_set_state(h, 0, li, h->n_reals ? reals.data() : nullptr, h->n_ints ? ints.data() : nullptr))) return fail(rc);
   }
   h->scm_log_norm = log_scaling;
   h->n_launches += c->n_launches;
   fail(0);
+#undef SCM_OK
   h->tables_valid = false;
   return ensure_tables(h);
 }
@@ -860,12 +912,12 @@ extern "C" int blangpt_initialize(blangpt_handle* h, int32_t init_type) {
   if (init_type != BLANGPT_INIT_FORWARD) FAIL(h, BLANGPT_EINVAL, "unknown initialization");
   int rc = launch_explore(h, MODE_FORWARD_INIT);
   if (rc) return rc;
-  if (h->cfg.worldSize == 1) {
+  if (h->one_view()) {
     prime_prev_kernel<<<(unsigned)((h->M_total + 255) / 256), 256, 0, h->stream>>>(h->E, h->St);
     CUDA_OK(h, cudaGetLastError());
     h->n_launches++;
   }
-  h->tables_valid = h->cfg.worldSize == 1;
+  h->tables_valid = h->one_view();
   return check_device_errors(h);
 }
 
@@ -873,7 +925,7 @@ extern "C" int blangpt_log_density(blangpt_handle* h, double* out_logdens, doubl
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
-  if (h->cfg.worldSize > 1) FAIL(h, BLANGPT_EUNSUPPORTED, "log_density is a single-process call; with worldSize > 1 gather the table (blangpt_table_ptr)");
+  if (!h->one_view()) FAIL(h, BLANGPT_EUNSUPPORTED, "log_density with worldSize > 1 needs the peer exchange (blangpt_peer_export / blangpt_peer_connect), or gather the table yourself (blangpt_table_ptr)");
   h->tables_valid = false;
   int rc = ensure_tables(h);
   if (rc) return rc;
@@ -900,14 +952,15 @@ extern "C" int blangpt_run_scans(blangpt_handle* h, int32_t n_scans, const blang
   if (!h) return BLANGPT_EINVAL;
   if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
-  if (h->cfg.worldSize > 1) FAIL(h, BLANGPT_EINVAL, "run_scans is the single-GPU path; use blangpt_explore / blangpt_swap with worldSize > 1");
+  if (!h->one_view()) FAIL(h, BLANGPT_EINVAL, "run_scans with worldSize > 1 needs the peer exchange (blangpt_peer_export / blangpt_peer_connect); without it drive the scan with blangpt_explore / blangpt_swap");
+  if (h->cfg.worldSize > 1 && out && out->intSamples) FAIL(h, BLANGPT_EUNSUPPORTED, "intSamples are not exchanged between ranks");
   if (n_scans <= 0) return BLANGPT_OK;
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   int rc;
   if ((rc = ensure_tables(h))) return rc;
   const int64_t M = h->M_total; const int R = h->cfg.nReplicas;
   DevOut O{}; O.n_reals = h->n_reals; O.reversible = h->cfg.reversible;
-  std::vector<void*> tmp;
+  struct TmpBuffers { std::vector<void*> v; ~TmpBuffers() { for (void* p : v) cudaFree(p); } void push_back(void* p) { v.push_back(p); } } tmp;
   auto alloc_out = [&](auto** dptr, const void* hostptr, size_t n) -> int {
     if (!hostptr) return 0;
     using T = std::remove_pointer_t<std::remove_pointer_t<decltype(dptr)>>;
@@ -965,7 +1018,6 @@ extern "C" int blangpt_run_scans(blangpt_handle* h, int32_t n_scans, const blang
     for (size_t i = 0; i < b.size(); i++) out->intSamples[i] = b[i];
   }
   cudaError_t e = cudaGetLastError();
-  for (void* p : tmp) cudaFree(p);
   if (!rc && e != cudaSuccess) FAIL(h, BLANGPT_ECUDA, "run_scans: %s", cudaGetErrorString(e));
   return rc;
 }
@@ -1300,6 +1352,72 @@ extern "C" int blangpt_swap(blangpt_handle* h, const blangpt_scan_outputs* out) 
 extern "C" int blangpt_synchronize(blangpt_handle* h) {
   if (!h) return BLANGPT_EINVAL;
   return check_device_errors(h);
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU exchange: connect the ranks' mailboxes (kernels.cuh PeerBox).  After this, run_scans / perform_inference /
+// initialize / log_density work on a sharded handle exactly as on a single GPU: every exploration pass publishes the
+// chains' records to all ranks over NVLink and no host code runs between the scans.
+// ---------------------------------------------------------------------------
+static int peer_finish(blangpt_handle* h, const std::vector<void*>& boxes) {
+  PeerBox& B = h->E.peers;
+  const int W = h->cfg.worldSize;
+  for (int r = 0; r < W; r++) {
+    B.record[r] = (MailHalf*)boxes[r];
+    B.sample[r] = (MailHalf*)((char*)boxes[r] + h->mail_record_bytes);
+  }
+  B.my_record = B.record[h->cfg.rank]; B.my_sample = B.sample[h->cfg.rank];
+  B.world = W; B.xseq = 0; B.n_reals = std::max(1, h->n_reals);
+  h->peers_ready = true; h->tables_valid = false;
+  return BLANGPT_OK;
+}
+extern "C" int blangpt_peer_export(blangpt_handle* h, void* out_handle64) {
+  if (!h || !out_handle64) return BLANGPT_EINVAL;
+  if (!h->model_set || !h->mailbox) FAIL(h, BLANGPT_ESTATE, "peer_export: set_model on a handle with worldSize > 1 first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hd;
+  CUDA_OK(h, cudaIpcGetMemHandle(&hd, h->mailbox));
+  memcpy(out_handle64, &hd, 64);
+  return BLANGPT_OK;
+}
+extern "C" int blangpt_peer_connect(blangpt_handle* h, const void* handles, int32_t n) {
+  if (!h || !handles) return BLANGPT_EINVAL;
+  if (!h->model_set || !h->mailbox) FAIL(h, BLANGPT_ESTATE, "peer_connect: set_model on a handle with worldSize > 1 first");
+  if (n != h->cfg.worldSize || n > kMaxPeers) FAIL(h, BLANGPT_EINVAL, "peer_connect: expected %d handles (at most %d ranks)", h->cfg.worldSize, kMaxPeers);
+  if (h->peers_ready) FAIL(h, BLANGPT_ESTATE, "peers already connected");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  std::vector<void*> boxes(n, nullptr);
+  for (int r = 0; r < n; r++) {
+    if (r == h->cfg.rank) { boxes[r] = h->mailbox; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, (const char*)handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    CUDA_OK(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_maps.push_back(p);
+    boxes[r] = p;
+  }
+  return peer_finish(h, boxes);
+}
+// same-process variant (one host process driving several GPUs, e.g. one JVM): the mailboxes are plain device pointers
+// (blangpt_peer_mailbox of each handle); peer access between the devices is enabled here
+extern "C" void* blangpt_peer_mailbox(blangpt_handle* h) { return h ? h->mailbox : nullptr; }
+extern "C" int blangpt_peer_connect_pointers(blangpt_handle* h, void* const* mailboxes, const int32_t* devices, int32_t n) {
+  if (!h || !mailboxes || !devices) return BLANGPT_EINVAL;
+  if (!h->model_set || !h->mailbox) FAIL(h, BLANGPT_ESTATE, "peer_connect: set_model on a handle with worldSize > 1 first");
+  if (n != h->cfg.worldSize || n > kMaxPeers) FAIL(h, BLANGPT_EINVAL, "peer_connect: expected %d mailboxes (at most %d ranks)", h->cfg.worldSize, kMaxPeers);
+  if (h->peers_ready) FAIL(h, BLANGPT_ESTATE, "peers already connected");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  std::vector<void*> boxes(n, nullptr);
+  for (int r = 0; r < n; r++) {
+    boxes[r] = r == h->cfg.rank ? h->mailbox : mailboxes[r];
+    if (r != h->cfg.rank && devices[r] != h->cfg.device) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) FAIL(h, BLANGPT_ECUDA, "cudaDeviceEnablePeerAccess(%d): %s", devices[r], cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+  }
+  return peer_finish(h, boxes);
 }
 
 // ---------------------------------------------------------------------------

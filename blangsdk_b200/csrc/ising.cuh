@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kIsingThreads) ising_kernel(DevEngine E, Ising
     sd[0] = loglik; sd[1] = 0.0; sd[2] = fixed; sd[3] = (double)ev;
     E.evals[l] += ev;
     E.execs[l] += ex;
+    peer_publish(E, g, pos, loglik, 0, fixed, ev, nullptr, 0);
   }
 }
 

@@ -22,6 +22,36 @@ namespace bpt {
 
 enum ExploreMode : int { MODE_EXPLORE = 0, MODE_EVAL = 1, MODE_FORWARD_INIT = 2 };
 
+// ---- multi-GPU exchange through peer-mapped mailboxes (one process per GPU, no collective library) ----
+// After its scan a chain's 32-byte record (loglik, nOutOfSupport, fixed, evaluations) is STORED into the mailbox of
+// every rank (NVLink peer writes through CUDA-IPC mappings), as two 16-byte halves that each carry the exchange's
+// sequence number, so a reader that sees the number it waits for in both halves holds the whole record.  The chain
+// at position 0 also publishes its reals (one 16-byte {value, sequence, index} record each): they are the sample the
+// swap pass records.  gather_kernel then fills the replicated table; two parities of buffers, because a fast rank may
+// already publish exchange x+1 while a slow one still reads exchange x (it cannot get two ahead: its next gather
+// needs the slow rank's records).
+constexpr int kMaxPeers = 16;
+struct __align__(16) MailHalf { double v; uint32_t seq; int i; };
+struct PeerBox {
+  int world;                 // 0 = exchange off (single process, or split-phase driven by the host)
+  uint32_t xseq;             // sequence number of the exchange the NEXT exploration pass publishes (host-incremented)
+  int n_reals;
+  MailHalf* record[kMaxPeers];   // rank r's mailbox: [2 parities][M][2 halves]
+  MailHalf* sample[kMaxPeers];   // rank r's sample mailbox: [2 parities][R][n_reals]
+  MailHalf* my_record; MailHalf* my_sample;
+  double* sample_buf;        // [R][n_reals] the gathered position-0 reals (read by the swap pass)
+};
+BPT_D void peer_st(MailHalf* p, double v, uint32_t seq, int i) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"((uint32_t)__double2loint(v)),
+               "r"((uint32_t)__double2hiint(v)), "r"(seq), "r"((uint32_t)i) : "memory");
+}
+BPT_D MailHalf peer_ld(const MailHalf* p) {
+  uint32_t a, b, c, d;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+  MailHalf h; h.v = __hiloint2double((int)b, (int)a); h.seq = c; h.i = (int)d;
+  return h;
+}
+
 struct DevEngine {
   int N, R;                 // chains per replica, replicas in this handle
   int slot_lo, M_local;     // first local global-slot, number of local slots
@@ -31,6 +61,7 @@ struct DevEngine {
   double beta_override;     // NaN = use the ladder; otherwise every chain runs at this exponent (SCM particles)
   int steps_override;       // 0 = floor(n_passes * S) sampler executions per scan; > 0 = exactly that many
   int use_prior, anneal_support;
+  int nan_neginf;           // treatNaNAsNegativeInfinity: a NaN factor counts as -inf (ExponentiatedFactor.enclosedLogDensity)
   int s_max;                // stride of the order array
   const double* ladder;     // [R][N] descending
   int* pos_of_slot;         // [R][N] (slot-in-replica -> position)
@@ -47,6 +78,7 @@ struct DevEngine {
   uint32_t* scan_counter;   // [R] scans done (Philox `scan`)
   uint32_t* swap_counter;   // [R] ParallelTempering.swapIndex
   uint32_t* batch_counter;  // [R] scan index inside the current run_scans batch
+  PeerBox peers;            // multi-GPU exchange (peers.world == 0: off)
 };
 
 struct DevStats {     // all indexed [R][N] by temperature position unless noted
@@ -92,14 +124,15 @@ struct LogDensityBase {
   unsigned long long& evals; int& err;
   BPT_D double eval(double x) {
     evals++;
-    const double fx = fam.fixed(k, x, aux);
+    double fx = fam.fixed(k, x, aux);
+    if (fx != fx) { if (E.nan_neginf) fx = BPT_NEG_INF; else err |= ERR_NAN; }   // ExponentiatedFactor.java:26-29
     if (beta == 0.0 || fx == BPT_NEG_INF) return fx;
     double s; int c;
     fam.annealed(k, x, aux, red, s, c);
     double a = beta * s;
     if (c) a += E.anneal_support ? c * annealed_minus_infinity(beta) : BPT_NEG_INF;
-    const double r = fx + a;
-    if (r != r) err |= ERR_NAN;   // ExponentiatedFactor.java:26-29
+    double r = fx + a;
+    if (r != r) { if (E.nan_neginf) r = BPT_NEG_INF; else err |= ERR_NAN; }   // ExponentiatedFactor.java:26-29
     return r;
   }
 };
@@ -114,6 +147,59 @@ template <class Fam>
 struct LogDensityCall : LogDensityBase<Fam> {
   __device__ __noinline__ double operator()(double x) { return this->eval(x); }
 };
+
+// one thread: publish global slot g's record (and, for the chain at position 0, its reals) to every rank
+BPT_D void peer_publish(const DevEngine& E, int g, int pos, double loglik, int noos, double fixed, unsigned long long evals,
+                        const double* P, int n_reals) {
+  const PeerBox& B = E.peers;
+  if (B.world == 0) return;
+  const size_t M = (size_t)E.R * E.N, par = B.xseq & 1u;
+  for (int r = 0; r < B.world; r++) {
+    MailHalf* rec = B.record[r] + (par * M + (size_t)g) * 2;
+    peer_st(rec, loglik, B.xseq, noos);
+    peer_st(rec + 1, fixed, B.xseq, (int)evals);
+    if (pos == 0 && P) {
+      const int rep = g / E.N;
+      MailHalf* sm = B.sample[r] + (par * E.R + rep) * (size_t)B.n_reals;
+      for (int v = 0; v < n_reals; v++) peer_st(sm + v, P[v], B.xseq, v);
+    }
+  }
+}
+
+// Fills the replicated table (and the position-0 sample buffer) from this rank's mailboxes once every rank's
+// records of exchange `xseq` have arrived.  A record that does not arrive within ~20 s (a rank died or the host
+// code is not SPMD) raises ERR_PEER_TIMEOUT instead of hanging.
+static __global__ void gather_kernel(DevEngine E) {
+  const PeerBox& B = E.peers;
+  const size_t M = (size_t)E.R * E.N, par = B.xseq & 1u;
+  const size_t n_rec = M, n_smp = (size_t)E.R * B.n_reals;
+  const long long t0 = clock64();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_rec + n_smp; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < n_rec) {
+      const MailHalf* rec = B.my_record + (par * M + i) * 2;
+      MailHalf a, b;
+      for (;;) {
+        a = peer_ld(rec); b = peer_ld(rec + 1);
+        if (a.seq == B.xseq && b.seq == B.xseq) break;
+        __nanosleep(200);
+        if (clock64() - t0 > 40LL * 1000 * 1000 * 1000) { atomicOr(E.err, ERR_PEER_TIMEOUT); return; }
+      }
+      double* t = E.table + i * 4;
+      t[0] = a.v; t[1] = (double)a.i; t[2] = b.v; t[3] = (double)b.i;
+    } else {
+      const size_t k = i - n_rec;
+      const MailHalf* sm = B.my_sample + par * n_smp + k;
+      MailHalf a;
+      for (;;) {
+        a = peer_ld(sm);
+        if (a.seq == B.xseq) break;
+        __nanosleep(200);
+        if (clock64() - t0 > 40LL * 1000 * 1000 * 1000) { atomicOr(E.err, ERR_PEER_TIMEOUT); return; }
+      }
+      B.sample_buf[k] = a.v;
+    }
+  }
+}
 
 // One chain's share of ParallelTempering.moveKernel for one scan: forward sample at beta = 0, else
 // floor(nPasses * S) sampler executions in the persistent shuffled order.  P / order are the chain's
@@ -192,6 +278,16 @@ BPT_D void explore_chain(const DevEngine& E, Fam& fam, GroupReducer& red, double
 template <class Fam, class = void> struct MinBlocksOf { static constexpr int value = 1; };
 template <class Fam> struct MinBlocksOf<Fam, decltype((void)Fam::kMinBlocks)> { static constexpr int value = Fam::kMinBlocks; };
 
+// NaN in the from-scratch sums (SampledModel.updateAll): an error (ExponentiatedFactor.java:26-29), or, under
+// treatNaNAsNegativeInfinity, a factor equal to -inf: a fixed one makes the fixed sum -inf, an annealed one is out of
+// support (families that sum their annealed factors in closed form cannot say how many were NaN: counted once)
+BPT_D void nan_policy(const DevEngine& E, double& loglik, int& noos, double& logprior, int& err) {
+  if (loglik == loglik && logprior == logprior) return;
+  if (!E.nan_neginf) { err |= ERR_NAN; return; }
+  if (logprior != logprior) logprior = BPT_NEG_INF;
+  if (loglik != loglik) { loglik = 0.0; noos += 1; }
+}
+
 template <class Fam>
 __global__ void __launch_bounds__(Fam::kThreads, MinBlocksOf<Fam>::value)
 explore_kernel(DevEngine E, typename Fam::Data D, int G, int mode) {
@@ -226,7 +322,7 @@ explore_kernel(DevEngine E, typename Fam::Data D, int G, int mode) {
 
   double loglik, logprior; int noos;
   fam.full(red, loglik, noos, logprior);
-  if (loglik != loglik || logprior != logprior) err |= ERR_NAN;
+  nan_policy(E, loglik, noos, logprior, err);
   __syncthreads();
   if (crank == 0) {
     for (int v = tid; v < nR; v += blockDim.x) E.reals[(size_t)v * E.M_local + l] = P[v];
@@ -240,6 +336,7 @@ explore_kernel(DevEngine E, typename Fam::Data D, int G, int mode) {
       E.evals[l] += evals;
       E.execs[l] += execs;
       if (err) atomicOr(E.err, err);
+      peer_publish(E, g, pos, loglik, noos, logprior, evals, P, nR);
     }
   }
 }
@@ -291,7 +388,10 @@ BPT_D void swap_replica(const DevEngine& E, const DevStats& St, const DevOut& O,
     if (O.indicators) O.indicators[obase + p] = 0;
     if (p == 0 && O.samples) {
       const int l = (int)g - E.slot_lo;
-      if (l >= 0 && l < E.M_local)
+      if (E.peers.world) {       // multi-GPU: the position-0 reals every rank received with the exchange
+        for (int v = 0; v < O.n_reals; v++)
+          O.samples[((size_t)b * E.R + rep) * O.n_reals + v] = E.peers.sample_buf[(size_t)rep * O.n_reals + v];
+      } else if (l >= 0 && l < E.M_local)
         for (int v = 0; v < O.n_reals; v++)
           O.samples[((size_t)b * E.R + rep) * O.n_reals + v] = E.reals[(size_t)v * E.M_local + l];
     }
@@ -388,7 +488,7 @@ __global__ void __launch_bounds__(1024) replica_kernel(DevEngine E, DevStats St,
     explore_chain<Fam, WarpSync>(E, fam, red, P, order, curpos, S, pos, beta, scan, key1, MODE_EXPLORE, evals, execs, err);
     double loglik, logprior; int noos;
     fam.full(red, loglik, noos, logprior);
-    if (loglik != loglik || logprior != logprior) err |= ERR_NAN;
+    nan_policy(E, loglik, noos, logprior, err);
     for (int v = lane; v < nR; v += 32) E.reals[(size_t)v * E.M_local + l] = P[v];
     if (lane == 0) {
       double* t = E.table + (size_t)l * 4;

@@ -527,7 +527,7 @@ BPT_D void pool_controller(const DevEngine& E, const typename PF::Data& D, const
   explore_chain<typename PF::Ctl, WarpSync>(E, fam, red, P, order, curpos, S, pos, beta, scan, key1, mode, evals, execs, err);
   double loglik, logprior; int noos;
   fam.full(red, loglik, noos, logprior);
-  if (loglik != loglik || logprior != logprior) err |= ERR_NAN;
+  nan_policy(E, loglik, noos, logprior, err);
   __syncwarp();
   for (int v = lane; v < nR; v += 32) E.reals[(size_t)v * E.M_local + l] = P[v];
   for (int k = lane; k < S; k += 32) E.order[(size_t)l * E.s_max + k] = order[k];
@@ -540,6 +540,7 @@ BPT_D void pool_controller(const DevEngine& E, const typename PF::Data& D, const
     E.evals[l] += evals;
     E.execs[l] += execs;
     if (err) atomicOr(E.err, err);
+    peer_publish(E, g, pos, loglik, noos, logprior, evals, P, nR);
   }
   if (pc.prof && lane == 0) {
     unsigned long long* q = pc.prof + ((size_t)blockIdx.x * kPoolWarps + warp) * 8;

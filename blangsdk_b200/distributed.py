@@ -48,6 +48,25 @@ def gather_table(send, table, group=None):
     return table
 
 
+def connect_peers(engine, group=None):
+    """Exchange the ranks' mailbox handles (64 bytes each) over torch.distributed and connect them: from here on the
+    chains' records travel GPU to GPU inside the exploration kernels, and Engine.run_scans / perform_inference /
+    initialize work on the sharded engine with no per-scan host code (include/blangpt.h, blangpt_peer_connect)."""
+    world = dist.get_world_size(group)
+    mine = engine.peer_handle()
+    if dist.get_backend(group) == "nccl":
+        dev = torch.device("cuda", engine.cfg.device)
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+        out = torch.empty(64 * world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, t, group=group)
+        blob = bytes(out.cpu().numpy().tobytes())
+    else:
+        objs = [None] * world
+        dist.all_gather_object(objs, mine, group=group)
+        blob = b"".join(objs)
+    engine.peer_connect([blob[64 * r:64 * (r + 1)] for r in range(world)])
+
+
 class _DevPtr:
     def __init__(self, ptr, n, itemsize=8, typestr="<f8"):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False),

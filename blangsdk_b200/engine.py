@@ -88,6 +88,7 @@ EXPORTS = [
     "blangpt_explore", "blangpt_table_ptr", "blangpt_local_chains", "blangpt_swap", "blangpt_synchronize",
     "blangpt_microbench", "blangpt_debug_logit_terms", "blangpt_make_ladder", "blangpt_get_diagnostics",
     "blangpt_set_scm_options", "blangpt_scm_summary", "blangpt_target_accept_ladder",
+    "blangpt_peer_export", "blangpt_peer_connect", "blangpt_peer_mailbox", "blangpt_peer_connect_pointers",
 ]
 
 _LIB = None
@@ -141,6 +142,11 @@ def load_library():
     L.blangpt_set_scm_options.argtypes = [vp, C.c_int32, C.c_double, C.c_double]
     L.blangpt_scm_summary.argtypes = [vp, _dp, _ip, _ip]
     L.blangpt_target_accept_ladder.argtypes = [vp, C.c_int64, C.c_double, _dp, C.c_int32, _ip]
+    L.blangpt_peer_export.argtypes = [vp, C.c_void_p]
+    L.blangpt_peer_connect.argtypes = [vp, C.c_void_p, C.c_int32]
+    L.blangpt_peer_mailbox.argtypes = [vp]
+    L.blangpt_peer_mailbox.restype = vp
+    L.blangpt_peer_connect_pointers.argtypes = [vp, C.POINTER(vp), _ip, C.c_int32]
     _LIB = L
     return L
 
@@ -301,6 +307,17 @@ class Engine:
         self.ctas_per_chain = self.L.blangpt_ctas_per_chain(self.h)
         self.kernel_variant = self.L.blangpt_kernel_variant(self.h)   # 0 = cluster per chain, 1 = pool
         self.family = fam
+
+    # ---- multi-GPU exchange (worldSize > 1): connect the ranks' mailboxes; afterwards every method works as on one GPU ----
+    def peer_handle(self):
+        buf = C.create_string_buffer(64)
+        self._check(self.L.blangpt_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_connect(self, handles):
+        """handles: the 64-byte strings of every rank's peer_handle(), in rank order"""
+        blob = b"".join(handles)
+        self._check(self.L.blangpt_peer_connect(self.h, C.c_char_p(blob), len(handles)))
 
     def set_ladder(self, betas):
         b = np.ascontiguousarray(betas, dtype=np.float64).ravel()

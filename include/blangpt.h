@@ -287,6 +287,21 @@ int64_t blangpt_local_chains(const blangpt_handle* h, int64_t* first_slot);
 int blangpt_swap(blangpt_handle* h, const blangpt_scan_outputs* out_one_scan_or_null);
 int blangpt_synchronize(blangpt_handle* h);
 
+/* Multi-GPU exchange without a collective library (replaces the thread pool over chains of
+ * R/engines/ParallelTempering.java:68,79 across GPUs).  Every rank owns a mailbox in its GPU's memory; once the
+ * mailboxes are connected, the exploration kernels STORE each chain's 32-byte record (loglik, nOutOfSupport, fixed,
+ * evaluations) and the beta = 1 sample into every rank's mailbox over NVLink, and blangpt_run_scans,
+ * blangpt_perform_inference, blangpt_initialize (SCM included) and blangpt_log_density work on a sharded handle
+ * (worldSize > 1) exactly as on one GPU, with no host code between the scans.  All ranks must make the same
+ * sequence of calls.  One process per GPU: exchange the 64-byte handles of blangpt_peer_export by any means
+ * (torch.distributed, MPI, a file) and pass them, in rank order, to blangpt_peer_connect.  One process driving
+ * several GPUs (one JVM): pass the device pointers of blangpt_peer_mailbox to blangpt_peer_connect_pointers and
+ * drive each handle from its own host thread. */
+int blangpt_peer_export(blangpt_handle* h, void* out_handle64);
+int blangpt_peer_connect(blangpt_handle* h, const void* handles /* worldSize x 64 bytes */, int32_t n);
+void* blangpt_peer_mailbox(blangpt_handle* h);
+int blangpt_peer_connect_pointers(blangpt_handle* h, void* const* mailboxes, const int32_t* devices, int32_t n);
+
 /* Measured compute ceilings on `device` (no handle needed): which = 0 -> fp64 FMA TFLOP/s,
  * which = 1 -> logistic-regression row terms per second with operands in registers (the
  * compute-only bound of the C2 likelihood kernel). */

@@ -34,6 +34,8 @@ def _case(D, rng):
         spec = D.ising(2 * int(rng.integers(1, 7)), moment=float(rng.choice([0.0, 0.1, -0.3])))
     opts = dict(usePriorSamples=bool(rng.integers(0, 2)), reversible=bool(rng.integers(0, 2)),
                 annealSupport=bool(rng.integers(0, 4) > 0), nPassesPerScan=float(rng.choice([0.5, 1.0, 3.0, 3.7])))
+    if fam == "ising":   # whole checkerboard sweeps only: a fractional number of passes is refused (BLANGPT_EUNSUPPORTED)
+        opts["nPassesPerScan"] = float(max(1, round(opts["nPassesPerScan"])))
     ctas = 0 if fam == "ising" else int(rng.choice([0, 1, 2, 4, 8]))
     return fam, spec, int(rng.integers(1, 14)), int(rng.integers(1, 1 << 20)), ctas, opts
 
