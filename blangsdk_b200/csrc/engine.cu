@@ -1367,7 +1367,7 @@ static int peer_finish(blangpt_handle* h, const std::vector<void*>& boxes) {
     B.sample[r] = (MailHalf*)((char*)boxes[r] + h->mail_record_bytes);
   }
   B.my_record = B.record[h->cfg.rank]; B.my_sample = B.sample[h->cfg.rank];
-  B.world = W; B.xseq = 0; B.n_reals = std::max(1, h->n_reals);
+  B.world = W; B.xseq = 0; B.n_reals = h->n_reals;   // 0 for Ising: no real-valued sample to exchange
   h->peers_ready = true; h->tables_valid = false;
   return BLANGPT_OK;
 }

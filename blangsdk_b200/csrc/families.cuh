@@ -25,7 +25,7 @@ namespace bpt {
 constexpr int kMaxParams = 64;    // latent reals per chain held in shared memory
 constexpr int kMaxSamplers = 65;
 
-enum SamplerType : int { S_REAL_SLICE = 0, S_SIMPLEX = 1, S_INT_SLICE = 3 };
+enum SamplerType : int { S_REAL_SLICE = 0, S_SIMPLEX = 1, S_INT_SLICE = 3, S_INT_FIXED = 4 };   // S_INT_FIXED: CategoricalSampler / UniformSampler
 
 // rows [lo, hi) of this CTA inside the chain group; lo is even
 struct RowRange { int lo, hi; };
@@ -1429,6 +1429,207 @@ struct MixtureFam {
     for (int c = 0; c < K; c++) { mu[c] = gen_normal(rng, d.m0, d.v0); var[c] = gen_gamma(rng, d.gshape, d.grate); }
     __syncthreads();
     for (int c = 0; c < K; c++) { P[c] = mu[c]; P[K + c] = var[c]; P[2 * K + c] = g[c]; }
+    __syncthreads();
+  }
+};
+
+// ===========================================================================
+// Family 10: blang.examples.MixtureModel (F/MixtureModel.bl) with K components and the cluster indicators NOT
+// marginalised.  P = [mu[K], var[K], pi[K], z[n] as exact doubles]
+//   pi ~ Dirichlet(conc); mu_k ~ Normal(m0, v0); var_k ~ Gamma(shape, rate); z_i | pi ~ Categorical(pi) (latent);
+//   y_i | z_i ~ Normal(means.get(z_i), variances.get(z_i)) (observed: three annealed factors each).
+// Samplers: k < K mu_k, K <= k < 2K var_k, 2K the simplex, 2K + 1 + i the indicator z_i, moved by CategoricalSampler =
+// IntSliceSampler with the fixed window [0, K) (R/mcmc/CategoricalSampler.xtend:24-28); with K > 10 the window test
+// IntSliceSampler.accept (:115-132) runs.  Connections are the DSL's static ones: the Normal's parameter closures read
+// the whole lists `means` / `variances`, so every mean's sampler sees every f2, every variance's sampler every f1 and
+// f2; the simplex sampler sees the Dirichlet factor and the n Categorical factors log pi[z_i].
+// A small-model family (3K + n <= 96 values, 2K + 1 + n <= 65 samplers): one CTA per chain.
+// ===========================================================================
+struct MixIndFam {
+  struct Data { const double* y; int n, K; double m0, v0, gshape, grate, conc; };
+  static constexpr int kThreads = 128;
+  static constexpr bool kWarpCapable = false;
+  static constexpr bool kHasIntFixed = true;
+  Data d; double* P; int* err; int t0, tn;
+
+  BPT_D static int n_reals(const Data& d) { return 3 * d.K + d.n; }
+  BPT_D static int n_samplers(const Data& d) { return 2 * d.K + 1 + d.n; }
+  BPT_D void init(const Data& d_, int, double* P_, int, int, int* err_) { d = d_; P = P_; err = err_; t0 = threadIdx.x; tn = blockDim.x; }
+  BPT_D int sampler_type(int k) const { return k < 2 * d.K ? S_REAL_SLICE : (k == 2 * d.K ? S_SIMPLEX : S_INT_FIXED); }
+  BPT_D int sampler_var(int k) const { return k <= 2 * d.K ? k : 3 * d.K + (k - 2 * d.K - 1); }
+  BPT_D int simplex_dim() const { return d.K; }
+  BPT_D int int_lo(int) const { return 0; }
+  BPT_D int int_hi(int) const { return d.K; }
+  BPT_D void begin_execution() {}
+  BPT_D static void tables_init() {}
+  // candidate-substituted weight of component c for the simplex sampler (SimplexWritableVariable.set :26-30)
+  BPT_D double pi_at(int c, double x, int aux) const {
+    const int K = d.K, nx = aux == K - 1 ? 0 : aux + 1;
+    if (c == aux) return x;
+    if (c == nx) return fmax(0.0, (P[2 * K + aux] + P[2 * K + nx]) - x);
+    return P[2 * K + c];
+  }
+  BPT_D double fixed(int k, double x, int aux) const {
+    const int K = d.K;
+    if (k < K) return normal_f2(d.m0, d.v0, x);
+    if (k < 2 * K) return gamma_ab(d.gshape, d.grate, x);
+    if (k == 2 * K) {     // Dirichlet.bl:13-22, then the n Categorical factors (Categorical.bl:12-15), connection order
+      double sum = 0.0;
+      for (int c = 0; c < K; c++) { if (d.conc < 0.0) return BPT_NEG_INF; sum += (d.conc - 1.0) * log(pi_at(c, x, aux)); }
+      for (int i = 0; i < d.n; i++) sum += log(pi_at((int)P[3 * K + i], x, aux));
+      return sum;
+    }
+    const int z = (int)x;   // indicator i: its own Categorical factor
+    return (z < 0 || z >= K) ? BPT_NEG_INF : log(P[2 * K + z]);
+  }
+  // Normal.bl:17-24 of observation i with component z
+  BPT_D void obs_f1(double var, double& s, int& c) const { acc_term(var <= 0.0 ? BPT_NEG_INF : -0.5 * log(var), s, c, err); }
+  BPT_D void obs_f2(double mu, double var, double yv, double& s, int& c) const {
+    const double dd = mu - yv;
+    acc_term(var <= 0.0 ? BPT_NEG_INF : -0.5 * (dd * dd) / var, s, c, err);
+  }
+  BPT_D void annealed(int k, double x, int, GroupReducer& red, double& s, int& c) const {
+    const int K = d.K;
+    double acc = 0.0; int cnt = 0;
+    if (k < 2 * K) {
+      for (int i = t0; i < d.n; i += tn) {
+        const int z = (int)P[3 * K + i];
+        const double mu = (k < K && z == k) ? x : P[z], var = (k >= K && z == k - K) ? x : P[K + z];
+        if (k >= K) obs_f1(var, acc, cnt);
+        obs_f2(mu, var, d.y[i], acc, cnt);
+      }
+    } else if (k > 2 * K) {
+      const int i = k - 2 * K - 1, z = (int)x;
+      if (t0 == 0) {
+        if (z < 0 || z >= K) cnt += 2;
+        else { obs_f1(P[K + z], acc, cnt); obs_f2(P[z], P[K + z], d.y[i], acc, cnt); }
+      }
+    }
+    red.reduce(acc, cnt);
+    s = acc; c = cnt;
+  }
+  BPT_D void commit(int k, double x, int aux) {
+    const int K = d.K;
+    const int nx = aux == K - 1 ? 0 : aux + 1;
+    const double comp = k == 2 * K ? fmax(0.0, (P[2 * K + aux] + P[2 * K + nx]) - x) : 0.0;
+    __syncthreads();
+    if (k == 2 * K) { P[2 * K + aux] = x; P[2 * K + nx] = comp; }
+    else P[sampler_var(k)] = x;
+    __syncthreads();
+  }
+  BPT_D void refresh() {}
+  BPT_D void full(GroupReducer& red, double& loglik, int& noos, double& logprior) const {
+    const int K = d.K;
+    double acc = 0.0; int cnt = 0;
+    for (int i = t0; i < d.n; i += tn) {
+      const int z = (int)P[3 * K + i];
+      acc += -0.5 * BPT_LOG_2PI;
+      obs_f1(P[K + z], acc, cnt); obs_f2(P[z], P[K + z], d.y[i], acc, cnt);
+    }
+    red.reduce(acc, cnt);
+    loglik = acc; noos = cnt;
+    double lp = 0.0;
+    for (int c = 0; c < K; c++) lp += (d.conc - 1.0) * log(P[2 * K + c]);
+    lp += d.conc < 0.0 ? BPT_NEG_INF : (-K * lgamma(d.conc) + lgamma(K * d.conc));
+    const double f01 = -0.5 * BPT_LOG_2PI + (d.v0 <= 0.0 ? BPT_NEG_INF : -0.5 * log(d.v0));
+    for (int c = 0; c < K; c++) {
+      lp += f01 + normal_f2(d.m0, d.v0, P[c]);
+      lp += gamma_ab(d.gshape, d.grate, P[K + c]) + gamma_cd(d.gshape, d.grate);
+    }
+    for (int i = 0; i < d.n; i++) lp += log(P[2 * K + (int)P[3 * K + i]]);
+    logprior = lp;
+  }
+  BPT_D void forward(Rng& rng) {   // pi, then (mu_k, var_k) per component, then the indicators (GraphAnalysis.createForwardSimulator order)
+    const int K = d.K;
+    double g[16]; double sum = 0.0;
+    if (d.conc < 1.0) {
+      double lse = BPT_NEG_INF;
+      for (int c = 0; c < K; c++) {
+        const double gv = gen_gamma(rng, d.conc + 1.0, 1.0);
+        const double logu = log(rng.next_double());
+        g[c] = log(gv) + logu / d.conc;
+        lse = log_add(lse, g[c]);
+      }
+      for (int c = 0; c < K; c++) g[c] = exp(g[c] - lse);
+    } else {
+      for (int c = 0; c < K; c++) { g[c] = gen_gamma(rng, d.conc, 1e7); sum += g[c]; }
+      for (int c = 0; c < K; c++) g[c] /= sum;
+    }
+    for (int c = 0; c < K; c++) { if (g[c] == 0.0) g[c] = 1e-300; else if (g[c] == 1.0) g[c] = 1.0 - 1e-16; }
+    double mu[16], var[16];
+    for (int c = 0; c < K; c++) { mu[c] = gen_normal(rng, d.m0, d.v0); var[c] = gen_gamma(rng, d.gshape, d.grate); }
+    __syncthreads();
+    for (int c = 0; c < K; c++) { P[c] = mu[c]; P[K + c] = var[c]; P[2 * K + c] = g[c]; }
+    for (int i = 0; i < d.n; i++) {   // Generators.categorical :163 -> first index whose cumulative sum exceeds U
+      const double u = rng.next_double();
+      double cum = 0.0; int z = K - 1;
+      for (int c = 0; c < K; c++) { cum += g[c]; if (u < cum) { z = c; break; } }
+      P[3 * K + i] = (double)z;
+    }
+    __syncthreads();
+  }
+};
+
+// ===========================================================================
+// Family 11: change point, the smallest model with a DiscreteUniform latent (UniformSampler =
+// IntSliceSampler with the fixed window [minInclusive, maxExclusive), R/mcmc/UniformSampler.xtend:21-27).
+//   mu_0, mu_1 ~ Normal(m0, v0); c ~ DiscreteUniform(0, n + 1); y_i | mu, c ~ Normal(i < c ? mu_0 : mu_1, s2), s2 constant.
+// P = [mu_0, mu_1, c as an exact double]; all three samplers see every observation's f2 (the mean closure reads all three).
+// ===========================================================================
+struct ChangePointFam {
+  struct Data { const double* y; int n; double m0, v0, s2; };
+  static constexpr int kThreads = 512;
+  static int launch_threads(const Data& d) { return d.n >= 32768 ? 512 : 128; }
+  static constexpr bool kWarpCapable = false;
+  static constexpr bool kHasIntFixed = true;
+  Data d; double* P; RowRange rr; int* err; int t0, tn;
+
+  BPT_D static int n_reals(const Data&) { return 3; }
+  BPT_D static int n_samplers(const Data&) { return 3; }
+  BPT_D void init(const Data& d_, int, double* P_, int G, int crank, int* err_) {
+    d = d_; P = P_; rr = group_rows(d.n, G, crank); err = err_; t0 = threadIdx.x; tn = blockDim.x;
+  }
+  BPT_D int sampler_type(int k) const { return k < 2 ? S_REAL_SLICE : S_INT_FIXED; }
+  BPT_D int sampler_var(int k) const { return k; }
+  BPT_D int simplex_dim() const { return 0; }
+  BPT_D int int_lo(int) const { return 0; }
+  BPT_D int int_hi(int) const { return d.n + 1; }
+  BPT_D void begin_execution() {}
+  BPT_D static void tables_init() {}
+  BPT_D double fixed(int k, double x, int) const {
+    if (k < 2) return normal_f2(d.m0, d.v0, x);
+    return (0.0 <= x && x < (double)(d.n + 1)) ? 0.0 : BPT_NEG_INF;      // DiscreteUniform.bl:16-20
+  }
+  BPT_D void sum_f2(double mu0, double mu1, double cp, double& s, int& c) const {
+    if (d.s2 <= 0.0) { c += rr.hi - rr.lo > 0 && t0 == 0 ? rr.hi - rr.lo : 0; return; }
+    for (int i = rr.lo + t0; i < rr.hi; i += tn) {
+      const double dd = ((double)i < cp ? mu0 : mu1) - d.y[i];
+      s += -0.5 * (dd * dd) / d.s2;
+    }
+  }
+  BPT_D void annealed(int k, double x, int, GroupReducer& red, double& s, int& c) const {
+    double acc = 0.0; int cnt = 0;
+    sum_f2(k == 0 ? x : P[0], k == 1 ? x : P[1], k == 2 ? x : P[2], acc, cnt);
+    red.reduce(acc, cnt);
+    s = acc; c = cnt;
+  }
+  BPT_D void commit(int k, double x, int) { __syncthreads(); P[k] = x; __syncthreads(); }
+  BPT_D void refresh() {}
+  BPT_D void full(GroupReducer& red, double& loglik, int& noos, double& logprior) const {
+    double acc = 0.0; int cnt = 0;
+    sum_f2(P[0], P[1], P[2], acc, cnt);
+    red.reduce(acc, cnt);
+    loglik = acc + d.n * (-0.5 * BPT_LOG_2PI);
+    if (d.s2 <= 0.0) cnt += d.n; else loglik += d.n * (-0.5 * log(d.s2));   // the n f1 factors
+    noos = cnt;
+    const double f01 = -0.5 * BPT_LOG_2PI + (d.v0 <= 0.0 ? BPT_NEG_INF : -0.5 * log(d.v0));
+    logprior = 2.0 * f01 + normal_f2(d.m0, d.v0, P[0]) + normal_f2(d.m0, d.v0, P[1]) - log((double)(d.n + 1)) + fixed(2, P[2], 0);
+  }
+  BPT_D void forward(Rng& rng) {
+    const double a = gen_normal(rng, d.m0, d.v0), b = gen_normal(rng, d.m0, d.v0);
+    const int cp = rng.next_int(d.n + 1);          // Generators.discreteUniform :205-222
+    __syncthreads();
+    P[0] = a; P[1] = b; P[2] = (double)cp;
     __syncthreads();
   }
 };

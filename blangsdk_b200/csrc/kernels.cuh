@@ -207,6 +207,9 @@ static __global__ void gather_kernel(DevEngine E) {
 // families with latent integers declare kHasIntSlice; the branch is not compiled into the other kernels
 template <class Fam, class = void> struct HasIntSlice { static constexpr bool value = false; };
 template <class Fam> struct HasIntSlice<Fam, decltype((void)Fam::kHasIntSlice)> { static constexpr bool value = Fam::kHasIntSlice; };
+// families whose latent integers move by CategoricalSampler / UniformSampler (IntSliceSampler with a fixed window)
+template <class Fam, class = void> struct HasIntFixed { static constexpr bool value = false; };
+template <class Fam> struct HasIntFixed<Fam, decltype((void)Fam::kHasIntFixed)> { static constexpr bool value = Fam::kHasIntFixed; };
 
 template <class Fam, class Sync>
 BPT_D void explore_chain(const DevEngine& E, Fam& fam, GroupReducer& red, double* P, int* order, int& curpos, int S,
@@ -255,6 +258,13 @@ BPT_D void explore_chain(const DevEngine& E, Fam& fam, GroupReducer& red, double
           if constexpr (HasIntSlice<Fam>::value) {
             const int x0 = (int)P[fam.sampler_var(k)];
             const int xn = int_slice(lp, rng, x0, false, 0, 0, err);
+            fam.commit(k, (double)xn, 0);
+          }
+        } else if (HasIntFixed<Fam>::value && fam.sampler_type(k) == S_INT_FIXED) {
+          // CategoricalSampler.xtend:24-28 / UniformSampler.xtend:21-27: IntSliceSampler with a fixed window
+          if constexpr (HasIntFixed<Fam>::value) {
+            const int x0 = (int)P[fam.sampler_var(k)];
+            const int xn = int_slice(lp, rng, x0, true, fam.int_lo(k), fam.int_hi(k), err);
             fam.commit(k, (double)xn, 0);
           }
         } else {   // SimplexSampler.xtend:21-28

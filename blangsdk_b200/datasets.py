@@ -163,3 +163,22 @@ def rockets_latent(groups=8, seed=20240009):
     p = rng.beta(1.5, 3.0, groups)
     failures = rng.binomial(launches, p).astype(np.int32)
     return dict(family="rockets_latent", hyper=dict(rate_a=1.0, rate_b=1.0, pois_mean=2.0), y=failures)
+
+
+def mixture_with_indicators(n=30, K=3, seed=20240010):
+    """blang.examples.MixtureModel (F/MixtureModel.bl) with K components and latent cluster indicators (family
+    `mixture_indicators`, SURVEY 8 row a9: CategoricalSampler; K > 10 runs IntSliceSampler's window test)."""
+    rng = np.random.default_rng(seed)
+    centres = np.linspace(-2.0 * (K - 1), 2.0 * (K - 1), K)
+    z = rng.integers(0, K, n)
+    y = rng.normal(centres[z], 0.7)
+    return dict(family="mixture_indicators", y=y, hyper=dict(K=K, m0=0.0, v0=25.0, gshape=2.0, grate=2.0, conc=1.0))
+
+
+def change_point(n=200, seed=20240011):
+    """y_i ~ Normal(i < c ? mu_0 : mu_1, s2) with a latent change point c ~ DiscreteUniform(0, n + 1) (family
+    `changepoint`, SURVEY 8 row a9: UniformSampler)."""
+    rng = np.random.default_rng(seed)
+    c = int(0.6 * n)
+    y = np.concatenate([rng.normal(-0.4, 1.0, c), rng.normal(0.5, 1.0, n - c)])
+    return dict(family="changepoint", y=y, hyper=dict(m0=0.0, v0=4.0, s2=1.0))

@@ -228,7 +228,12 @@ enum {
   F_POIS_INT,         /* family 9: block i1 of Poisson.bl:11-26 on the latent int i0, mean = c0 */
   F_HBINOM_LAT,       /* family 9: block i1 of Binomial.bl:14-27, group i0, trials = 1 + int i0, p = real 2 + i0 */
   F_BETA_A, F_BETA_B,                      /* Beta.bl:14-27 prior on real i0, alpha = c0, beta = c1  */
-  F_UNIF_B                                 /* ContinuousUniform.bl:16-19 prior on real i0, [c0, c1]  */
+  F_UNIF_B,                                /* ContinuousUniform.bl:16-19 prior on real i0, [c0, c1]  */
+  F_CAT_LOGP,         /* family 10: Categorical.bl:12-15 log(probabilities.get(realization)): realization = int i0, simplex = reals i1.. (K = i2) */
+  F_MIXIND_F1,        /* family 10: Normal.bl:17-20 with variance = variances.get(indicator i0)                    */
+  F_MIXIND_F2,        /* family 10: Normal.bl:21-24 with mean / variance of component indicator i0, x = y[i0]      */
+  F_DUNIF_B,          /* family 11: DiscreteUniform.bl:16-20 support of int i0 in [c0, c1)                         */
+  F_CP_F2             /* family 11: Normal.bl:21-24, mean = (i0 < changePoint ? real 0 : real 1), variance = c0, x = y[i0] */
 };
 
 typedef struct {
@@ -237,17 +242,19 @@ typedef struct {
   double c0, c1;
 } Factor;
 
-enum { S_REAL_SLICE = 0, S_SIMPLEX = 1, S_CATEGORICAL = 2, S_INT_SLICE = 3 };
+enum { S_REAL_SLICE = 0, S_SIMPLEX = 1, S_CATEGORICAL = 2, S_INT_SLICE = 3, S_UNIFORM = 4 };
 
 typedef struct {
   int32_t type;
   int32_t var;        /* real index (REAL_SLICE), first simplex real (SIMPLEX), int index (CATEGORICAL) */
-  int32_t K;          /* simplex dimension / number of categories */
+  int32_t K;          /* simplex dimension / number of categories / maxExclusive (S_UNIFORM) */
+  int32_t lo;         /* minInclusive (S_UNIFORM, UniformSampler.xtend:23-27) */
   int32_t n_fixed, n_ann;
   int32_t *fixed_idx, *ann_idx;   /* sampler2sparseUpdate{Fixed,Annealed}, SampledModel.java:67-69 */
 } Sampler;
 
-enum { FW_NORMAL = 0, FW_EXPONENTIAL, FW_GAMMA, FW_DIRICHLET_SYM, FW_BERNOULLI_INT, FW_BETA, FW_UNIFORM, FW_BETA_LATENT, FW_POISSON_INT };
+enum { FW_NORMAL = 0, FW_EXPONENTIAL, FW_GAMMA, FW_DIRICHLET_SYM, FW_BERNOULLI_INT, FW_BETA, FW_UNIFORM, FW_BETA_LATENT, FW_POISSON_INT,
+       FW_CATEGORICAL_INT, FW_DISCRETE_UNIFORM_INT };
 typedef struct { int32_t kind, var, K; double a, b; } Forward;
 
 struct orc_model {
@@ -535,6 +542,35 @@ static double factor_eval(const orc_model* m, const Factor* f, const double* re,
       if (f->c0 <= x && x <= f->c1) return 0.0;
       return NEG_INF;
     }
+    case F_CAT_LOGP: {   /* Categorical.bl:12-15; an index outside the simplex throws in the reference (never reached: fixed window) */
+      int z = in[f->i0];
+      if (z < 0 || z >= f->i2) return NEG_INF;
+      return log(re[f->i1 + z]);
+    }
+    case F_MIXIND_F1: {
+      int K = m->K, z = in[f->i0];
+      if (z < 0 || z >= K) return NEG_INF;
+      double v = re[K + z];
+      if (v <= 0.0) return NEG_INF;
+      return -0.5 * log(v);
+    }
+    case F_MIXIND_F2: {
+      int K = m->K, z = in[f->i0];
+      if (z < 0 || z >= K) return NEG_INF;
+      double mean = re[z], v = re[K + z], x = m->y[f->i0];
+      if (v <= 0.0) return NEG_INF;
+      return -0.5 * pow(mean - x, 2) / v;
+    }
+    case F_DUNIF_B: {
+      int x = in[f->i0];
+      if ((int)f->c0 <= x && x < (int)f->c1) return 0.0;
+      return NEG_INF;
+    }
+    case F_CP_F2: {
+      double mean = f->i0 < in[0] ? re[0] : re[1], v = f->c0, x = m->y[f->i0];
+      if (v <= 0.0) return NEG_INF;
+      return -0.5 * pow(mean - x, 2) / v;
+    }
     case F_BETABINOM: {
       double alpha = re[f->i1], beta = re[f->i2];
       double x = (double)m->yi[f->i0], n = (double)m->ntrials[f->i0];
@@ -806,6 +842,72 @@ orc_model* orc_model_mixture(const double* y, int n, int K, double m0, double v0
   return b_end(&b);
 }
 
+/* family 10: blang.examples.MixtureModel (F/MixtureModel.bl) with K components and the cluster indicators NOT
+ * marginalised: pi ~ Dirichlet(conc), mu_k ~ Normal(m0, v0), var_k ~ Gamma(shape, rate),
+ * z_i | pi ~ Categorical(pi) (latent: CategoricalSampler = IntSliceSampler with the fixed window [0, K),
+ * R/mcmc/CategoricalSampler.xtend:24-28; with K > 10 the window test of IntSliceSampler.accept :115-132 runs),
+ * y_i | z_i ~ Normal(means.get(z_i), variances.get(z_i)) (observed: annealed).
+ * Connections follow the DSL's static dependencies: the Normal's mean / variance closures read the whole lists
+ * `means` / `variances` and the indicator, so every mean's sampler sees every observation's f2, every variance's
+ * sampler every f1 and f2, and indicator i's sampler its own Categorical factor, f1_i and f2_i; the simplex sampler
+ * sees the Dirichlet factor and all n Categorical factors.
+ * reals = [mu_0..mu_{K-1}, var_0.., pi_0..]; ints = z_0..z_{n-1}; samplers: mu, var, pi (simplex), then z_i. */
+orc_model* orc_model_mixture_indicators(const double* y, int n, int K, double m0, double v0, double gshape, double grate, double conc) {
+  Builder b = b_begin(ORC_FAM_MIXTURE_INDICATORS, 3 * K, n, 2 * K + 1 + n);
+  orc_model* m = b.m;
+  m->n_obs = n; m->K = K;
+  m->y = (double*)malloc(sizeof(double) * (n > 0 ? n : 1)); memcpy(m->y, y, sizeof(double) * n);
+  m->samplers[2 * K].type = S_SIMPLEX; m->samplers[2 * K].var = 2 * K; m->samplers[2 * K].K = K;
+  b_connect(&b, 2 * K, b_factor(&b, F_DIRICHLET_A, 0, 2 * K, K, 0, conc, 0));
+  b_factor(&b, F_CONST, 0, 0, 0, 0, conc < 0 ? NEG_INF : (-K * orc_lngamma(conc) + orc_lngamma(K * conc)), 0);
+  b_forward(m, FW_DIRICHLET_SYM, 2 * K, K, conc, 0);
+  for (int k = 0; k < K; k++) {
+    m->samplers[k].type = S_REAL_SLICE; m->samplers[k].var = k;
+    m->samplers[K + k].type = S_REAL_SLICE; m->samplers[K + k].var = K + k;
+    b_normal_prior(&b, k, k, m0, v0);
+    b_gamma_prior(&b, K + k, K + k, gshape, grate, 0);
+  }
+  for (int i = 0; i < n; i++) {
+    const int sz = 2 * K + 1 + i;
+    m->samplers[sz].type = S_CATEGORICAL; m->samplers[sz].var = i; m->samplers[sz].K = K;
+    int fc = b_factor(&b, F_CAT_LOGP, 0, i, 2 * K, K, 0, 0);
+    b_connect(&b, 2 * K, fc); b_connect(&b, sz, fc);
+    b_forward(m, FW_CATEGORICAL_INT, i, K, 2 * K, 0);
+    b_factor(&b, F_CONST, 1, 0, 0, 0, -0.5 * log(2.0 * M_PI), 0);
+    int f1 = b_factor(&b, F_MIXIND_F1, 1, i, 0, 0, 0, 0);
+    int f2 = b_factor(&b, F_MIXIND_F2, 1, i, 0, 0, 0, 0);
+    for (int k = 0; k < K; k++) { b_connect(&b, k, f2); b_connect(&b, K + k, f1); b_connect(&b, K + k, f2); }
+    b_connect(&b, sz, f1); b_connect(&b, sz, f2);
+  }
+  for (int k = 0; k < K; k++) { m->init_reals[k] = 0.0; m->init_reals[K + k] = 1.0; m->init_reals[2 * K + k] = 1.0 / K; }
+  return b_end(&b);
+}
+
+/* family 11: a change-point model, the smallest model with a DiscreteUniform latent (R/distributions/DiscreteUniform.bl,
+ * sampled by UniformSampler = IntSliceSampler with the fixed window [minInclusive, maxExclusive), UniformSampler.xtend:21-27):
+ *   mu_0, mu_1 ~ Normal(m0, v0); c ~ DiscreteUniform(0, n + 1); y_i | mu, c ~ Normal(i < c ? mu_0 : mu_1, s2) with s2 a constant.
+ * The Normal's mean closure reads mu_0, mu_1 and c, so all three samplers see every f2; f0 and f1 depend on nothing latent.
+ * reals = [mu_0, mu_1]; ints = [c]; samplers: mu_0, mu_1, c. */
+orc_model* orc_model_changepoint(const double* y, int n, double m0, double v0, double s2) {
+  Builder b = b_begin(ORC_FAM_CHANGEPOINT, 2, 1, 3);
+  orc_model* m = b.m;
+  m->n_obs = n;
+  m->y = (double*)malloc(sizeof(double) * (n > 0 ? n : 1)); memcpy(m->y, y, sizeof(double) * n);
+  for (int k = 0; k < 2; k++) { m->samplers[k].type = S_REAL_SLICE; m->samplers[k].var = k; b_normal_prior(&b, k, k, m0, v0); }
+  m->samplers[2].type = S_UNIFORM; m->samplers[2].var = 0; m->samplers[2].lo = 0; m->samplers[2].K = n + 1;
+  b_factor(&b, F_CONST, 0, 0, 0, 0, -log((double)(n + 1)), 0);                       /* DiscreteUniform.bl:12-15 */
+  b_connect(&b, 2, b_factor(&b, F_DUNIF_B, 0, 0, 0, 0, 0.0, (double)(n + 1)));      /* :16-20 */
+  b_forward(m, FW_DISCRETE_UNIFORM_INT, 0, 0, 0.0, (double)(n + 1));
+  for (int i = 0; i < n; i++) {
+    b_factor(&b, F_CONST, 1, 0, 0, 0, -0.5 * log(2.0 * M_PI), 0);
+    b_factor(&b, F_CONST, 1, 0, 0, 0, s2 <= 0.0 ? NEG_INF : -0.5 * log(s2), 0);
+    int f2 = b_factor(&b, F_CP_F2, 1, i, 0, 0, s2, 0);
+    b_connect(&b, 0, f2); b_connect(&b, 1, f2); b_connect(&b, 2, f2);
+  }
+  m->init_reals[0] = 0.0; m->init_reals[1] = 0.0; m->init_ints[0] = 0;
+  return b_end(&b);
+}
+
 /* F/Ising.bl + F/Functions.xtend:8-23 (edge order preserved) */
 orc_model* orc_model_ising(int N, double coupling, double moment) {
   Builder b = b_begin(ORC_FAM_ISING, 0, N * N, N * N);
@@ -983,6 +1085,13 @@ static void sm_forward_sample(SampledModel* s, Rng* r) {
       case FW_BETA_LATENT: s->reals[f->var] = gen_beta(r, s->reals[0] + f->a, s->reals[1] + f->a); break;   /* parameters drawn just before */
       case FW_POISSON_INT: s->ints[f->var] = gen_poisson_small(r, f->a); break;
       case FW_UNIFORM: s->reals[f->var] = f->a + rng_double(r) * (f->b - f->a); break;   /* Generators.uniform :197-202 */
+      case FW_DISCRETE_UNIFORM_INT: s->ints[f->var] = gen_discrete_uniform(r, (int)f->a, (int)f->b); break;   /* :205-222 */
+      case FW_CATEGORICAL_INT: {   /* Generators.categorical :155-160 -> Random.nextCategorical: first index whose cumulative sum exceeds U */
+        const double* pi = s->reals + (int)f->a; int K = f->K;
+        double u = rng_double(r), cum = 0.0; int z = K - 1;
+        for (int d = 0; d < K; d++) { cum += pi[d]; if (u < cum) { z = d; break; } }
+        s->ints[f->var] = z;
+      } break;
       case FW_DIRICHLET_SYM: {   /* Generators.dirichletInPlace :233-272 */
         double* out = s->reals + f->var; int K = f->K; double conc = f->a;
         if (conc < 1.0) {
@@ -1150,6 +1259,7 @@ static void sampler_execute(SampledModel* s, int k, Rng* r) {
     } break;
     case S_CATEGORICAL: int_slice_execute(&c, r, 1, 0, c.sp->K); break;   /* CategoricalSampler.xtend:24-28 */
     case S_INT_SLICE: int_slice_execute(&c, r, 0, 0, 0); break;             /* IntSliceSampler on a latent IntVar */
+    case S_UNIFORM: int_slice_execute(&c, r, 1, c.sp->lo, c.sp->K); break;  /* UniformSampler.xtend:23-27 */
   }
 }
 

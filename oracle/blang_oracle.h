@@ -45,7 +45,9 @@ enum {
   ORC_FAM_IID = 6,          /* y_i ~ Dist(theta) i.i.d., theta_j ~ prior_j          */
   ORC_FAM_HIERARCHICAL = 7, /* F/HierarchicalModel.bl: a,b ~ Exp; p_g ~ Beta(a,b); y_g ~ Binomial(n_g,p_g) */
   ORC_FAM_LINREG = 8,       /* F/LinRegression.bl: w_j ~ Normal(0,v0), sigma ~ U(0,smax), y_i ~ Normal(x_i.w, sigma^2) */
-  ORC_FAM_ROCKETS_LATENT = 9/* F/SimpleHierarchicalModel.bl: family 7 with latent Poisson launch counts            */
+  ORC_FAM_ROCKETS_LATENT = 9,/* F/SimpleHierarchicalModel.bl: family 7 with latent Poisson launch counts            */
+  ORC_FAM_MIXTURE_INDICATORS = 10, /* F/MixtureModel.bl with K components, indicators NOT marginalised (CategoricalSampler) */
+  ORC_FAM_CHANGEPOINT = 11  /* change point c ~ DiscreteUniform(0, n + 1) (UniformSampler), y_i ~ Normal(i < c ? mu_0 : mu_1, s2) */
 };
 /* observation laws of family 6 and their parameters (reals, in this order) */
 enum {
@@ -90,6 +92,8 @@ orc_model* orc_model_logistic(const double* x_rowmajor, const int32_t* y, int n,
 orc_model* orc_model_mixture(const double* y, int n, int K, double m0, double v0,
                              double gshape, double grate, double conc);
 orc_model* orc_model_ising(int N, double coupling, double moment);
+orc_model* orc_model_mixture_indicators(const double* y, int n, int K, double m0, double v0, double gshape, double grate, double conc);
+orc_model* orc_model_changepoint(const double* y, int n, double m0, double v0, double s2);
 orc_model* orc_model_betabinomial(const int32_t* y, const int32_t* ntrials, int n, double rate);
 /* family 9: reals = [a, b, p_0..p_{G-1}], ints = [L_0..L_{G-1}] */
 orc_model* orc_model_rockets_latent(const int32_t* failures, int G, double rate_a, double rate_b, double pois_mean);

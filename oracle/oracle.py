@@ -73,6 +73,10 @@ def lib():
     L.orc_model_mixture.argtypes = [_dp, C.c_int, C.c_int] + [C.c_double] * 5
     L.orc_model_ising.restype = vp
     L.orc_model_ising.argtypes = [C.c_int, C.c_double, C.c_double]
+    L.orc_model_mixture_indicators.restype = vp
+    L.orc_model_mixture_indicators.argtypes = [_dp, C.c_int, C.c_int] + [C.c_double] * 5
+    L.orc_model_changepoint.restype = vp
+    L.orc_model_changepoint.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_double]
     L.orc_model_betabinomial.restype = vp
     L.orc_model_betabinomial.argtypes = [_ip, _ip, C.c_int, C.c_double]
     L.orc_pt_error.restype = C.c_int
@@ -190,6 +194,12 @@ class Model:
         elif fam == "mixture":
             y = np.ascontiguousarray(spec["y"], dtype=np.float64)
             self.h = L.orc_model_mixture(_d(y), len(y), int(h["K"]), h["m0"], h["v0"], h["gshape"], h["grate"], h["conc"])
+        elif fam == "mixture_indicators":
+            y = np.ascontiguousarray(spec["y"], dtype=np.float64)
+            self.h = L.orc_model_mixture_indicators(_d(y), len(y), int(h["K"]), h["m0"], h["v0"], h["gshape"], h["grate"], h["conc"])
+        elif fam == "changepoint":
+            y = np.ascontiguousarray(spec["y"], dtype=np.float64)
+            self.h = L.orc_model_changepoint(_d(y), len(y), h["m0"], h["v0"], h["s2"])
         elif fam == "ising":
             self.h = L.orc_model_ising(int(h["N"]), h["coupling"], h["moment"])
         elif fam == "betabinomial":

@@ -79,6 +79,56 @@ def test_eit_mixture(oracle):
          [lambda t: t[0], lambda t: t[2], lambda t: t[4], lambda t: t[0] * t[4] + t[1] * t[5]], 4)
 
 
+def _eit_mixed(oracle, make_spec, draw_prior, simulate, stat_fns, seed0):
+    """exact-invariance test for models with integer latents: theta = (reals, ints)"""
+    rng = np.random.default_rng(seed0)
+    prior_vals, post_vals = [], []
+    for rep in range(N_REP):
+        re, it = draw_prior(rng)
+        m = oracle.Model(make_spec(simulate(rng, re, it)))
+        pt = oracle.PT(m, nChains=1, seed=3000 + rep)
+        pt.set_state(0, re, it)
+        for _ in range(K_SCANS):
+            pt.scan()
+        pre, pit = pt.get_state(0)
+        prior_vals.append([f(np.asarray(re), np.asarray(it)) for f in stat_fns])
+        post_vals.append([f(pre, pit) for f in stat_fns])
+        assert pt.check_caches() < 1e-9
+    prior_vals, post_vals = np.array(prior_vals), np.array(post_vals)
+    for j in range(len(stat_fns)):
+        p = stats.ks_2samp(prior_vals[:, j], post_vals[:, j]).pvalue
+        assert p > ALPHA / len(stat_fns), "statistic %d: KS p = %.2e" % (j, p)
+
+
+@pytest.mark.parametrize("K", [2, 12])
+def test_eit_mixture_indicators(oracle, K):
+    """F/MixtureModel.bl with latent indicators, after T/TestSDKDistributions' `mix` instance: the CategoricalSampler
+    (fixed window [0, K); with K = 12 > 10 the window test of IntSliceSampler.accept runs), the simplex sampler seeing
+    the n Categorical factors, and the mean / variance samplers seeing every observation."""
+    n = 4
+    def prior(rng):
+        pi = rng.dirichlet(np.ones(K))
+        re = np.concatenate([rng.normal(0.0, 2.0, K), rng.gamma(2.0, 1.0 / 2.0, K), pi])
+        return re, rng.choice(K, size=n, p=pi).astype(np.int32)
+    def sim(rng, re, z):
+        return rng.normal(re[z], np.sqrt(re[K + z]))
+    spec = lambda y: dict(family="mixture_indicators", hyper=dict(K=K, m0=0.0, v0=4.0, gshape=2.0, grate=2.0, conc=1.0), y=y)
+    _eit_mixed(oracle, spec, prior, sim,
+               [lambda r, z: r[0], lambda r, z: r[K], lambda r, z: r[2 * K], lambda r, z: float(z[0]), lambda r, z: float(np.sum(z == 0)),
+                lambda r, z: r[z[0]]], 11 + K)
+
+
+def test_eit_changepoint(oracle):
+    """a DiscreteUniform latent moved by UniformSampler (fixed window [0, n + 1), n + 1 > 10)"""
+    n = 14
+    def prior(rng):
+        return rng.normal(0.0, 2.0, 2), np.array([rng.integers(0, n + 1)], dtype=np.int32)
+    def sim(rng, re, c):
+        return rng.normal(np.where(np.arange(n) < c[0], re[0], re[1]), 1.0)
+    spec = lambda y: dict(family="changepoint", hyper=dict(m0=0.0, v0=4.0, s2=1.0), y=y)
+    _eit_mixed(oracle, spec, prior, sim, [lambda r, c: r[0], lambda r, c: r[1], lambda r, c: float(c[0]), lambda r, c: r[0] * c[0]], 29)
+
+
 @pytest.mark.parametrize("order", ["reference", "checkerboard"])
 def test_ising_16_states(oracle, datasets, order):
     """Ising N=2 at beta = 1: state frequencies of a long single-chain run against exact enumeration."""
