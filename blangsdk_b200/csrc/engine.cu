@@ -50,6 +50,8 @@ struct blangpt_handle {
   LogisticFam::Data logistic{};
   MixtureFam<4>::Data mixture{};
   BetaBinomialFam::Data betabin{};
+  MixIndFam::Data mixind{};
+  ChangePointFam::Data changepoint{};
   IsingData ising{};
   std::vector<void*> allocs;      // every device allocation (freed in destroy)
   std::vector<double> ladder;     // host copy [R][N]
@@ -197,6 +199,8 @@ static int launch_explore_local(blangpt_handle* h, int mode) {
       if (h->mixture.K <= 4) return launch_explore_t<MixtureFam<4>>(h, h->mixture, mode);
       else { MixtureFam<8>::Data d8; memcpy(&d8, &h->mixture, sizeof d8); return launch_explore_t<MixtureFam<8>>(h, d8, mode); }
     case BLANGPT_FAM_BETABINOMIAL: return launch_explore_t<BetaBinomialFam>(h, h->betabin, mode);
+    case BLANGPT_FAM_MIXTURE_INDICATORS: return launch_explore_t<MixIndFam>(h, h->mixind, mode);
+    case BLANGPT_FAM_CHANGEPOINT: return launch_explore_t<ChangePointFam>(h, h->changepoint, mode);
     case BLANGPT_FAM_ISING: {
       int rc = ising_launch(h->E, h->ising, mode, h->stream);
       if (rc != 0) FAIL(h, BLANGPT_ECUDA, "ising launch failed: %s", cudaGetErrorString((cudaError_t)rc));
@@ -530,6 +534,25 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
       h->mixture = {y, n, K, hyper[1], hyper[2], hyper[3], hyper[4], hyper[5], rest, e1, e2, npad};
       h->n_reals = 3 * K; h->n_samplers = 2 * K + 1; rows = n;
     } break;
+    case BLANGPT_FAM_MIXTURE_INDICATORS: {
+      if (na != 1 || nh != 6 || a[0].dtype != BLANGPT_F64) FAIL(h, BLANGPT_EINVAL, "mixture_indicators: expects y[f64], hyper (K, m0, v0, gshape, grate, conc)");
+      const int n = (int)a[0].n_elem, K = (int)hyper[0];
+      if (K < 2 || K > 16) FAIL(h, BLANGPT_EUNSUPPORTED, "mixture_indicators: 2 <= K <= 16");
+      if (3 * K + n > kMaxParams + 32 || 2 * K + 1 + n > kMaxSamplers)
+        FAIL(h, BLANGPT_EUNSUPPORTED, "mixture_indicators is a small-model family: 3K + n <= %d and 2K + 1 + n <= %d (marginalise the indicators -- family MIXTURE -- for large n)", kMaxParams + 32, kMaxSamplers);
+      double* y; if ((rc = dev_alloc(h, &y, n + 2))) return rc;
+      CUDA_OK(h, cudaMemcpyAsync(y, a[0].data, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      h->mixind = {y, n, K, hyper[1], hyper[2], hyper[3], hyper[4], hyper[5]};
+      h->n_reals = 3 * K + n; h->n_samplers = 2 * K + 1 + n; rows = 1;
+    } break;
+    case BLANGPT_FAM_CHANGEPOINT: {
+      if (na != 1 || nh != 3 || a[0].dtype != BLANGPT_F64) FAIL(h, BLANGPT_EINVAL, "changepoint: expects y[f64], hyper (m0, v0, s2)");
+      const int n = (int)a[0].n_elem;
+      double* y; if ((rc = dev_alloc(h, &y, n + 2))) return rc;
+      CUDA_OK(h, cudaMemcpyAsync(y, a[0].data, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      h->changepoint = {y, n, hyper[0], hyper[1], hyper[2]};
+      h->n_reals = 3; h->n_samplers = 3; rows = n;
+    } break;
     case BLANGPT_FAM_BETABINOMIAL: {
       if (na != 2 || nh != 1 || a[0].dtype != BLANGPT_I32 || a[1].dtype != BLANGPT_I32) FAIL(h, BLANGPT_EINVAL, "betabinomial: expects y[i32 R*n], ntrials[i32 R*n], hyper (rate)");
       if (a[0].n_elem % c.nReplicas != 0 || a[0].n_elem != a[1].n_elem) FAIL(h, BLANGPT_EINVAL, "betabinomial: data size must be nReplicas * n");
@@ -567,7 +590,7 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
     } break;
     default: FAIL(h, BLANGPT_EUNSUPPORTED, "unknown model family %d: the engine only runs the closed catalogue (no CPU fallback)", family);
   }
-  h->G = family == BLANGPT_FAM_ISING ? 1 : pick_ctas_per_chain(h, rows);
+  h->G = (family == BLANGPT_FAM_ISING || family == BLANGPT_FAM_MIXTURE_INDICATORS) ? 1 : pick_ctas_per_chain(h, rows);
   // (256 threads x two CTAs per SM x twice the cluster, and 768-thread CTAs, were measured and dropped: DESIGN.md 5.1)
   if (family == BLANGPT_FAM_LOGISTIC) {
     // CTA shape: 512 threads when a cluster of CTAs serves the chain (C2: 2 x 512), 1024 when one CTA does (more
@@ -600,6 +623,7 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
   if (family == BLANGPT_FAM_BETABINOMIAL) { fill(0, 1.0); fill(1, 1.0); }
   if (family == BLANGPT_FAM_HIERARCHICAL) { fill(0, 1.0); fill(1, 1.0); for (int g = 0; g < h->hier.G; g++) fill(2 + g, 0.5); }
   if (family == BLANGPT_FAM_ROCKETS_LATENT) { fill(0, 1.0); fill(1, 1.0); for (int g = 0; g < h->rockets.G; g++) fill(2 + g, 0.5); }
+  if (family == BLANGPT_FAM_MIXTURE_INDICATORS) { const int K = h->mixind.K; for (int k = 0; k < K; k++) { fill(k, 0.0); fill(K + k, 1.0); fill(2 * K + k, 1.0 / K); } }
   if (family == BLANGPT_FAM_MIXTURE) { const int K = h->mixture.K; for (int k = 0; k < K; k++) { fill(k, 0.0); fill(K + k, 1.0); fill(2 * K + k, 1.0 / K); } }
   if (h->n_reals) CUDA_OK(h, cudaMemcpyAsync(h->E.reals, init.data(), init.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
@@ -778,7 +802,7 @@ static int scm_initialize(blangpt_handle* h) {
   c->cfg.random = h->cfg.random ^ 0x53434D2D696E6974ULL;   // its own Philox key ("SCM-init")
   c->M_total = P; c->family = h->family; c->stream = h->stream; c->logistic_threads = h->logistic_threads;
   c->n_reals = h->n_reals; c->n_ints = h->n_ints; c->n_samplers = h->n_samplers;
-  c->normal = h->normal; c->iid = h->iid; c->hier = h->hier; c->linreg = h->linreg; c->rockets = h->rockets; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising;
+  c->normal = h->normal; c->iid = h->iid; c->hier = h->hier; c->linreg = h->linreg; c->rockets = h->rockets; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising; c->mixind = h->mixind; c->changepoint = h->changepoint;
   c->betabin.chains_per_replica = P;
   auto fail = [&](int code) { for (void* p : c->allocs) cudaFree(p); if (code) h->error = c->error; delete c; return code; };
   // CUDA calls on the child go through fail(): the child's allocations are released and its message reaches the caller
@@ -793,8 +817,8 @@ static int scm_initialize(blangpt_handle* h) {
         (rc = dev_alloc(c, &c->mixture.e2, sz, false))) return fail(rc);
   }
   int64_t rows = h->family == BLANGPT_FAM_NORMAL ? h->normal.n : h->family == BLANGPT_FAM_LINREG ? h->linreg.n : h->family == BLANGPT_FAM_IID ? h->iid.n : h->family == BLANGPT_FAM_LOGISTIC ? h->logistic.n
-               : h->family == BLANGPT_FAM_MIXTURE ? h->mixture.n : 1;
-  c->G = h->family == BLANGPT_FAM_ISING || h->family == BLANGPT_FAM_BETABINOMIAL ? 1 : pick_ctas_per_chain(c, rows);
+               : h->family == BLANGPT_FAM_MIXTURE ? h->mixture.n : h->family == BLANGPT_FAM_CHANGEPOINT ? h->changepoint.n : 1;
+  c->G = h->family == BLANGPT_FAM_ISING || h->family == BLANGPT_FAM_BETABINOMIAL || h->family == BLANGPT_FAM_MIXTURE_INDICATORS ? 1 : pick_ctas_per_chain(c, rows);
   if ((rc = alloc_engine(c))) return fail(rc);
   c->model_set = true;
   if ((rc = launch_explore(c, MODE_FORWARD_INIT))) return fail(rc);   // AdaptiveJarzynski.sampleInitial :214-222
@@ -1103,6 +1127,32 @@ extern "C" int blangpt_adapt(blangpt_handle* h, double* cum_xy) {
   CUDA_OK(h, cudaMemcpyAsync((void*)h->E.ladder, h->ladder.data(), M * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
   return reset_round(h);
+}
+
+// The ladder (and cumulative-Lambda knots) blangpt_adapt WOULD install for the current round's statistics, without
+// touching the engine: PT.adapt after the last round "for instrumentation" (PT.java:103-107) for callers that want it
+// while the final round's accumulators stay readable.
+extern "C" int blangpt_adapt_preview(blangpt_handle* h, double* out_ladder, double* cum_xy) {
+  if (!h || !out_ladder) return BLANGPT_EINVAL;
+  if (!h->model_set) FAIL(h, BLANGPT_ESTATE, "set_model first");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  const int64_t M = h->M_total; const int N = h->cfg.nChains, R = h->cfg.nReplicas;
+  if (N < 2) { std::copy(h->ladder.begin(), h->ladder.end(), out_ladder); return BLANGPT_OK; }
+  std::vector<long long> acc_n(M); std::vector<double> acc_m1(M);
+  CUDA_OK(h, cudaMemcpyAsync(acc_n.data(), h->St.acc_n, M * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaMemcpyAsync(acc_m1.data(), h->St.acc_m1, M * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < R; r++) {
+    std::vector<double> betas(h->ladder.begin() + (size_t)r * N, h->ladder.begin() + (size_t)(r + 1) * N);
+    std::vector<double> acc(N - 1);
+    for (int i = 0; i < N - 1; i++) acc[i] = acc_n[(size_t)r * N + i] ? acc_m1[(size_t)r * N + i] : std::nan("");
+    std::vector<double> cx, cy;
+    std::vector<double> upd = adapt_ladder(betas, acc, &cx, &cy);
+    upd[0] = 1.0;
+    std::copy(upd.begin(), upd.end(), out_ladder + (size_t)r * N);
+    if (cum_xy) { std::copy(cx.begin(), cx.end(), cum_xy + (size_t)r * 2 * N); std::copy(cy.begin(), cy.end(), cum_xy + (size_t)r * 2 * N + N); }
+  }
+  return BLANGPT_OK;
 }
 
 extern "C" int blangpt_rounds(int32_t nScans, double f, int32_t* rn, int32_t* ra) {

@@ -20,7 +20,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libblangpt.so")
 
-FAMILIES = {"normal": 1, "logistic": 2, "mixture": 3, "ising": 4, "betabinomial": 5, "iid": 6, "hierarchical": 7, "linreg": 8, "rockets_latent": 9}
+FAMILIES = {"normal": 1, "logistic": 2, "mixture": 3, "ising": 4, "betabinomial": 5, "iid": 6, "hierarchical": 7, "linreg": 8, "rockets_latent": 9,
+            "mixture_indicators": 10, "changepoint": 11}
 # family "iid" (include/blangpt.h BLANGPT_IID_* / BLANGPT_PRIOR_*): observation laws and priors
 IID_DISTS = {"poisson": 1, "binomial": 2, "negbinomial": 3, "studentt": 4, "geometric": 5, "laplace": 6,
              "exponential": 7, "gamma": 8, "weibull": 9, "gumbel": 10, "logisticdist": 11, "halfstudentt": 12,
@@ -83,7 +84,7 @@ EXPORTS = [
     "blangpt_default_config", "blangpt_create", "blangpt_destroy", "blangpt_last_error", "blangpt_set_model",
     "blangpt_n_reals", "blangpt_n_ints", "blangpt_n_samplers", "blangpt_ctas_per_chain", "blangpt_kernel_variant", "blangpt_set_ladder", "blangpt_get_ladder",
     "blangpt_set_state", "blangpt_get_state", "blangpt_initialize", "blangpt_log_density", "blangpt_run_scans",
-    "blangpt_get_round_stats", "blangpt_adapt", "blangpt_reset_round", "blangpt_rounds",
+    "blangpt_get_round_stats", "blangpt_adapt", "blangpt_adapt_preview", "blangpt_reset_round", "blangpt_rounds",
     "blangpt_perform_inference", "blangpt_counters", "blangpt_set_stream", "blangpt_evaluate", "blangpt_prime",
     "blangpt_explore", "blangpt_table_ptr", "blangpt_local_chains", "blangpt_swap", "blangpt_synchronize",
     "blangpt_microbench", "blangpt_debug_logit_terms", "blangpt_make_ladder", "blangpt_get_diagnostics",
@@ -122,6 +123,7 @@ def load_library():
     L.blangpt_run_scans.argtypes = [vp, C.c_int32, C.POINTER(ScanOutputs)]
     L.blangpt_get_round_stats.argtypes = [vp, C.POINTER(RoundStats)]
     L.blangpt_adapt.argtypes = [vp, _dp]
+    L.blangpt_adapt_preview.argtypes = [vp, _dp, _dp]
     L.blangpt_reset_round.argtypes = [vp]
     L.blangpt_rounds.argtypes = [C.c_int32, C.c_double, _ip, _ip]
     L.blangpt_perform_inference.argtypes = [vp, C.c_int32, C.c_double, C.c_int32, C.POINTER(ScanOutputs),
@@ -275,6 +277,11 @@ class Engine:
         elif fam == "mixture":
             arrays = [arr(spec["y"], 0)]
             hyper = [float(h["K"]), h["m0"], h["v0"], h["gshape"], h["grate"], h["conc"]]
+        elif fam == "mixture_indicators":
+            arrays = [arr(spec["y"], 0)]
+            hyper = [float(h["K"]), h["m0"], h["v0"], h["gshape"], h["grate"], h["conc"]]
+        elif fam == "changepoint":
+            arrays, hyper = [arr(spec["y"], 0)], [h["m0"], h["v0"], h["s2"]]
         elif fam == "ising":
             arrays, hyper = [], [float(h["N"]), h["coupling"], h["moment"]]
         elif fam == "betabinomial":
@@ -420,6 +427,13 @@ class Engine:
         knots = np.zeros((self.R, 2, self.N))
         self._check(self.L.blangpt_adapt(self.h, _d(knots)))
         return knots
+
+    def adapt_preview(self):
+        """the ladder PT.adapt would install now (PT.java:103-107: the reference adapts once more after the last round
+        "for instrumentation"), without touching the engine; returns (ladder[R][N], knots[R][2][N])"""
+        ladder, knots = np.zeros((self.R, self.N)), np.zeros((self.R, 2, self.N))
+        self._check(self.L.blangpt_adapt_preview(self.h, _d(ladder), _d(knots)))
+        return ladder, knots
 
     def reset_round(self):
         self._check(self.L.blangpt_reset_round(self.h))

@@ -58,10 +58,18 @@ enum {
   BLANGPT_FAM_LINREG = 8,       /* F/LinRegression.bl with p covariates: w_j ~ Normal(0, v0), sigma ~ Uniform(0, smax),
                                    y_i ~ Normal(x_i . w, sigma^2).  data: x[n*p] f64 row-major, y[n] f64.
                                    hyper: v0, smax.  reals = w_0 .. w_{p-1}, sigma                                 */
-  BLANGPT_FAM_ROCKETS_LATENT = 9/* F/SimpleHierarchicalModel.bl: family 7 with latent launch counts L_g ~ Poisson(mean),
+  BLANGPT_FAM_ROCKETS_LATENT = 9,/* F/SimpleHierarchicalModel.bl: family 7 with latent launch counts L_g ~ Poisson(mean),
                                    p_g ~ Beta(a + 0.5, b + 0.5), failures_g ~ Binomial(1 + L_g, p_g); the L_g are updated
                                    by IntSliceSampler with stepping out.  data: failures[G] i32.  hyper: rate_a, rate_b,
                                    mean.  reals = a, b, p_0 .. p_{G-1}, L_0 .. L_{G-1} (the integers as exact doubles)   */
+  BLANGPT_FAM_MIXTURE_INDICATORS = 10, /* blang.examples.MixtureModel (F/MixtureModel.bl) with K components and the cluster
+                                   indicators NOT marginalised: z_i | pi ~ Categorical(pi) latent, moved by CategoricalSampler
+                                   (R/mcmc/CategoricalSampler.xtend:24-28; K > 10 runs IntSliceSampler.accept :115-132).
+                                   A small-model family: 3K + n <= 96, 2K + 1 + n <= 65.  data: y[n] f64.  hyper: K, m0, v0,
+                                   gshape, grate, conc.  reals = mu[K], var[K], pi[K], z[n] (exact doubles)               */
+  BLANGPT_FAM_CHANGEPOINT = 11  /* mu_0, mu_1 ~ Normal(m0, v0); c ~ DiscreteUniform(0, n + 1) moved by UniformSampler
+                                   (R/mcmc/UniformSampler.xtend:21-27); y_i ~ Normal(i < c ? mu_0 : mu_1, s2).  data: y[n] f64.
+                                   hyper: m0, v0, s2.  reals = mu_0, mu_1, c (exact double)                               */
 };
 /* family 6: observation laws (R/distributions/<Name>.bl) and their latent parameters, in this order */
 enum {
@@ -208,6 +216,10 @@ int blangpt_get_round_stats(blangpt_handle* h, blangpt_round_stats* out);
  * (EngineStaticUtils.java:95-168, Spline.java:129-203), then resets the accumulators.
  * cum_lambda_xy (nullable): [nReplicas][2][nChains] knots (ascending beta, cumulative Lambda). */
 int blangpt_adapt(blangpt_handle* h, double* cum_lambda_xy);
+/* What blangpt_adapt would install, without installing it.  The reference adapts once more after the last round
+ * "for instrumentation" (PT.java:103-107); here the final round's accumulators stay readable and this call returns
+ * that ladder ([nReplicas][nChains], descending) and, if cum_lambda_xy is not NULL, the knots. */
+int blangpt_adapt_preview(blangpt_handle* h, double* out_ladder, double* cum_lambda_xy);
 /* reset accumulators without changing the ladder */
 int blangpt_reset_round(blangpt_handle* h);
 
@@ -247,7 +259,12 @@ int blangpt_target_accept_ladder(blangpt_handle* h, int64_t replica, double targ
 int blangpt_rounds(int32_t nScans, double adaptFraction, int32_t* round_nscans, int32_t* round_is_adapt);
 
 /* PT.performInference (PT.java:85-113) in one call; per-round diagnostics
- * (reportParallelTemperingDiagnostics :387-505) for replica 0..nReplicas-1. */
+ * (reportParallelTemperingDiagnostics :387-505) for replica 0..nReplicas-1.
+ * BUFFER SIZES: the per-scan outputs are written for EVERY scan of EVERY round, i.e. for the SUM of the
+ * blangpt_rounds(nScans, adaptFraction) round sizes, which can exceed nScans by one (the reference's own quirk:
+ * 1000 scans at adaptFraction 0.5 run 2+4+8+16+31+63+126+251+500 = 1001 scans, PT.java:239-265).  Size `out` for
+ * that sum, not for nScans.  `thinning` is accepted for symmetry with the reference's option and ignored: every scan
+ * is recorded and the caller thins when it writes (PT.java:98-99 does `if (scanIndex % thinning == 0) recordSamples`). */
 typedef struct {
   int32_t nRounds;
   int32_t roundNScans[64];

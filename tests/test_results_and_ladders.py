@@ -169,3 +169,51 @@ def test_pigeons_protocol(oracle, datasets):
     with pytest.raises(ValueError):
         srv.handle("bogus()")
     srv.engine.close()
+
+
+def test_java_number_format():
+    """Double.toString as the JVM prints it: what Pigeons.jl parses from `response(<double>)` (Pigeons.java:66-70)"""
+    from blangsdk_b200.pigeons import java_double_to_string as f
+    cases = [(1.0, "1.0"), (-1234.5, "-1234.5"), (1e7, "1.0E7"), (9999999.0, "9999999.0"), (0.001, "0.001"), (0.00099, "9.9E-4"),
+             (1.5e-10, "1.5E-10"), (float("-inf"), "-Infinity"), (float("inf"), "Infinity"), (float("nan"), "NaN"),
+             (-2.5e100, "-2.5E100"), (123456789.125, "1.23456789125E8"), (0.0, "0.0"), (-0.0, "-0.0"), (100.0, "100.0")]
+    for x, want in cases:
+        assert f(x) == want, (x, f(x), want)
+    for x in (3.141592653589793, -98765.4321, 6.02214076e23, 1.0 / 3.0, 2.2250738585072014e-308):
+        assert float(f(x)) == x            # round trip, like Double.parseDouble(Double.toString(x))
+
+
+@pytest.mark.gpu
+def test_batched_pigeons_server(oracle, datasets):
+    """many replicas in one handle: the vector form and the tagged form give, replica by replica, what
+    a one-replica server with the same Philox key gives; -inf is printed as Java prints it"""
+    from blangsdk_b200.pigeons import BatchedPigeonsServer, PigeonsServer
+    spec = datasets.normal_meanvar(n=60)
+    R = 5
+    srv = BatchedPigeonsServer(spec, R, random=9)
+    betas = [1.0, 0.6, 0.3, 0.1, 0.0]
+    arg = ",".join(repr(b) for b in betas)
+    inp = io.StringIO("log_potential(%s)\ncall_sampler!(%s)\nlog_potential(%s)\n" % (arg, arg, arg) +
+                      "".join("@%d call_sampler!(%r)\n" % (r, betas[r]) for r in range(R)) +
+                      "".join("@%d log_potential(%r)\n" % (r, betas[r]) for r in range(R)))
+    out = io.StringIO()
+    srv.serve(inp, out)
+    lines = out.getvalue().strip().split("\n")
+    assert len(lines) == 3 + R + R and lines[1] == "response()"
+    assert lines[3:3 + R] == ["@%d response()" % r for r in range(R)]        # held until all replicas asked, then one launch
+    v_after_one = [float(v) for v in lines[2][len("response("):-1].split(",")]
+    m = oracle.Model(spec)
+    d = srv.engine.log_density()
+    for r in range(R):     # the tagged answers are the annealed densities of the states after the second launch
+        got = float(lines[3 + R + r].split("response(")[1][:-1])
+        want = d["fixed"][r, 0] + betas[r] * d["loglik"][r, 0]
+        assert abs(got - want) <= 1e-12 * max(1.0, abs(want))
+        st, _ = srv.engine.get_state(0, replica=r)
+        assert abs(m.log_density(st, beta=betas[r])["logdens"] - want) <= 1e-9 * max(1.0, abs(want))
+    assert all(math.isfinite(v) for v in v_after_one)
+    # out of support at beta = 1 prints as Java's -Infinity
+    srv.engine.set_state(0, [0.0, -1.0], None, replica=0)
+    assert srv.handle("@0 log_potential(1.0)") == ["@0 response(-Infinity)"]
+    with pytest.raises(ValueError):
+        srv.handle("log_potential(1.0)")       # vector form needs one exponent per replica
+    srv.engine.close()
