@@ -176,7 +176,7 @@ def run_gpu(args):
     import torch.distributed as dist
     from blangsdk_b200 import datasets
     from blangsdk_b200.engine import Engine, microbench
-    from blangsdk_b200.distributed import ShardedEngine
+    from blangsdk_b200.distributed import ShardedEngine, connect_peers
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -191,6 +191,8 @@ def run_gpu(args):
     spec = datasets.logistic_regression(N_ROWS, N_FEATURES)
     eng = Engine(nChains=n_chains, random=1, device=local_rank, rank=rank, worldSize=world, ctasPerChain=args.ctas)
     eng.set_model(spec)
+    if world > 1:
+        connect_peers(eng)        # mailboxes over NVLink: from here on no host code runs between the scans' kernels
     eng.initialize("COPIES")
     sh = ShardedEngine(eng)
     stream = torch.cuda.Stream(device=dev)
@@ -202,6 +204,11 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    if world > 1:
+        # the in-library exchange replaces the NCCL all-gather of ShardedEngine: explore publishes the chains' records
+        # to every rank and completes this rank's table (gather_kernel), so the step is two C calls and no collective
+        sh.exchange = lambda: None
+        sh._gather = lambda: None
     with torch.cuda.stream(stream):
         sh.prepare()
         for _ in range(args.warmup):
@@ -240,7 +247,7 @@ def run_gpu(args):
         evals, launches = int(t[0]), int(t[1])
     value = evals / (ms_total * 1e-3)
 
-    # ---- end to end through the C ABI with host buffers (rank-local engine, same workload) ----
+    # ---- end to end through the public API with host buffers: the SAME sharded engine shape as `value` ----
     e2e = None
     if not args.no_e2e:
         xs, _k1 = pinned(spec["x"]); ys, _k2 = pinned(spec["y"])
@@ -250,35 +257,39 @@ def run_gpu(args):
         for _rep in range(3):                         # three complete repetitions, the median is reported:
             barrier()                                 # a driver hiccup in create/free (seen: +0.3 s) is not the path
             t0 = time.perf_counter()
-            e2 = Engine(nChains=CHAINS_PER_GPU, random=2 + rank, device=local_rank, ctasPerChain=args.ctas)
-            e2.set_model(spec_p)                      # H2D of the data set (host pointers)
+            e2 = Engine(nChains=n_chains, random=2, device=local_rank, rank=rank, worldSize=world, ctasPerChain=args.ctas)
+            e2.set_model(spec_p)                      # H2D of the data set (host pointers), on every rank
+            if world > 1:
+                connect_peers(e2)
             e2.initialize("COPIES")
             out = e2.run_scans(k_e2e, want=("energy", "swapIndicators", "samples", "logDensity", "nOutOfSupport"))
             cc = e2.counters()
             torch.cuda.synchronize(dev)
             runs.append((time.perf_counter() - t0, cc["evals"]))
+            barrier()                                 # nobody frees its mailbox while a peer may still write to it
             e2.close()
         runs.sort()
         dt, n_evals = runs[1]
-        cc = {"evals": n_evals}
         d2h = sum(v.nbytes for v in out.values()) / k_e2e
         h2d = (xs.nbytes + ys.nbytes) / k_e2e
-        e2e_local = cc["evals"] / dt
+        e2e_value = n_evals / dt
         if world > 1:
-            t = torch.tensor([dt, float(cc["evals"])], dtype=torch.float64, device=dev)
+            t = torch.tensor([dt, float(n_evals)], dtype=torch.float64, device=dev)
             tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            e2e_local = float(tsum[1]) / float(tmax[0])
-        e2e = {"value": e2e_local, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "what": "blangpt_create + set_model (data set H2D from pinned host memory) + initialize + "
-                       "run_scans(%d) with per-scan outputs copied D2H + counters, wall clock, median of 3 "
-                       "complete repetitions; N independent 64-chain engines when N > 1" % k_e2e}
+            e2e_value = float(tsum[1]) / float(tmax[0])
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "what": "Engine(nChains=%d, worldSize=%d) create + set_model (data set H2D from pinned host memory, every rank) + "
+                       "%sinitialize + run_scans(%d) with per-scan outputs copied D2H + counters; wall clock, max over ranks, "
+                       "median of 3 complete repetitions" % (n_chains, world, "peer connect + " if world > 1 else "", k_e2e)}
 
     # ---- NRPT quality of the same workload: adaptive rounds, then round trips/s of the final round ----
     nrpt = None
-    if not args.no_nrpt and world == 1:
-        e3 = Engine(nChains=n_chains, random=5, device=local_rank, ctasPerChain=args.ctas)
+    if not args.no_nrpt:
+        e3 = Engine(nChains=n_chains, random=5, device=local_rank, rank=rank, worldSize=world, ctasPerChain=args.ctas)
         e3.set_model(spec)
+        if world > 1:
+            connect_peers(e3)
         e3.initialize("COPIES")
         t0 = time.perf_counter()
         res = e3.perform_inference(args.nrpt_scans, 0.5, want=())
@@ -293,7 +304,37 @@ def run_gpu(args):
                 "Lambda": float(last["Lambda"][0]), "mean_swap_accept": float(last["meanAccept"][0]),
                 "min_swap_accept": float(last["minAccept"][0]), "logZ_stepping_stone": float(last["logZ"][0]),
                 "wall_s": wall_nrpt}
+        st3 = e3.round_stats()
+        dens3 = e3.log_density()
+        nrpt["bottom_pair_accept"] = float(st3["swapAcceptMean"][0][-1])
+        nrpt["n_out_of_support_at_beta0"] = int(dens3["noos"][0][-1])
+        nrpt["note"] = ("round trips are 0 on this workload under the reference's own semantics: a draw from the N(0, 10) prior "
+                        "gives margins x.w with standard deviation ~18, so thousands of the 100 000 naive Bernoulli factors "
+                        "log(1 - p) are -inf (p rounds to 1.0 beyond 36.7); with annealSupport such a state has density "
+                        "-beta * 1e100 * nOutOfSupport (ExponentiatedFactor.java:82-87), the swap between the beta = 0 chain "
+                        "and its neighbour is never accepted (bottom_pair_accept), and no particle that visited beta = 0 can "
+                        "reach beta = 1.  nrpt_other holds the same measurement on workloads whose prior draws are in support.")
+        barrier()
         e3.close()
+        if rank == 0:        # BASELINE configs 0 and 2 (C1 at its named size, a down-scaled twin of C3) on this rank's GPU
+            nrpt["nrpt_other"] = []
+            for name, spec_o, chains_o, scans_o, init_o in (
+                    ("C1 Normal 1000 obs, 8 chains, 1000 scans, SCM init", datasets.normal_meanvar(), 8, 1000, "SCM"),
+                    ("C3 twin: mixture K=4, 20000 obs, 32 chains, 2000 scans, SCM init", datasets.gaussian_mixture(20000), 32, 2000, "SCM")):
+                eo = Engine(nChains=chains_o, random=7, device=local_rank)
+                eo.set_model(spec_o)
+                eo.initialize(init_o)
+                t0 = time.perf_counter()
+                ro = eo.perform_inference(scans_o, 0.5, want=())
+                wo = time.perf_counter() - t0
+                lo = ro["rounds"][-1]
+                nrpt["nrpt_other"].append({"workload": name, "final_round_scans": lo["nScans"], "final_round_s": lo["millis"] * 1e-3,
+                                           "round_trips": int(lo["roundTrips"][0]),
+                                           "round_trips_per_s": float(lo["roundTrips"][0]) / (lo["millis"] * 1e-3),
+                                           "Lambda": float(lo["Lambda"][0]), "mean_swap_accept": float(lo["meanAccept"][0]),
+                                           "min_swap_accept": float(lo["minAccept"][0]), "logZ_stepping_stone": float(lo["logZ"][0]),
+                                           "wall_s": wo, "n_gpus": 1})
+                eo.close()
 
     if rank == 0:
         peak, peak_src = read_peaks()

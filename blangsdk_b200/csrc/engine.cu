@@ -52,6 +52,7 @@ struct blangpt_handle {
   BetaBinomialFam::Data betabin{};
   MixIndFam::Data mixind{};
   ChangePointFam::Data changepoint{};
+  AnnealPairFam::Data annealpair{};
   IsingData ising{};
   std::vector<void*> allocs;      // every device allocation (freed in destroy)
   std::vector<double> ladder;     // host copy [R][N]
@@ -201,6 +202,7 @@ static int launch_explore_local(blangpt_handle* h, int mode) {
     case BLANGPT_FAM_BETABINOMIAL: return launch_explore_t<BetaBinomialFam>(h, h->betabin, mode);
     case BLANGPT_FAM_MIXTURE_INDICATORS: return launch_explore_t<MixIndFam>(h, h->mixind, mode);
     case BLANGPT_FAM_CHANGEPOINT: return launch_explore_t<ChangePointFam>(h, h->changepoint, mode);
+    case BLANGPT_FAM_ANNEAL_PAIR: return launch_explore_t<AnnealPairFam>(h, h->annealpair, mode);
     case BLANGPT_FAM_ISING: {
       int rc = ising_launch(h->E, h->ising, mode, h->stream);
       if (rc != 0) FAIL(h, BLANGPT_ECUDA, "ising launch failed: %s", cudaGetErrorString((cudaError_t)rc));
@@ -306,9 +308,18 @@ __global__ void transpose_kernel(const double* __restrict__ in, const uint8_t* _
   }
 }
 
-__global__ void init_perm_kernel(DevEngine E, int s_max_used) {
+// Initial slot <-> position map.  One process: identity.  Sharded (W ranks own contiguous blocks of slots): position p
+// starts on slot (p % W) * (N / W) + p / W, so every rank holds an even spread of the ladder from the first scan on --
+// colder chains need ~25 % more evaluations per scan, and with the identity map rank 0 would hold the whole cold half
+// until the particles have mixed.  Results are keyed by position (Philox streams, statistics), so they do not depend
+// on this map; the index process counts round trips of particles, whatever their labels.
+__global__ void init_perm_kernel(DevEngine E, int s_max_used, int world) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < E.R * E.N) { const int p = i % E.N; E.pos_of_slot[i] = p; E.slot_of_pos[i] = p; }
+  if (i < E.R * E.N) {
+    const int p = i % E.N, base = i - p;
+    const int s = world > 1 ? (p % world) * (E.N / world) + p / world : p;
+    E.slot_of_pos[base + p] = s; E.pos_of_slot[base + s] = p;
+  }
   if (i < E.M_local) {
     E.curpos[i] = -1;
     for (int k = 0; k < s_max_used; k++) E.order[(size_t)i * E.s_max + k] = k;
@@ -368,7 +379,7 @@ static int alloc_engine(blangpt_handle* h) {
     CUDA_OK(h, cudaMemsetAsync(h->mailbox, 0, h->mailbox_bytes, h->stream));
     if ((rc = dev_alloc(h, &E.peers.sample_buf, (size_t)c.nReplicas * std::max(1, h->n_reals)))) return rc;
   }
-  init_perm_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(E, h->family == BLANGPT_FAM_ISING ? 0 : h->n_samplers);
+  init_perm_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(E, h->family == BLANGPT_FAM_ISING ? 0 : h->n_samplers, c.worldSize);
   CUDA_OK(h, cudaGetLastError());
   // default ladder: EquallySpaced
   std::vector<double> one = equally_spaced(c.nChains);
@@ -544,6 +555,11 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
       CUDA_OK(h, cudaMemcpyAsync(y, a[0].data, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
       h->mixind = {y, n, K, hyper[1], hyper[2], hyper[3], hyper[4], hyper[5]};
       h->n_reals = 3 * K + n; h->n_samplers = 2 * K + 1 + n; rows = 1;
+    } break;
+    case BLANGPT_FAM_ANNEAL_PAIR: {
+      if (na != 0 || nh != 5) FAIL(h, BLANGPT_EINVAL, "anneal_pair: no data arrays, hyper (x, m0, v0, s2, manual)");
+      h->annealpair = {hyper[0], hyper[1], hyper[2], hyper[3], hyper[4] != 0.0 ? 1 : 0};
+      h->n_reals = 1; h->n_samplers = 1; rows = 1;
     } break;
     case BLANGPT_FAM_CHANGEPOINT: {
       if (na != 1 || nh != 3 || a[0].dtype != BLANGPT_F64) FAIL(h, BLANGPT_EINVAL, "changepoint: expects y[f64], hyper (m0, v0, s2)");
@@ -802,7 +818,7 @@ static int scm_initialize(blangpt_handle* h) {
   c->cfg.random = h->cfg.random ^ 0x53434D2D696E6974ULL;   // its own Philox key ("SCM-init")
   c->M_total = P; c->family = h->family; c->stream = h->stream; c->logistic_threads = h->logistic_threads;
   c->n_reals = h->n_reals; c->n_ints = h->n_ints; c->n_samplers = h->n_samplers;
-  c->normal = h->normal; c->iid = h->iid; c->hier = h->hier; c->linreg = h->linreg; c->rockets = h->rockets; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising; c->mixind = h->mixind; c->changepoint = h->changepoint;
+  c->normal = h->normal; c->iid = h->iid; c->hier = h->hier; c->linreg = h->linreg; c->rockets = h->rockets; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising; c->mixind = h->mixind; c->changepoint = h->changepoint; c->annealpair = h->annealpair;
   c->betabin.chains_per_replica = P;
   auto fail = [&](int code) { for (void* p : c->allocs) cudaFree(p); if (code) h->error = c->error; delete c; return code; };
   // CUDA calls on the child go through fail(): the child's allocations are released and its message reaches the caller

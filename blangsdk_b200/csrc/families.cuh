@@ -1571,6 +1571,56 @@ struct MixIndFam {
 };
 
 // ===========================================================================
+// Family 12: F/CustomAnnealRef.bl / F/CustomAnnealTest.bl, the pair of T/TestEndToEnd.xtend:169-186:
+//   mu ~ Normal(m0, v0); x (observed) | mu ~ Normal(mu, s2)
+// annealed automatically (three exponentiated factors) or "manually" (one LogPotential whose body multiplies
+// Normal::distribution(mu, s2).logDensity(x) by an AnnealingParameter: SampledModel.sumOtherAnnealed :219-225).
+// A custom-annealed factor that is LINEAR in the annealing parameter is carried as pre-annealing log-likelihood: the
+// annealed density fixed + beta * L is the same number at every beta either way (logDensity :161-176 adds the same
+// terms in another order), so samplers, swaps and SCM weights take identical decisions.  What differs in the
+// reference is only what it REPORTS for such a factor: energy 0 and no out-of-support softening (exponent == null);
+// the engine reports -L.  P = [mu].
+// ===========================================================================
+struct AnnealPairFam {
+  struct Data { double x, m0, v0, s2; int manual; };
+  static constexpr int kThreads = 32;
+  static constexpr bool kWarpCapable = true;
+  Data d; double* P; int* err;
+  BPT_D static int n_reals(const Data&) { return 1; }
+  BPT_D static int n_samplers(const Data&) { return 1; }
+  BPT_D void init(const Data& d_, int, double* P_, int, int, int* err_) { d = d_; P = P_; err = err_; }
+  BPT_D void set_lanes(int, int) {}
+  BPT_D int sampler_type(int) const { return S_REAL_SLICE; }
+  BPT_D int sampler_var(int) const { return 0; }
+  BPT_D int simplex_dim() const { return 0; }
+  BPT_D void begin_execution() {}
+  BPT_D static void tables_init() {}
+  BPT_D double fixed(int, double x, int) const { return normal_f2(d.m0, d.v0, x); }
+  // Normal.bl:14-24, the three blocks in file order (what Normal::distribution(mu, s2).logDensity(x) adds up)
+  BPT_D void blocks(double mu, double& s, int& c) const {
+    s = 0.0; c = 0;
+    acc_term(-0.5 * BPT_LOG_2PI, s, c, err);
+    acc_term(d.s2 <= 0.0 ? BPT_NEG_INF : -0.5 * log(d.s2), s, c, err);
+    const double dd = mu - d.x;
+    acc_term(d.s2 <= 0.0 ? BPT_NEG_INF : -0.5 * (dd * dd) / d.s2, s, c, err);
+  }
+  BPT_D void annealed(int, double x, int, GroupReducer&, double& s, int& c) const {
+    // the sampler of mu sees the block that names the mean (automatic) or the whole LogPotential (manual)
+    if (d.manual) { blocks(x, s, c); return; }
+    const double dd = x - d.x;      // Normal.bl:21-24 with mean = mu
+    s = 0.0; c = 0;
+    acc_term(d.s2 <= 0.0 ? BPT_NEG_INF : -0.5 * (dd * dd) / d.s2, s, c, err);
+  }
+  BPT_D void commit(int, double x, int) { P[0] = x; }
+  BPT_D void refresh() {}
+  BPT_D void full(GroupReducer&, double& loglik, int& noos, double& logprior) const {
+    blocks(P[0], loglik, noos);
+    logprior = -0.5 * BPT_LOG_2PI + (d.v0 <= 0.0 ? BPT_NEG_INF : -0.5 * log(d.v0)) + normal_f2(d.m0, d.v0, P[0]);
+  }
+  BPT_D void forward(Rng& rng) { const double mu = gen_normal(rng, d.m0, d.v0); P[0] = mu; }
+};
+
+// ===========================================================================
 // Family 11: change point, the smallest model with a DiscreteUniform latent (UniformSampler =
 // IntSliceSampler with the fixed window [minInclusive, maxExclusive), R/mcmc/UniformSampler.xtend:21-27).
 //   mu_0, mu_1 ~ Normal(m0, v0); c ~ DiscreteUniform(0, n + 1); y_i | mu, c ~ Normal(i < c ? mu_0 : mu_1, s2), s2 constant.

@@ -182,3 +182,10 @@ def change_point(n=200, seed=20240011):
     c = int(0.6 * n)
     y = np.concatenate([rng.normal(-0.4, 1.0, c), rng.normal(0.5, 1.0, n - c)])
     return dict(family="changepoint", y=y, hyper=dict(m0=0.0, v0=4.0, s2=1.0))
+
+
+def custom_anneal_pair(manual, x=10.0):
+    """F/CustomAnnealRef.bl (manual = False: x | mu ~ Normal(mu, 1) observed, annealed automatically) and
+    F/CustomAnnealTest.bl (manual = True: the same density as a LogPotential multiplied by an AnnealingParameter):
+    the pair of T/TestEndToEnd.xtend:169-186."""
+    return dict(family="anneal_pair", x=float(x), hyper=dict(m0=0.0, v0=1.0, s2=1.0, manual=bool(manual)))

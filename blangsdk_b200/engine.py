@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libblangpt.so")
 
 FAMILIES = {"normal": 1, "logistic": 2, "mixture": 3, "ising": 4, "betabinomial": 5, "iid": 6, "hierarchical": 7, "linreg": 8, "rockets_latent": 9,
-            "mixture_indicators": 10, "changepoint": 11}
+            "mixture_indicators": 10, "changepoint": 11, "anneal_pair": 12}
 # family "iid" (include/blangpt.h BLANGPT_IID_* / BLANGPT_PRIOR_*): observation laws and priors
 IID_DISTS = {"poisson": 1, "binomial": 2, "negbinomial": 3, "studentt": 4, "geometric": 5, "laplace": 6,
              "exponential": 7, "gamma": 8, "weibull": 9, "gumbel": 10, "logisticdist": 11, "halfstudentt": 12,
@@ -282,6 +282,8 @@ class Engine:
             hyper = [float(h["K"]), h["m0"], h["v0"], h["gshape"], h["grate"], h["conc"]]
         elif fam == "changepoint":
             arrays, hyper = [arr(spec["y"], 0)], [h["m0"], h["v0"], h["s2"]]
+        elif fam == "anneal_pair":
+            arrays, hyper = [], [float(spec["x"]), h["m0"], h["v0"], h["s2"], 1.0 if h["manual"] else 0.0]
         elif fam == "ising":
             arrays, hyper = [], [float(h["N"]), h["coupling"], h["moment"]]
         elif fam == "betabinomial":

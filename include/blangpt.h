@@ -67,6 +67,9 @@ enum {
                                    (R/mcmc/CategoricalSampler.xtend:24-28; K > 10 runs IntSliceSampler.accept :115-132).
                                    A small-model family: 3K + n <= 96, 2K + 1 + n <= 65.  data: y[n] f64.  hyper: K, m0, v0,
                                    gshape, grate, conc.  reals = mu[K], var[K], pi[K], z[n] (exact doubles)               */
+  BLANGPT_FAM_ANNEAL_PAIR = 12, /* F/CustomAnnealRef.bl / F/CustomAnnealTest.bl (T/TestEndToEnd.xtend:169-186): mu ~ Normal(m0, v0),
+                                   x | mu ~ Normal(mu, s2) annealed automatically (manual = 0) or through an AnnealingParameter
+                                   (manual = 1, SampledModel.sumOtherAnnealed :219-225).  no data.  hyper: x, m0, v0, s2, manual */
   BLANGPT_FAM_CHANGEPOINT = 11  /* mu_0, mu_1 ~ Normal(m0, v0); c ~ DiscreteUniform(0, n + 1) moved by UniformSampler
                                    (R/mcmc/UniformSampler.xtend:21-27); y_i ~ Normal(i < c ? mu_0 : mu_1, s2).  data: y[n] f64.
                                    hyper: m0, v0, s2.  reals = mu_0, mu_1, c (exact double)                               */

@@ -180,7 +180,10 @@ static double gen_beta(Rng* r, double alpha, double beta) {
  * differs from lgamma by < 3e-10 absolute for x>0 (tests/test_oracle_pins.py
  * measures it).  That is inside the 1e-9 relative bar for every catalogue
  * density but it is NOT bit parity: "parity unpinned". */
-double orc_lngamma(double x) { return lgamma(x); }
+static int g_lngamma_impl = 0;   /* 0 = libm lgamma (the documented choice), 1 = the Pike & Hill restatement */
+double orc_lngamma_pike_hill(double alpha);
+void orc_set_lngamma(int which) { g_lngamma_impl = which; }
+double orc_lngamma(double x) { return g_lngamma_impl ? orc_lngamma_pike_hill(x) : lgamma(x); }
 double orc_lngamma_pike_hill(double alpha) {
   double x = alpha, f = 0.0, z;
   if (x < 7.0) {
@@ -233,11 +236,13 @@ enum {
   F_MIXIND_F1,        /* family 10: Normal.bl:17-20 with variance = variances.get(indicator i0)                    */
   F_MIXIND_F2,        /* family 10: Normal.bl:21-24 with mean / variance of component indicator i0, x = y[i0]      */
   F_DUNIF_B,          /* family 11: DiscreteUniform.bl:16-20 support of int i0 in [c0, c1)                         */
+  F_MANUAL_NORMAL,    /* family 12: F/CustomAnnealTest.bl: Normal::distribution(mu, c1).logDensity(x = c0) * beta, beta = AnnealingParameter */
   F_CP_F2             /* family 11: Normal.bl:21-24, mean = (i0 < changePoint ? real 0 : real 1), variance = c0, x = y[i0] */
 };
 
 typedef struct {
-  int32_t kind, annealed;
+  int32_t kind, annealed;   /* annealed: 0 fixed, 1 exponentiated (automatic annealing), 2 "other annealed": reads the
+                               AnnealingParameter itself (GraphAnalysis.java:249-262), never cached (SampledModel.java:55) */
   int32_t i0, i1, i2;
   double c0, c1;
 } Factor;
@@ -249,8 +254,9 @@ typedef struct {
   int32_t var;        /* real index (REAL_SLICE), first simplex real (SIMPLEX), int index (CATEGORICAL) */
   int32_t K;          /* simplex dimension / number of categories / maxExclusive (S_UNIFORM) */
   int32_t lo;         /* minInclusive (S_UNIFORM, UniformSampler.xtend:23-27) */
-  int32_t n_fixed, n_ann;
+  int32_t n_fixed, n_ann, n_other;
   int32_t *fixed_idx, *ann_idx;   /* sampler2sparseUpdate{Fixed,Annealed}, SampledModel.java:67-69 */
+  int32_t *other_idx;             /* connected custom-annealed factors: evaluated by the sampler, not cached */
 } Sampler;
 
 enum { FW_NORMAL = 0, FW_EXPONENTIAL, FW_GAMMA, FW_DIRICHLET_SYM, FW_BERNOULLI_INT, FW_BETA, FW_UNIFORM, FW_BETA_LATENT, FW_POISSON_INT,
@@ -262,6 +268,7 @@ struct orc_model {
   int n_reals, n_ints;
   int n_factors; Factor* factors;
   int n_fixed_idx, n_ann_idx; int32_t *fixed_idx, *ann_idx;  /* sparseUpdate{Fixed,Annealed}Indices */
+  int n_other_idx; int32_t* other_idx;                        /* otherAnnealedFactors, SampledModel.java:81 */
   int n_samplers; Sampler* samplers;
   int n_forward; Forward* forward;     /* GraphAnalysis.createForwardSimulator order */
   /* data */
@@ -566,6 +573,14 @@ static double factor_eval(const orc_model* m, const Factor* f, const double* re,
       if ((int)f->c0 <= x && x < (int)f->c1) return 0.0;
       return NEG_INF;
     }
+    case F_MANUAL_NORMAL: {   /* Normal::distribution(mu, variance).logDensity(x): the three blocks of Normal.bl:14-24 in order */
+      double mean = re[f->i0], v = f->c1, x = f->c0, sum = 0.0;
+      sum += -0.5 * log(2.0 * M_PI);
+      if (v <= 0.0) return NEG_INF;
+      sum += -0.5 * log(v);
+      sum += -0.5 * pow(mean - x, 2) / v;
+      return sum;
+    }
     case F_CP_F2: {
       double mean = f->i0 < in[0] ? re[0] : re[1], v = f->c0, x = m->y[f->i0];
       if (v <= 0.0) return NEG_INF;
@@ -597,7 +612,7 @@ static void iv_push(IVec* a, int x) {
 typedef struct {
   orc_model* m;
   int fcap;
-  IVec* s_fixed; IVec* s_ann;  /* per sampler */
+  IVec* s_fixed; IVec* s_ann; IVec* s_other;  /* per sampler */
 } Builder;
 
 static int b_factor(Builder* b, int kind, int annealed, int i0, int i1, int i2, double c0, double c1) {
@@ -608,7 +623,8 @@ static int b_factor(Builder* b, int kind, int annealed, int i0, int i1, int i2, 
   return m->n_factors++;
 }
 static void b_connect(Builder* b, int sampler, int factor) {
-  iv_push(b->m->factors[factor].annealed ? &b->s_ann[sampler] : &b->s_fixed[sampler], factor);
+  const int a = b->m->factors[factor].annealed;
+  iv_push(a == 2 ? &b->s_other[sampler] : (a ? &b->s_ann[sampler] : &b->s_fixed[sampler]), factor);
 }
 static Builder b_begin(int family, int n_reals, int n_ints, int n_samplers) {
   Builder b; memset(&b, 0, sizeof b);
@@ -617,20 +633,22 @@ static Builder b_begin(int family, int n_reals, int n_ints, int n_samplers) {
   b.m->samplers = (Sampler*)calloc(n_samplers > 0 ? n_samplers : 1, sizeof(Sampler));
   b.s_fixed = (IVec*)calloc(n_samplers > 0 ? n_samplers : 1, sizeof(IVec));
   b.s_ann = (IVec*)calloc(n_samplers > 0 ? n_samplers : 1, sizeof(IVec));
+  b.s_other = (IVec*)calloc(n_samplers > 0 ? n_samplers : 1, sizeof(IVec));
   b.m->init_reals = (double*)calloc(n_reals > 0 ? n_reals : 1, sizeof(double));
   b.m->init_ints = (int32_t*)calloc(n_ints > 0 ? n_ints : 1, sizeof(int32_t));
   return b;
 }
 static orc_model* b_end(Builder* b) {
   orc_model* m = b->m;
-  IVec fx = {0, 0, 0}, an = {0, 0, 0};
-  for (int i = 0; i < m->n_factors; i++) iv_push(m->factors[i].annealed ? &an : &fx, i);
-  m->fixed_idx = fx.v; m->n_fixed_idx = fx.n; m->ann_idx = an.v; m->n_ann_idx = an.n;
+  IVec fx = {0, 0, 0}, an = {0, 0, 0}, ot = {0, 0, 0};
+  for (int i = 0; i < m->n_factors; i++) iv_push(m->factors[i].annealed == 2 ? &ot : (m->factors[i].annealed ? &an : &fx), i);
+  m->fixed_idx = fx.v; m->n_fixed_idx = fx.n; m->ann_idx = an.v; m->n_ann_idx = an.n; m->other_idx = ot.v; m->n_other_idx = ot.n;
   for (int s = 0; s < m->n_samplers; s++) {
     m->samplers[s].fixed_idx = b->s_fixed[s].v; m->samplers[s].n_fixed = b->s_fixed[s].n;
     m->samplers[s].ann_idx = b->s_ann[s].v; m->samplers[s].n_ann = b->s_ann[s].n;
+    m->samplers[s].other_idx = b->s_other[s].v; m->samplers[s].n_other = b->s_other[s].n;
   }
-  free(b->s_fixed); free(b->s_ann);
+  free(b->s_fixed); free(b->s_ann); free(b->s_other);
   return m;
 }
 static void b_forward(orc_model* m, int kind, int var, int K, double a, double bb) {
@@ -908,6 +926,27 @@ orc_model* orc_model_changepoint(const double* y, int n, double m0, double v0, d
   return b_end(&b);
 }
 
+/* family 12: F/CustomAnnealRef.bl (manual = 0) and F/CustomAnnealTest.bl (manual = 1), the pair behind
+ * T/TestEndToEnd.xtend:169-186 ("automatic and manual annealing give the same beta = 1 logDensity to 1e-10"):
+ *   mu ~ Normal(m0, v0);  x (fixed, observed) | mu ~ Normal(mu, s2)                      -- three exponentiated factors
+ *   mu ~ Normal(m0, v0);  | x, mu, beta = new AnnealingParameter ~ LogPotential(Normal::distribution(mu, s2).logDensity(x) * beta)
+ *                                                                                         -- one "other annealed" factor */
+orc_model* orc_model_anneal_pair(double x, double m0, double v0, double s2, int manual) {
+  Builder b = b_begin(ORC_FAM_ANNEAL_PAIR, 1, 0, 1);
+  orc_model* m = b.m; m->n_obs = 1;
+  m->y = (double*)malloc(sizeof(double)); m->y[0] = x;
+  m->samplers[0].type = S_REAL_SLICE; m->samplers[0].var = 0;
+  b_normal_prior(&b, 0, 0, m0, v0);
+  if (manual) b_connect(&b, 0, b_factor(&b, F_MANUAL_NORMAL, 2, 0, 0, 0, x, s2));
+  else {
+    b_factor(&b, F_CONST, 1, 0, 0, 0, -0.5 * log(2.0 * M_PI), 0);
+    b_factor(&b, F_CONST, 1, 0, 0, 0, s2 <= 0.0 ? NEG_INF : -0.5 * log(s2), 0);
+    b_connect(&b, 0, b_factor(&b, F_NORMAL_F2_PRIOR + 0, 1, 0, 0, 0, x, s2));   /* Normal.bl:21-24 with mean = mu: (mu - x)^2 is symmetric */
+  }
+  m->init_reals[0] = 0.0;
+  return b_end(&b);
+}
+
 /* F/Ising.bl + F/Functions.xtend:8-23 (edge order preserved) */
 orc_model* orc_model_ising(int N, double coupling, double moment) {
   Builder b = b_begin(ORC_FAM_ISING, 0, N * N, N * N);
@@ -947,8 +986,8 @@ orc_model* orc_model_betabinomial(const int32_t* y, const int32_t* nt, int n, do
 
 void orc_model_free(orc_model* m) {
   if (!m) return;
-  for (int s = 0; s < m->n_samplers; s++) { free(m->samplers[s].fixed_idx); free(m->samplers[s].ann_idx); }
-  free(m->samplers); free(m->factors); free(m->fixed_idx); free(m->ann_idx); free(m->forward);
+  for (int s = 0; s < m->n_samplers; s++) { free(m->samplers[s].fixed_idx); free(m->samplers[s].ann_idx); free(m->samplers[s].other_idx); }
+  free(m->samplers); free(m->factors); free(m->fixed_idx); free(m->ann_idx); free(m->other_idx); free(m->forward);
   free(m->y); free(m->x); free(m->yi); free(m->ntrials); free(m->init_reals); free(m->init_ints);
   free(m);
 }
@@ -988,13 +1027,14 @@ typedef struct {
 /* enclosedLogDensity :22-33 (NaN -> error flag; InvalidParameter is folded into the factor bodies) */
 static double sm_enclosed(SampledModel* s, int fi) {
   double r = factor_eval(s->m, &s->m->factors[fi], s->reals, s->ints);
+  if (s->m->factors[fi].annealed == 2) r = r * s->exponent;   /* `dist.logDensity(x) * beta`, beta = the AnnealingParameter */
   s->n_factor_evals++;
   if (isnan(r)) { s->error |= 1; return NEG_INF; }
   return r;
 }
 /* ExponentiatedFactor.logDensity :70-80; exponent==null (fixed factor) means 1.0 */
 static double sm_factor_log_density(SampledModel* s, int fi) {
-  double exp_value = s->m->factors[fi].annealed ? s->exponent : 1.0;
+  double exp_value = s->m->factors[fi].annealed == 1 ? s->exponent : 1.0;   /* other-annealed: exponent == null, :70-80 */
   if (exp_value == 0.0) return 0.0;
   double e = sm_enclosed(s, fi);
   if (e == NEG_INF && s->anneal_support) return annealed_minus_infinity(exp_value);
@@ -1038,11 +1078,17 @@ static void sm_update(SampledModel* s, int sampler) {
     else s->sum_pre += c;
   }
 }
-/* logDensity() :161-176 (no otherAnnealedFactors in the catalogue) */
+/* sumOtherAnnealed() :219-225: custom-annealed factors are evaluated explicitly every time */
+static double sm_sum_other_annealed(const SampledModel* s) {
+  double sum = 0.0;
+  for (int k = 0; k < s->m->n_other_idx; k++) sum += sm_factor_log_density((SampledModel*)s, s->m->other_idx[k]);
+  return sum;
+}
+/* logDensity() :161-176 */
 static double sm_log_density(const SampledModel* s) {
   double e = s->exponent;
   if (!s->anneal_support && s->n_oos > 0) return NEG_INF;
-  return 0.0 + s->sum_fixed + e * s->sum_pre +
+  return sm_sum_other_annealed(s) + s->sum_fixed + e * s->sum_pre +
          (s->n_oos == 0 ? 0.0 : s->n_oos * annealed_minus_infinity(e));
 }
 /* logDensity(beta) :190-197 */
@@ -1132,6 +1178,7 @@ static double sampler_log_density(SamplerCtx* c) {
   double sum = 0.0;
   for (int k = 0; k < sp->n_fixed; k++) sum += sm_factor_log_density(s, sp->fixed_idx[k]);
   for (int k = 0; k < sp->n_ann; k++) sum += sm_factor_log_density(s, sp->ann_idx[k]);
+  for (int k = 0; k < sp->n_other; k++) sum += sm_factor_log_density(s, sp->other_idx[k]);
   s->n_evals++;
   return sum;
 }

@@ -63,6 +63,7 @@ def lib():
     for f in ("orc_lngamma", "orc_lngamma_pike_hill", "orc_logistic"):
         getattr(L, f).restype = C.c_double
         getattr(L, f).argtypes = [C.c_double]
+    L.orc_set_lngamma.argtypes = [C.c_int]
     L.orc_log_add.restype = C.c_double
     L.orc_log_add.argtypes = [C.c_double, C.c_double]
     L.orc_model_normal.restype = vp
@@ -77,6 +78,8 @@ def lib():
     L.orc_model_mixture_indicators.argtypes = [_dp, C.c_int, C.c_int] + [C.c_double] * 5
     L.orc_model_changepoint.restype = vp
     L.orc_model_changepoint.argtypes = [_dp, C.c_int, C.c_double, C.c_double, C.c_double]
+    L.orc_model_anneal_pair.restype = vp
+    L.orc_model_anneal_pair.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
     L.orc_model_betabinomial.restype = vp
     L.orc_model_betabinomial.argtypes = [_ip, _ip, C.c_int, C.c_double]
     L.orc_pt_error.restype = C.c_int
@@ -200,6 +203,8 @@ class Model:
         elif fam == "changepoint":
             y = np.ascontiguousarray(spec["y"], dtype=np.float64)
             self.h = L.orc_model_changepoint(_d(y), len(y), h["m0"], h["v0"], h["s2"])
+        elif fam == "anneal_pair":
+            self.h = L.orc_model_anneal_pair(float(spec["x"]), h["m0"], h["v0"], h["s2"], int(h["manual"]))
         elif fam == "ising":
             self.h = L.orc_model_ising(int(h["N"]), h["coupling"], h["moment"])
         elif fam == "betabinomial":

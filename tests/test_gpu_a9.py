@@ -95,3 +95,28 @@ def test_changepoint_recovers_the_change_point(datasets):
     c = out["samples"][:, 0, 2]
     assert abs(np.median(c) - 240) < 60, np.median(c)
     eng.close()
+
+
+def test_automatic_and_manual_annealing_agree_on_the_device(oracle, datasets):
+    """T/TestEndToEnd.xtend:169-186 on the engine: PT with the reference's defaults (8 chains, 1000 scans, seed 1, SCM
+    initialisation) on F/CustomAnnealRef.bl and on F/CustomAnnealTest.bl ends with the same beta = 1 logDensity to 1e-10
+    (here: the same run, bit for bit), and both walk the oracle's trajectories."""
+    from blangsdk_b200.engine import PT
+    finals = []
+    for manual in (False, True):
+        spec = datasets.custom_anneal_pair(manual)
+        pt = PT(nChains=8, nScans=1000, adaptFraction=0.5, random=1, initialization="SCM")
+        pt.setSampledModel(spec)
+        res = pt.performInference(want=("swapIndicators", "samples", "logDensity"))
+        ref = oracle.PT(oracle.Model(spec), nChains=8, seed=1)
+        ref.initialize_scm()
+        rres = ref.perform_inference(1000, 0.5)
+        assert np.array_equal(res["swapIndicators"][:, 0, :], rres["indicators"])
+        assert rel(res["samples"][:, 0, :], rres["samples"]) < TOL
+        assert rel(res["ladder"][0], ref.get_ladder()) < TOL
+        d = pt.engine.log_density()
+        assert abs(d["logdens"][0, 0] - ref.densities()["logdens"][0]) <= 1e-9 * max(1.0, abs(d["logdens"][0, 0]))
+        finals.append((d["logdens"][0, 0], res["swapIndicators"].copy(), res["samples"].copy()))
+        pt.engine.close()
+    assert abs(finals[0][0] - finals[1][0]) <= 1e-10
+    assert np.array_equal(finals[0][1], finals[1][1]) and np.array_equal(finals[0][2], finals[1][2])

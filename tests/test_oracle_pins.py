@@ -293,3 +293,63 @@ def test_round_trip_counter_matches_path_replay(oracle, datasets):
             elif s == n - 1:
                 new = True
     assert count == pt.round_stats()["round_trips"] and count > 0
+
+
+def test_automatic_and_manual_annealing_agree(oracle, datasets):
+    """T/TestEndToEnd.xtend:169-186 (testCustomAnnealer): PT on F/CustomAnnealRef.bl (x | mu ~ Normal(mu, 1), annealed
+    automatically through ExponentiatedFactor) and on F/CustomAnnealTest.bl (the same density written as a LogPotential
+    times an AnnealingParameter, SampledModel.sumOtherAnnealed :219-225) with the reference's defaults (8 chains, 1000
+    scans, seed 1, SCM initialisation) must end with the same beta = 1 logDensity to 1e-10.  In the oracle the two
+    paths share no code below the factor list: exponent * cached pre-annealing sum vs an uncached factor that reads
+    the exponent itself."""
+    finals = []
+    for manual in (False, True):
+        m = oracle.Model(datasets.custom_anneal_pair(manual))
+        assert m.n_reals == 1 and m.n_samplers == 1
+        pt = oracle.PT(m, nChains=8, seed=1)
+        pt.initialize_scm()
+        res = pt.perform_inference(1000, 0.5)
+        d = pt.densities()
+        finals.append((d["logdens"][0], res["indicators"].copy(), pt.get_state(0)[0][0], pt.get_ladder().copy()))
+    (l1, i1, mu1, lad1), (l2, i2, mu2, lad2) = finals
+    assert abs(l1 - l2) <= 1e-10                      # the reference's own assertion
+    assert np.array_equal(i1, i2) and mu1 == mu2      # stronger: the whole run is the same
+    assert np.allclose(lad1, lad2, rtol=0, atol=1e-15)
+    # the automatic model reports the pre-annealing log-likelihood; the manual one has none (it is all "other annealed")
+    a = oracle.Model(datasets.custom_anneal_pair(False)).log_density([0.3], beta=0.4)
+    b = oracle.Model(datasets.custom_anneal_pair(True)).log_density([0.3], beta=0.4)
+    assert abs(a["logdens"] - b["logdens"]) <= 1e-12 and b["loglik"] == 0.0 and a["loglik"] != 0.0
+
+
+def test_lngamma_switch_moves_every_lgamma_based_density_by_less_than_1e9(oracle, datasets):
+    """bayonet's SpecialFunctions.lnGamma is not in the tree; the oracle uses libm lgamma and carries the
+    Pike & Hill series bayonet is believed to use as a switch.  Every catalogue density that calls lnGamma -- the
+    beta-binomial family (nine calls per factor), the hierarchical rocket models (Beta / Binomial laws), the i.i.d. laws
+    with lnGamma (Poisson, Binomial, NegativeBinomial, StudentT, Gamma, HalfStudentT, YuleSimon), Gamma / Beta priors
+    and the Dirichlet constant of the mixtures -- moves by less than 1e-9 relative under the switch, on states drawn
+    from the priors.  So WHICHEVER of the two bayonet implements, the 1e-9 parity bar of north_star holds for the other.
+    What stays unpinned: bit parity with bayonet, and the arithmetic of its Random."""
+    L = oracle.lib()
+    rng = np.random.default_rng(11)
+    specs = [datasets.beta_binomial(0), datasets.hierarchical_rockets(9), datasets.rockets_latent(6), datasets.gaussian_mixture(200),
+             datasets.mixture_with_indicators(n=20, K=3)]
+    specs += [datasets.iid_observations(d, 300) for d in ("poisson", "binomial", "negbinomial", "studentt", "gamma", "halfstudentt", "yulesimon")]
+    worst = 0.0
+    for spec in specs:
+        m = oracle.Model(spec)
+        pt = oracle.PT(m, nChains=6, seed=int(rng.integers(1, 1000)))
+        pt.initialize()                       # prior draws: lnGamma arguments spread over (0, ~100)
+        states = [pt.get_state(p) for p in range(6)]
+        vals = []
+        for which in (0, 1):
+            L.orc_set_lngamma(which)
+            try:
+                vals.append([m.log_density(re, it, beta=0.7) for re, it in states])
+            finally:
+                L.orc_set_lngamma(0)
+        for a, b in zip(*vals):
+            for key in ("logdens", "loglik", "fixed"):
+                if math.isfinite(a[key]) and math.isfinite(b[key]):
+                    worst = max(worst, abs(a[key] - b[key]) / max(1.0, abs(a[key])))
+            assert a["noos"] == b["noos"]
+    assert 0.0 < worst < 1e-9, worst          # the switch does something, and stays inside the bar
