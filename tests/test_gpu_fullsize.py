@@ -234,3 +234,35 @@ def test_c2_posterior_against_laplace(datasets):
     assert np.all(np.abs(s.mean(axis=0) - w) < 5 * se + 0.1 * sd), np.max(np.abs(s.mean(axis=0) - w) / sd)
     assert np.all(s.std(axis=0) > 0.6 * sd) and np.all(s.std(axis=0) < 1.5 * sd)
     eng.close()
+
+
+@pytest.mark.parametrize("pool", ["0", "1"])
+def test_c2_full_size_against_the_oracle(oracle, datasets, monkeypatch, pool):
+    """BASELINE config 1 at its full data size (100 000 x 32) against the ORACLE, draw for draw: four chains, one scan of
+    96 sampler executions each (the oracle needs ~ 3 ms per evaluation, a few seconds in all), through both exploration
+    kernels -- the cluster kernel and the pool kernel that bench.py times."""
+    from gpu_util import assert_trajectory_parity, make_pair, start_from
+    monkeypatch.setenv("BLANGPT_POOL", pool)
+    spec = datasets.logistic_regression()
+    eng, ref = make_pair(oracle, spec, 4, seed=17, init=None)
+    assert eng.kernel_variant == int(pool)
+    rng = np.random.default_rng(5)
+    start_from(eng, ref, [rng.normal(0.0, 0.05, 32) for _ in range(4)])      # near the mode: the regime PT spends its time in
+    assert_trajectory_parity(eng, ref, 1)
+    eng.close()
+
+
+def test_c3_full_size_against_the_oracle(oracle, datasets):
+    """BASELINE config 2 at its full data size (K = 4, 1 000 000 observations) against the ORACLE, draw for draw: two chains,
+    two scans of three sampler executions each (nPassesPerScan = 0.34 of 9 samplers; ~ 50 ms per oracle evaluation).
+    This is the size at which pass_first / pass_cached stream their per-chain scratch from HBM, two pairs per thread
+    in flight, with the warp votes and the n_valid masks of the last, ragged batch."""
+    from gpu_util import assert_trajectory_parity, make_pair, start_from
+    spec = datasets.gaussian_mixture()
+    assert len(spec["y"]) == 1_000_000
+    eng, ref = make_pair(oracle, spec, 2, seed=23, init=None, nPassesPerScan=0.34)
+    states = [[-6.1, -2.05, 1.9, 6.2, 1.1, 0.3, 0.2, 0.9, 0.25, 0.25, 0.25, 0.25],
+              [-5.0, -1.0, 1.0, 5.0, 2.0, 1.0, 1.0, 2.0, 0.1, 0.4, 0.3, 0.2]]
+    start_from(eng, ref, states)
+    assert_trajectory_parity(eng, ref, 2)
+    eng.close()
