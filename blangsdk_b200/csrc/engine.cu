@@ -197,6 +197,12 @@ static int launch_explore_local(blangpt_handle* h, int mode) {
       }
       return launch_explore_t<LogisticFam>(h, h->logistic, mode);
     case BLANGPT_FAM_MIXTURE:
+      if (h->pool) {   // persistent pool kernel (pool_mixture.cuh)
+        const int prc = pool_launch_mixture(h->pool, h->E, h->mixture, mode, h->stream);
+        if (prc != 0) FAIL(h, BLANGPT_ECUDA, "pool launch failed: %s", cudaGetErrorString((cudaError_t)prc));
+        h->n_launches++;
+        return 0;
+      }
       if (h->mixture.K <= 4) return launch_explore_t<MixtureFam<4>>(h, h->mixture, mode);
       else { MixtureFam<8>::Data d8; memcpy(&d8, &h->mixture, sizeof d8); return launch_explore_t<MixtureFam<8>>(h, d8, mode); }
     case BLANGPT_FAM_BETABINOMIAL: return launch_explore_t<BetaBinomialFam>(h, h->betabin, mode);
@@ -626,7 +632,16 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
     bool want_pool = local_chains >= 24 && rows >= 16384 && c.ctasPerChain == 0;
     if (const char* t = getenv("BLANGPT_POOL")) want_pool = atoi(t) != 0;
     if (want_pool) {
-      const int prc = pool_create(&h->pool, (int)local_chains, c.device);
+      const int prc = pool_create(&h->pool, (int)local_chains, c.device, BLANGPT_FAM_LOGISTIC, 0);
+      if (prc > 0) FAIL(h, BLANGPT_ECUDA, "pool setup failed: %s", cudaGetErrorString((cudaError_t)prc));
+    }
+  }
+  if (family == BLANGPT_FAM_MIXTURE) {   // pool kernel under the same rule as the logistic family
+    const int64_t local_chains = h->M_total / c.worldSize;
+    bool want_pool = local_chains >= 24 && rows >= 16384 && c.ctasPerChain == 0;
+    if (const char* t = getenv("BLANGPT_POOL")) want_pool = atoi(t) != 0;
+    if (want_pool) {
+      const int prc = pool_create(&h->pool, (int)local_chains, c.device, BLANGPT_FAM_MIXTURE, h->mixture.K);
       if (prc > 0) FAIL(h, BLANGPT_ECUDA, "pool setup failed: %s", cudaGetErrorString((cudaError_t)prc));
     }
   }

@@ -1,10 +1,12 @@
 // pool.cu -- host side of the pool exploration kernel (see pool.cuh for the design).
 #include "pool_host.hpp"
 #include "pool.cuh"
+#include "pool_mixture.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 #include <algorithm>
+#include <cstring>
 
 namespace bpt {
 
@@ -18,7 +20,14 @@ struct PoolState {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int pool_create(PoolState** out, int chains, int device) {
+template <class K>
+static cudaError_t prepare_kernel(K kernel, int* per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolDynSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kernel, kPoolThreads, kPoolDynSmemBytes);
+}
+
+int pool_create(PoolState** out, int chains, int device, int family, int mixture_K) {
   *out = nullptr;
   int sms = 0;
   cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -26,9 +35,8 @@ int pool_create(PoolState** out, int chains, int device) {
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
   int per_sm = 0;
-  e = cudaFuncSetAttribute(pool_kernel<LogisticPool>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolDynSmemBytes);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_kernel<LogisticPool>, kPoolThreads, kPoolDynSmemBytes);
+  if (family == 3) e = mixture_K <= 4 ? prepare_kernel(pool_kernel<MixturePool<4>>, &per_sm) : prepare_kernel(pool_kernel<MixturePool<8>>, &per_sm);
+  else e = prepare_kernel(pool_kernel<LogisticPool>, &per_sm);
   if (e != cudaSuccess) return (int)e;
   const int n_ctrl = (chains + kPoolWarps - 1) / kPoolWarps;   // controller CTAs: one chain per warp
   const int n_work = sms - n_ctrl;                             // worker CTAs: one slab of rows each
@@ -88,7 +96,20 @@ void pool_destroy(PoolState* ps) {
   delete ps;
 }
 
+template <class PF>
+static int pool_launch_t(const PoolState* psp, const DevEngine& E, const typename PF::Data& D, int mode, cudaStream_t stream);
+
 int pool_launch_logistic(const PoolState* psp, const DevEngine& E, const LogisticFam::Data& D, int mode, cudaStream_t stream) {
+  return pool_launch_t<LogisticPool>(psp, E, D, mode, stream);
+}
+int pool_launch_mixture(const PoolState* psp, const DevEngine& E, const MixtureFam<4>::Data& D, int mode, cudaStream_t stream) {
+  if (D.K <= 4) return pool_launch_t<MixturePool<4>>(psp, E, D, mode, stream);
+  MixtureFam<8>::Data d8; memcpy(&d8, &D, sizeof d8);
+  return pool_launch_t<MixturePool<8>>(psp, E, d8, mode, stream);
+}
+
+template <class PF>
+static int pool_launch_t(const PoolState* psp, const DevEngine& E, const typename PF::Data& D, int mode, cudaStream_t stream) {
   const PoolState& ps = *psp;
   const_cast<PoolState*>(psp)->launches++;
   cudaError_t e = cudaMemsetAsync(ps.control, 0, ps.control_bytes, stream);
@@ -102,7 +123,7 @@ int pool_launch_logistic(const PoolState* psp, const DevEngine& E, const Logisti
   at[0].id = cudaLaunchAttributeCooperative;
   at[0].val.cooperative = 1;
   lc.attrs = at; lc.numAttrs = 1;
-  e = cudaLaunchKernelEx(&lc, pool_kernel<LogisticPool>, E, D, ps.ctl, mode);
+  e = cudaLaunchKernelEx(&lc, pool_kernel<PF>, E, D, ps.ctl, mode);
   return (int)e;
 }
 

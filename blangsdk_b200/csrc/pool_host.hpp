@@ -11,9 +11,10 @@ struct PoolState;   // opaque: global-memory request / result blocks of one hand
 // Allocates the pool for `chains` local chains on `device`.  Returns 0 and *out != nullptr on success; 0 and
 // *out == nullptr when the pool cannot serve this shape (no cooperative launch, too many chains per SM);
 // a cudaError_t (> 0) when an allocation fails.
-int pool_create(PoolState** out, int chains, int device);
+int pool_create(PoolState** out, int chains, int device, int family /* BLANGPT_FAM_LOGISTIC | BLANGPT_FAM_MIXTURE */, int mixture_K);
 void pool_destroy(PoolState* ps);
 // one launch = one exploration pass (mode: ExploreMode) of every local chain; returns a cudaError_t
 int pool_launch_logistic(const PoolState* ps, const DevEngine& E, const LogisticFam::Data& D, int mode, cudaStream_t stream);
+int pool_launch_mixture(const PoolState* ps, const DevEngine& E, const MixtureFam<4>::Data& D, int mode, cudaStream_t stream);
 
 }  // namespace bpt

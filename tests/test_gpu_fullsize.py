@@ -252,15 +252,18 @@ def test_c2_full_size_against_the_oracle(oracle, datasets, monkeypatch, pool):
     eng.close()
 
 
-def test_c3_full_size_against_the_oracle(oracle, datasets):
+@pytest.mark.parametrize("pool", ["0", "1"])
+def test_c3_full_size_against_the_oracle(oracle, datasets, monkeypatch, pool):
     """BASELINE config 2 at its full data size (K = 4, 1 000 000 observations) against the ORACLE, draw for draw: two chains,
     two scans of three sampler executions each (nPassesPerScan = 0.34 of 9 samplers; ~ 50 ms per oracle evaluation).
     This is the size at which pass_first / pass_cached stream their per-chain scratch from HBM, two pairs per thread
     in flight, with the warp votes and the n_valid masks of the last, ragged batch."""
     from gpu_util import assert_trajectory_parity, make_pair, start_from
+    monkeypatch.setenv("BLANGPT_POOL", pool)      # both exploration kernels: one CTA per chain, and the pool (pool_mixture.cuh)
     spec = datasets.gaussian_mixture()
     assert len(spec["y"]) == 1_000_000
     eng, ref = make_pair(oracle, spec, 2, seed=23, init=None, nPassesPerScan=0.34)
+    assert eng.kernel_variant == int(pool)
     states = [[-6.1, -2.05, 1.9, 6.2, 1.1, 0.3, 0.2, 0.9, 0.25, 0.25, 0.25, 0.25],
               [-5.0, -1.0, 1.0, 5.0, 2.0, 1.0, 1.0, 2.0, 0.1, 0.4, 0.3, 0.2]]
     start_from(eng, ref, states)

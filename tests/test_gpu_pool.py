@@ -107,3 +107,61 @@ def test_pool_rounds_and_scm(oracle, datasets, pool_on):
     ref.initialize_scm(nParticles=20)
     assert_trajectory_parity(eng, ref, 3)
     eng.close()
+
+
+# ---- the mixture family (BASELINE config 2) on the pool kernel: blangsdk_b200/csrc/pool_mixture.cuh ----
+@pytest.mark.parametrize("n,chains", [(300, 5), (4_097, 3), (1, 2), (130, 1), (20_000, 6), (63, 4)])
+def test_pool_mixture_trajectory_parity(oracle, datasets, pool_on, n, chains):
+    spec = datasets.gaussian_mixture(n, seed=40 + n)
+    eng, ref = make_pair(oracle, spec, chains, seed=19)
+    assert eng.kernel_variant == 1
+    assert_trajectory_parity(eng, ref, 6)
+    eng.close()
+
+
+@pytest.mark.parametrize("opts", [dict(nPassesPerScan=0.7), dict(nPassesPerScan=3.7, usePriorSamples=False),
+                                  dict(reversible=True), dict(annealSupport=False)])
+def test_pool_mixture_engine_options(oracle, datasets, pool_on, opts):
+    spec = datasets.gaussian_mixture(2_000, seed=5)
+    eng, ref = make_pair(oracle, spec, 5, seed=8, **opts)
+    assert eng.kernel_variant == 1
+    assert_trajectory_parity(eng, ref, 5)
+    eng.close()
+
+
+def test_pool_mixture_out_of_range_rows_and_k8(oracle, datasets, pool_on):
+    """states whose mixture sums underflow on many rows (the literal path, NaN marks in the scratch array), an invalid
+    variance (out of support), and K = 8 components (the second template instance)"""
+    spec = datasets.gaussian_mixture(1_500, seed=2)
+    eng, ref = make_pair(oracle, spec, 4, seed=3, init=None)
+    states = [[-6.0, -2.0, 2.0, 6.0, 1.0, 0.25, 0.25, 1.0, 0.25, 0.25, 0.25, 0.25],
+              [300.0, 310.0, 320.0, 330.0, 1e-3, 1e-3, 1e-3, 1e-3, 0.1, 0.2, 0.3, 0.4],       # every component underflows
+              [-6.0, -2.0, 2.0, 6.0, 1.0, -0.5, 0.25, 1.0, 0.25, 0.25, 0.25, 0.25],            # a negative variance
+              [0.0, 0.0, 0.0, 0.0, 50.0, 60.0, 70.0, 80.0, 0.7, 0.1, 0.1, 0.1]]
+    start_from(eng, ref, states)
+    assert_trajectory_parity(eng, ref, 4)
+    eng.close()
+    spec8 = datasets.gaussian_mixture(900, K=8, seed=6)
+    eng, ref = make_pair(oracle, spec8, 3, seed=4)
+    assert eng.kernel_variant == 1
+    assert_trajectory_parity(eng, ref, 4)
+    eng.close()
+
+
+def test_pool_mixture_matches_cluster_kernel_and_is_deterministic(datasets, monkeypatch):
+    from blangsdk_b200.engine import Engine
+    spec = datasets.gaussian_mixture(30_000, seed=21)
+    outs = []
+    for variant in ("0", "1", "1"):
+        monkeypatch.setenv("BLANGPT_POOL", variant)
+        eng = Engine(nChains=40, random=4)
+        eng.set_model(spec)
+        assert eng.kernel_variant == int(variant)
+        eng.initialize("FORWARD")
+        outs.append((eng.run_scans(4, want=("energy", "swapIndicators", "samples")), eng.counters()["evals"]))
+        eng.close()
+    (a, ea), (b, eb), (c, ec) = outs
+    assert ea == eb == ec
+    assert np.array_equal(a["swapIndicators"], b["swapIndicators"])
+    assert rel(a["energy"], b["energy"]) < 1e-10 and rel(a["samples"], b["samples"]) < 1e-9
+    assert np.array_equal(b["energy"], c["energy"]) and np.array_equal(b["samples"], c["samples"])      # bit-identical repeat
