@@ -316,6 +316,28 @@ def run_gpu(args):
                         "reach beta = 1.  nrpt_other holds the same measurement on workloads whose prior draws are in support.")
         barrier()
         e3.close()
+        # the same shape with the slab prior of the reference's own fixture (F/SpikedGLM.bl:22, Normal(0, 1)): prior draws
+        # are in support, so particles do travel between beta = 0 and beta = 1 and the round-trip rate is not zero
+        spec1 = datasets.logistic_regression(N_ROWS, N_FEATURES, prior_var=1.0)
+        e4 = Engine(nChains=n_chains, random=6, device=local_rank, rank=rank, worldSize=world, ctasPerChain=args.ctas)
+        e4.set_model(spec1)
+        if world > 1:
+            connect_peers(e4)
+        e4.initialize("COPIES")
+        t0 = time.perf_counter()
+        res4 = e4.perform_inference(args.nrpt_scans_unit_prior, 0.5, want=())
+        wall4 = time.perf_counter() - t0
+        l4 = res4["rounds"][-1]
+        nrpt["unit_prior"] = {
+            "workload": "C2 shape (100000 x 32, %d chains) with w_j ~ Normal(0, 1), the slab of F/SpikedGLM.bl:22; "
+                        "PT.performInference(nScans=%d, adaptFraction=0.5), COPIES init" % (n_chains, args.nrpt_scans_unit_prior),
+            "final_round_scans": l4["nScans"], "final_round_s": l4["millis"] * 1e-3,
+            "round_trips": int(l4["roundTrips"][0]),
+            "round_trips_per_s": float(l4["roundTrips"][0]) / (l4["millis"] * 1e-3),
+            "Lambda": float(l4["Lambda"][0]), "mean_swap_accept": float(l4["meanAccept"][0]),
+            "min_swap_accept": float(l4["minAccept"][0]), "logZ_stepping_stone": float(l4["logZ"][0]), "wall_s": wall4}
+        barrier()
+        e4.close()
         if rank == 0:        # BASELINE configs 0 and 2 (C1 at its named size, a down-scaled twin of C3) on this rank's GPU
             nrpt["nrpt_other"] = []
             for name, spec_o, chains_o, scans_o, init_o in (
@@ -380,7 +402,9 @@ def run_gpu(args):
                            "parallelism": "chain-sharded x%d" % world},
                 "scans_per_s": 1e3 * args.steps / ms_total, "evals": evals, "wall_s_timed_region": wall,
                 "kernel_variant": "pool" if eng.kernel_variant == 1 else "cluster",
-                "round_trips_per_s": nrpt["round_trips_per_s"] if nrpt else None, "nrpt": nrpt,
+                "round_trips_per_s": nrpt["unit_prior"]["round_trips_per_s"] if nrpt else None,
+                "round_trips_workload": nrpt["unit_prior"]["workload"] if nrpt else None,
+                "round_trips_per_s_baseline_prior": nrpt["round_trips_per_s"] if nrpt else None, "nrpt": nrpt,
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cpu_cores, "kind": "port", "sample": cpu_desc}}
         print(json.dumps(line))
@@ -402,6 +426,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-nrpt", action="store_true", help="skip the adaptive NRPT run that measures round trips/s")
     ap.add_argument("--nrpt-scans", type=int, default=NRPT_SCANS)
+    ap.add_argument("--nrpt-scans-unit-prior", type=int, default=1600)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.chains_per_gpu != CHAINS_PER_GPU:

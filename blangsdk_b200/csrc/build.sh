@@ -22,7 +22,7 @@ PIDS=""
 if stale "$OBJ/engine.o" "$HERE/engine.cu" "$HERE/ising.cuh" "$HERE/schedule.hpp" "$HERE/../../include/blangpt.h" $COMMON; then
   "$NVCC" $FLAGS -c "$HERE/engine.cu" -o "$OBJ/engine.o" & PIDS="$PIDS $!"
 fi
-if stale "$OBJ/pool.o" "$HERE/pool.cu" "$HERE/pool.cuh" $COMMON; then
+if stale "$OBJ/pool.o" "$HERE/pool.cu" "$HERE/pool.cuh" "$HERE/pool_mixture.cuh" $COMMON; then
   "$NVCC" $FLAGS -c "$HERE/pool.cu" -o "$OBJ/pool.o" & PIDS="$PIDS $!"
 fi
 for p in $PIDS; do wait "$p"; done

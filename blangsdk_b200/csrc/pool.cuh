@@ -31,7 +31,13 @@
 
 namespace bpt {
 
-constexpr int kPoolThreads = 768;         // 24 warps per CTA: controller warps (one per chain), one dispatcher, the rest workers
+#ifndef BLANGPT_POOL_BELL
+#define BLANGPT_POOL_BELL 0          // idle workers sleep on an mbarrier phase (1) or poll shared memory with nanosleep (0)
+#endif
+#ifndef BLANGPT_POOL_THREADS
+#define BLANGPT_POOL_THREADS 768
+#endif
+constexpr int kPoolThreads = BLANGPT_POOL_THREADS;   // 24 warps per CTA: controller warps (one per chain), one dispatcher, the rest workers
 constexpr int kPoolWarps = kPoolThreads / 32;
 constexpr int kPoolMaxChains = 1024;      // chains per GPU served by the pool (size of the per-CTA request ring; power of two)
 constexpr int kPoolMaxSlotsPerLane = 8;   // n_SM <= 256
@@ -74,6 +80,23 @@ BPT_D void pool_st_half(PoolHalf* p, double v, uint32_t seq, int i) {
                "r"((uint32_t)__double2hiint(v)), "r"(seq), "r"((uint32_t)i) : "memory");
 }
 
+// The doorbell: idle worker warps sleep in hardware on an mbarrier phase instead of polling shared memory (ncu on
+// the polling version: a quarter of all issued instructions were idle workers' polls, competing with the working
+// warps of their scheduler).  The dispatcher arrives once per publication; a waiter names the phase by its parity.
+BPT_D void bell_init(unsigned long long* b) {
+  asm volatile("mbarrier.init.shared.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
+}
+BPT_D void bell_ring(unsigned long long* b) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared.b64 st, [%0];\n\t}" :: "r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
+}
+// sleeps until phase `parity` of the bell has completed, or for the hardware's time limit (then false)
+BPT_D bool bell_wait(unsigned long long* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
 // Requests reach the worker warps of a CTA through a ring in shared memory filled by the CTA's dispatcher warp, the
 // only warp of the SM that polls global memory for requests (every warp polling saturated the L2 slices that hold
 // the request records: 75 % of the L2's throughput went to polls).  entry.i = k | type << 8 | commit << 12 | chain << 16.
@@ -81,6 +104,9 @@ struct PoolQueue {
   unsigned int head;                              // next ticket (workers, shared-memory atomic)
   unsigned int tail;                              // entries published (dispatcher)
   int done;                                       // every chain has finished
+  int lo, hi;                                     // this SM's rows (PF::slab), the same for every request
+  unsigned int pubs;                              // publications so far (dispatcher); phase pubs of `bell` is the one in progress
+  unsigned long long bell;                        // mbarrier (count 1): the dispatcher arrives once per publication
   PoolHalf entry[kPoolMaxChains];
 };
 struct PoolSmem {
@@ -111,8 +137,13 @@ BPT_D void pool_tables_init(unsigned char* dyn) {
   for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) lg[i] = kLgtLogTabC[i >> 3];
   for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) ex[i] = kLgtExpTabC[i >> 4];
 }
-// logit_fast<2>() on the replicated tables: tl / te = shared-memory address of this lane's column of the log / exp table
-BPT_D void logit_fast2_rep(double z0, double z1, double& s, uint32_t tl, uint32_t te_base) {
+// logit_fast<2>() on the replicated tables.  tl_b = shared-memory address of this lane's column of the log table minus
+// 0x3ff00 rows (the biased exponent of u in (1, 2] is folded into the base), te_base = this lane's column of the exp
+// table.  Index arithmetic as shift + multiply-add pairs (two integer instructions per lookup); results are
+// bit-identical to logit_fast<2>().
+// Returns logit_is_fast_bits(z0) && logit_is_fast_bits(z1), evaluated on words the arithmetic produces anyway:
+// z > -12 on the high word of z - |z| (= 2 min(z, 0)), |z| < 700 (and not NaN) on the high word of z.
+BPT_D bool logit_fast2_rep(double z0, double z1, double& s, uint32_t tl, uint32_t te_base) {
   const double z[2] = {z0, z1};
   double kd[2], r[2], p[2], te[2]; int m[2];
 #pragma unroll
@@ -121,7 +152,9 @@ BPT_D void logit_fast2_rep(double z0, double z1, double& s, uint32_t tl, uint32_
     kd[w] = fma(a, kLgtK[0], kLgtK[1]);     // magic add: low word = round(-a * 64 log2 e)
     m[w] = __double2loint(kd[w]);
     kd[w] -= kLgtK[1];
-    asm("ld.shared.f64 %0, [%1];" : "=d"(te[w]) : "r"(te_base + (((uint32_t)m[w] & 63u) << 7)));
+    uint32_t ea;
+    asm("{\n\t.reg .u32 t;\n\tand.b32 t, %1, 63;\n\tmad.lo.u32 %0, t, 128, %2;\n\t}" : "=r"(ea) : "r"(m[w]), "r"(te_base));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(te[w]) : "r"(ea));
     r[w] = fma(kd[w], kLgtK[2], -a);
     r[w] = fma(kd[w], kLgtK[3], r[w]);
     p[w] = kLgtExpC[0];
@@ -134,7 +167,9 @@ BPT_D void logit_fast2_rep(double z0, double z1, double& s, uint32_t tl, uint32_
 #pragma unroll
   for (int w = 0; w < 2; w++) {
     const double tp = te[w] * p[w];
-    const double t = __hiloint2double(__double2hiint(tp) + ((m[w] >> 6) << 20), __double2loint(tp));
+    int thi;                                  // high word + ((m >> 6) << 20): scale by 2^(m >> 6)
+    asm("{\n\t.reg .s32 t;\n\tshr.s32 t, %1, 6;\n\tmad.lo.s32 %0, t, 1048576, %2;\n\t}" : "=r"(thi) : "r"(m[w]), "r"(__double2hiint(tp)));
+    const double t = __hiloint2double(thi, __double2loint(tp));
     const double u = 1.0 + t;
     const unsigned j = min(255u, (unsigned)(__double2hiint(u) - 0x3ff00000) >> 12);
     double2 cj;
@@ -147,11 +182,15 @@ BPT_D void logit_fast2_rep(double z0, double z1, double& s, uint32_t tl, uint32_
   for (int i = 1; i < 4; i++)
 #pragma unroll
     for (int w = 0; w < 2; w++) q[w] = fma(q[w], rr[w], kLgtLogC[i]);
+  bool ok = true;
 #pragma unroll
   for (int w = 0; w < 2; w++) {
     const double l = fma(rr[w] * rr[w], q[w], rr[w]) + lc[w];     // log1p(exp(-|z|))
-    s += fma(0.5, z[w] - fabs(z[w]), -l);                          // min(z,0) - log1p(exp(-|z|))
+    const double wz = z[w] - fabs(z[w]);                           // 2 min(z, 0)
+    ok = ok && (unsigned)__double2hiint(wz) < 0xC0380000u && ((unsigned)__double2hiint(z[w]) & 0x7fffffffu) < 0x4085E000u;
+    s += fma(0.5, wz, -l);                                         // min(z,0) - log1p(exp(-|z|))
   }
+  return ok;
 }
 
 // integer form of logit_is_fast(): zs > -12 (to within one high-word step) and |zs| < 700; NaN and inf fail
@@ -233,9 +272,8 @@ struct LogisticPool {
           // e, x (and q) are dead from here on: the next step's rows are loaded into the same registers right away
           // and have the whole step's arithmetic to arrive
           if (j + 64 <= n_pairs) { e = ldg2(pe + j + 32); x = ldg2(px + j + 32); if (COMMIT) q = ldg2(pp + j + 32); }
-          const bool ok = logit_is_fast_bits(za) && logit_is_fast_bits(zb);
           double t = acc;
-          logit_fast2_rep(za, zb, t, tl, te);
+          const bool ok = logit_fast2_rep(za, zb, t, tl, te);
           const bool all = __all_sync(0xffffffffu, ok);
           acc = all ? t : acc;
           bad |= all ? 0u : bit;
@@ -283,10 +321,8 @@ struct LogisticPool {
   }
 
   // a worker warp serves request (a, b) of chain c on this SM's slab; returns true when the request stored to eta
-  BPT_D static bool serve(const Data& D, const PoolCtl& pc, int c, int cta, const PoolHalf& a, const PoolHalf& b, int lane,
+  BPT_D static bool serve(const Data& D, const PoolCtl& pc, int c, int lo, int hi, const PoolHalf& a, const PoolHalf& b, int lane,
                           uint32_t tab, int* err, double& s, int& cnt) {
-    int lo, hi;
-    slab(D, cta, pc.n_cta, lo, hi);
     s = 0.0; cnt = 0;
     const int type = (a.i >> 8) & 0xf, k = a.i & 0xff;
     if (type == PR_EVAL) {
@@ -405,7 +441,7 @@ BPT_D void pool_dispatcher(const PoolCtl& pc, PoolSmem& sm, int lane) {
   const unsigned full = 0xffffffffu;
   const int C = pc.C;
   volatile unsigned int* tail_p = &sm.q.tail;
-  unsigned int tail = 0;
+  unsigned int tail = 0, pubs = 0;
   const long long t0 = clock64();
   unsigned spins = 0;
   for (;;) {
@@ -438,10 +474,15 @@ BPT_D void pool_dispatcher(const PoolCtl& pc, PoolSmem& sm, int lane) {
     if (any) {
       __syncwarp();
       __threadfence_block();
-      if (lane == 0) *tail_p = tail;
+      if (lane == 0) {
+        *tail_p = tail;
+        __threadfence_block();
+        bell_ring(&sm.q.bell);                                   // completes phase `pubs`
+        *(volatile unsigned int*)&sm.q.pubs = ++pubs;
+      }
       continue;
     }
-    if (all_done) { __syncwarp(); if (lane == 0) *(volatile int*)&sm.q.done = 1; return; }
+    if (all_done) { __syncwarp(); if (lane == 0) { *(volatile int*)&sm.q.done = 1; __threadfence_block(); bell_ring(&sm.q.bell); } return; }
     __nanosleep(20);
     if ((++spins & 1023u) == 0) {
       int stop = 0;
@@ -449,7 +490,7 @@ BPT_D void pool_dispatcher(const PoolCtl& pc, PoolSmem& sm, int lane) {
         stop = pool_ld_s32(pc.abort_flag);
         if (!stop && clock64() - t0 > 40 * kPoolTimeoutCycles) { atomicExch(pc.abort_flag, 1); stop = 1; }   // whole-launch limit
       }
-      if (__shfl_sync(full, stop, 0)) { if (lane == 0) *(volatile int*)&sm.q.done = 1; return; }
+      if (__shfl_sync(full, stop, 0)) { if (lane == 0) { *(volatile int*)&sm.q.done = 1; __threadfence_block(); bell_ring(&sm.q.bell); } return; }
     }
   }
 }
@@ -458,7 +499,12 @@ template <class PF>
 BPT_D void pool_worker(const typename PF::Data& D, const PoolCtl& pc, PoolSmem& sm, int warp, int lane, int cta, int* err) {
   const unsigned full = 0xffffffffu;
   const uint32_t tab = logit_table_address();
-  const long long t_enter = clock64();
+#ifdef BLANGPT_POOL_PROF      // cycle counters (tools/build_variant.sh <name> -DBLANGPT_POOL_PROF, run with BLANGPT_POOL_PROFILE=1)
+  const bool prof = pc.prof != nullptr;
+#else
+  constexpr bool prof = false;
+#endif
+  const long long t_enter = prof ? clock64() : 0;
   unsigned long long n_served = 0, cyc_serve = 0;
   unsigned n_poll = 0;
   volatile unsigned int* tail_p = &sm.q.tail;
@@ -469,19 +515,23 @@ BPT_D void pool_worker(const typename PF::Data& D, const PoolCtl& pc, PoolSmem& 
     if (lane == 0) ticket = atomicAdd(&sm.q.head, 1u);
     ticket = __shfl_sync(full, ticket, 0);
     bool stop = false;
-    while ((int)(*tail_p - ticket) <= 0) {
-      n_poll++;
+    for (;;) {
+      // order: publication count, then tail -- a publication that this pass misses completes the phase waited for
+      const unsigned int pubs = *(volatile unsigned int*)&sm.q.pubs;
+      if ((int)(*tail_p - ticket) > 0) break;
+      if (prof) n_poll++;
       if (*done_p) { stop = true; break; }
-      __nanosleep(150);
+      if (BLANGPT_POOL_BELL) bell_wait(&sm.q.bell, pubs & 1u);
+      else __nanosleep(150);
     }
     if (stop) {
-      if (pc.prof && lane == 0) {
+      if (prof && lane == 0) {
         unsigned long long* q = pc.prof + ((size_t)blockIdx.x * kPoolWarps + warp) * 8;
         q[0] += n_served; q[1] += cyc_serve; q[2] += (unsigned long long)(clock64() - t_enter); q[3] += n_poll;
       }
       return;
     }
-    const long long t_s0 = clock64();
+    const long long t_s0 = prof ? clock64() : 0;
     PoolHalf a = sm.q.entry[ticket & (kPoolMaxChains - 1)];
     const int hit_c = (int)((unsigned)a.i >> 16);
     // No acquire fence here: everything read below is reached through the request (address dependency) and was
@@ -491,12 +541,13 @@ BPT_D void pool_worker(const typename PF::Data& D, const PoolCtl& pc, PoolSmem& 
     b.v = 0.0; b.seq = a.seq; b.i = 0;
     if (a.i & PR_HAS_COMMIT) b = pool_ld_half(pc.reqb + hit_c);   // written (and fenced) before a
     double s; int cnt;
-    const bool stored = PF::serve(D, pc, hit_c, cta, a, b, lane, tab, err, s, cnt);
+    const bool stored = PF::serve(D, pc, hit_c, *(volatile int*)&sm.q.lo, *(volatile int*)&sm.q.hi, a, b, lane, tab, err, s, cnt);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(full, s, o); cnt += __shfl_xor_sync(full, cnt, o); }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(full, s, o);
+    if (__any_sync(full, cnt != 0)) cnt = __reduce_add_sync(full, cnt);   // out-of-support rows: rare
     if (stored) { pool_fence(); __syncwarp(); }   // release this request's eta stores before the result becomes visible
     if (lane == 0) pool_st_half(pc.slot + (size_t)hit_c * pc.n_cta + cta, s, a.seq, cnt);
-    n_served++; cyc_serve += (unsigned long long)(clock64() - t_s0);
+    if (prof) { n_served++; cyc_serve += (unsigned long long)(clock64() - t_s0); }
   }
 }
 
@@ -557,7 +608,14 @@ pool_kernel(DevEngine E, typename PF::Data D, PoolCtl pc, int mode) {
   __shared__ PoolSmem sm;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((int)blockIdx.x >= pc.n_ctrl) for (int i = tid; i < pc.C; i += blockDim.x) sm.seen[i] = 0;
-  if (tid == 0) { sm.q.head = 0; sm.q.tail = 0; sm.q.done = 0; }
+  if (tid == 0) {
+    sm.q.head = 0; sm.q.tail = 0; sm.q.done = 0; sm.q.pubs = 0;
+    if ((int)blockIdx.x >= pc.n_ctrl) {
+      int lo, hi; PF::slab(D, blockIdx.x - pc.n_ctrl, pc.n_cta, lo, hi); sm.q.lo = lo; sm.q.hi = hi;
+      bell_init(&sm.q.bell);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
   logit_table_init();
   {
     extern __shared__ __align__(128) unsigned char pool_dyn[];

@@ -34,6 +34,44 @@ struct MixturePool {
     const unsigned hi = (unsigned)__double2hiint(S);
     return hi - 0x0C100000u < (0x73D00000u - 0x0C100000u);
   }
+  // exp_tab() / log_tab() (families.cuh) on the pool's bank-conflict-free replicated tables (pool_tables_init): the
+  // same arithmetic, bit for bit; only the shared-memory addresses differ.  te / tl = this lane's column of the exp /
+  // log table.  exp_rep clamps its argument below at -700 on the high word (one integer min instead of fmax's compare
+  // and selects; arguments in (-700.016, -700) keep their own value, 1e-304 either way).
+  BPT_D static double exp_rep(double x, uint32_t te) {
+    x = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC085E000u), __double2loint(x));
+    double kd = fma(x, -kLgtK[0], kLgtK[1]);       // low word = m = round(x * 64 log2 e) = 64 k + j
+    const int m = __double2loint(kd);
+    kd -= kLgtK[1];
+    uint32_t ea;
+    asm("{\n\t.reg .u32 t;\n\tand.b32 t, %1, 63;\n\tmad.lo.u32 %0, t, 128, %2;\n\t}" : "=r"(ea) : "r"(m), "r"(te));
+    double tv;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tv) : "r"(ea));
+    double r = fma(kd, kLgtK[2], x);
+    r = fma(kd, kLgtK[3], r);
+    double p = kLgtExpC[0];
+#pragma unroll
+    for (int i = 1; i < 6; i++) p = fma(p, r, kLgtExpC[i]);
+    const double tp = tv * p;
+    int thi;
+    asm("{\n\t.reg .s32 t;\n\tshr.s32 t, %1, 6;\n\tmad.lo.s32 %0, t, 1048576, %2;\n\t}" : "=r"(thi) : "r"(m), "r"(__double2hiint(tp)));
+    return __hiloint2double(thi, __double2loint(tp));
+  }
+  BPT_D static double log_rep(double a, uint32_t tl) {   // log(a) for normal positive a
+    const int hi = __double2hiint(a);
+    const int e = (hi >> 20) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(a));   // [1, 2)
+    double2 cj;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cj.x), "=d"(cj.y) : "r"(tl + ((((uint32_t)hi >> 12) & 0xffu) << 7)));
+    const double rr = fma(m, cj.x, -1.0);
+    double q = kLgtLogC[0];
+#pragma unroll
+    for (int i = 1; i < 4; i++) q = fma(q, rr, kLgtLogC[i]);
+    const double lm = fma(rr * rr, q, rr) + cj.y;
+    return fma((double)e, 6.93147180559945309417e-01, lm);
+  }
+  BPT_D static void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
   // literal form: log( sum_k pi_k * exp(logN_k(y)) ) with library exp / log (handles -inf, 0, NaN)
   __device__ __noinline__ static void obs_slow(double yv, const Cst& C, double& s, int& c, int* err) {
     double acc = 0.0;
@@ -41,17 +79,29 @@ struct MixturePool {
     for (int q = 0; q < KT; q++) { const double dd = C.mu[q] - yv; acc += C.pi[q] * exp(fma(C.b[q], dd * dd, C.a[q])); }
     acc_term(log(acc), s, c, err);
   }
+  // the same from the request's constants in wbuf (the cached passes do not keep all K components in registers)
+  struct RowSum { double s; int c; };      // results by value: an accumulator whose address escapes lives in local memory
+  __device__ __noinline__ static RowSum obs_slow_wb(double yv, const double* wb, double s, int* err) {
+    Cst C;
+#pragma unroll
+    for (int q = 0; q < KT; q++) {
+      C.mu[q] = pool_ld_f64(wb + q); C.a[q] = pool_ld_f64(wb + KT + q); C.b[q] = pool_ld_f64(wb + 2 * KT + q); C.pi[q] = pool_ld_f64(wb + 3 * KT + q);
+    }
+    RowSum r; r.s = s; r.c = 0;
+    obs_slow(yv, C, r.s, r.c, err);
+    return r;
+  }
   // all components of one row: R = sum of the unmoved ones, S = all, E1 / E2 = the moved components' densities
-  BPT_D static void lean(double yv, const Cst& C, int j0, int j1, uint32_t tab, double& R, double& S, double& E1, double& E2) {
+  BPT_D static void lean(double yv, const Cst& C, int j0, int j1, uint32_t te, double& R, double& S, double& E1, double& E2) {
     double M = 0.0; R = 0.0; E1 = 0.0; E2 = 0.0;
 #pragma unroll
     for (int q0 = 0; q0 < KT; q0 += 4) {
       double arg[4];
 #pragma unroll
-      for (int q = 0; q < 4; q++) { const double dd = C.mu[q0 + q] - yv; arg[q] = fmax(fma(C.b[q0 + q], dd * dd, C.a[q0 + q]), -700.0); }
+      for (int q = 0; q < 4; q++) { const double dd = C.mu[q0 + q] - yv; arg[q] = fma(C.b[q0 + q], dd * dd, C.a[q0 + q]); }
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const double e = exp_tab(arg[q], tab);
+        const double e = exp_rep(arg[q], te);     // clamps at -700
         const bool moved = (q0 + q == j0) || (q0 + q == j1);
         if (q0 + q == j0) E1 = e;
         if (q0 + q == j1) E2 = e;
@@ -68,11 +118,15 @@ struct MixturePool {
     double* rest = D.rest + (size_t)c * D.npad; double* e1 = D.e1 + (size_t)c * D.npad; double* e2 = D.e2 + (size_t)c * D.npad;
     const int n_pairs = (hi - lo) >> 1;
     const double2* py = reinterpret_cast<const double2*>(D.y + lo) + lane;
+    extern __shared__ __align__(128) unsigned char pool_dyn[];
+    uint32_t tl = (uint32_t)__cvta_generic_to_shared(pool_dyn) + ((uint32_t)lane & 7u) * 16u;
+    uint32_t te = (uint32_t)__cvta_generic_to_shared(pool_dyn) + kPoolLogTabBytes + ((uint32_t)lane & 15u) * 8u;
+    asm volatile("" : "+r"(tl), "+r"(te));
     // one row, literal fallback included; r_out = NaN marks a row the cached passes must redo literally
     auto one = [&](double yv, double& r_out, double& x1, double& x2) {
       double R, S;
-      lean(yv, C, j0, j1, tab, R, S, x1, x2);
-      if (in_range(S)) { acc += log_tab(S, tab); r_out = R; }
+      lean(yv, C, j0, j1, te, R, S, x1, x2);
+      if (in_range(S)) { acc += log_rep(S, tl); r_out = R; }
       else { obs_slow(yv, C, acc, cnt, err); r_out = CUDART_NAN; }
     };
     auto store = [&](int pair, double2 r, double2 x1, double2 x2) {
@@ -89,8 +143,8 @@ struct MixturePool {
       for (; j < j_end; j += 32, bit <<= 1) {
         const double2 v = py[j];
         double2 r, x1, x2; double S0, S1;
-        lean(v.x, C, j0, j1, tab, r.x, S0, x1.x, x2.x); lean(v.y, C, j0, j1, tab, r.y, S1, x1.y, x2.y);
-        const double l0 = log_tab(S0, tab), l1 = log_tab(S1, tab);
+        lean(v.x, C, j0, j1, te, r.x, S0, x1.x, x2.x); lean(v.y, C, j0, j1, te, r.y, S1, x1.y, x2.y);
+        const double l0 = log_rep(S0, tl), l1 = log_rep(S1, tl);
         const bool all = __all_sync(0xffffffffu, in_range(S0) && in_range(S1));
         acc = all ? (acc + l0) + l1 : acc;
         bad |= all ? 0u : bit;
@@ -121,41 +175,65 @@ struct MixturePool {
 
   // PR_EVAL on rows [lo, hi): S_i = R_i + (moved terms at the candidate)
   template <bool SIMPLEX>
-  BPT_D static void cached_rows(const Data& D, int c, int lo, int hi, const Cst& C, int j0, int j1, int lane, uint32_t tab, int* err,
+  BPT_D static void cached_rows(const Data& D, int c, int lo, int hi, const double* wb, int j0, int j1, int lane, uint32_t tab, int* err,
                                 double& acc, int& cnt) {
     const double* rest = D.rest + (size_t)c * D.npad; const double* e1 = D.e1 + (size_t)c * D.npad; const double* e2 = D.e2 + (size_t)c * D.npad;
-    const double mu0 = C.mu[j0], a0 = C.a[j0], b0 = C.b[j0], pi0 = C.pi[j0];
-    const double pi1 = SIMPLEX ? C.pi[j1] : 0.0;
+    const double mu0 = pool_ld_f64(wb + j0), a0 = pool_ld_f64(wb + KT + j0), b0 = pool_ld_f64(wb + 2 * KT + j0), pi0 = pool_ld_f64(wb + 3 * KT + j0);
+    const double pi1 = SIMPLEX ? pool_ld_f64(wb + 3 * KT + j1) : 0.0;
     const int n_pairs = (hi - lo) >> 1;
     const double2* py = reinterpret_cast<const double2*>(D.y + lo) + lane;
     const double2* pr = reinterpret_cast<const double2*>(rest + lo) + lane;
     const double2* p1 = reinterpret_cast<const double2*>(e1 + lo) + lane;
     const double2* p2 = reinterpret_cast<const double2*>(e2 + lo) + lane;
+    // opaque: the stream pointers stay in registers (the compiler otherwise re-derives them from the kernel
+    // arguments inside the hot loop, a dozen instructions per step)
+    asm volatile("" : "+l"(py), "+l"(pr));
+    if (SIMPLEX) asm volatile("" : "+l"(p1), "+l"(p2));
+    extern __shared__ __align__(128) unsigned char pool_dyn[];
+    uint32_t tl = (uint32_t)__cvta_generic_to_shared(pool_dyn) + ((uint32_t)lane & 7u) * 16u;
+    uint32_t te = (uint32_t)__cvta_generic_to_shared(pool_dyn) + kPoolLogTabBytes + ((uint32_t)lane & 15u) * 8u;
+    asm volatile("" : "+r"(tl), "+r"(te));   // opaque: kept in registers instead of being re-derived per use
     auto value = [&](double yv, double R, double E1, double E2) {
-      if (!SIMPLEX) { const double dd = mu0 - yv; return fma(pi0, exp_tab(fmax(fma(b0, dd * dd, a0), -700.0), tab), R); }
+      if (!SIMPLEX) { const double dd = mu0 - yv; return fma(pi0, exp_rep(fma(b0, dd * dd, a0), te), R); }
       return fma(pi0, E1, fma(pi1, E2, R));
     };
+    // out-of-line step for the rare literal rows: same arithmetic as the lean path where the lean path applies
     auto one = [&](double yv, double R, double E1, double E2) {
       const double S = value(yv, R, E1, E2);
-      if (in_range(S)) acc += log_tab(S, tab);
-      else obs_slow(yv, C, acc, cnt, err);
+      if (in_range(S)) acc += log_rep(S, tl);
+      else { const RowSum r = obs_slow_wb(yv, wb, acc, err); acc = r.s; cnt += r.c; }
     };
     int j = 0;
     if (n_pairs >= 32) {
-      // the scratch streams from HBM (no reuse inside an evaluation): two steps ahead; y is cache-resident: one step
-      double2 r0 = __ldcs(pr), r1 = n_pairs >= 64 ? __ldcs(pr + 32) : make_double2(0.0, 0.0), v = py[0];
-      double2 f0 = make_double2(0.0, 0.0), f1 = f0, g0 = f0, g1 = f0;
-      if (SIMPLEX) { f0 = __ldcs(p1); g0 = __ldcs(p2); if (n_pairs >= 64) { f1 = __ldcs(p1 + 32); g1 = __ldcs(p2 + 32); } }
+      // The scratch arrays stream from HBM (no reuse inside an evaluation).  One lane in eight asks the L2 for the
+      // 128-byte line kAhead steps ahead; the registers are refilled one step ahead, right after their last use
+      // (the loads then find their line in the L2), so no register set is rotated.  y is cache-resident.
+      constexpr int kAhead = 6;
+      bool pf_lane = (lane & 7) == 0;
+      { int t = pf_lane; asm volatile("" : "+r"(t)); pf_lane = t != 0; }   // opaque: not re-derived from %tid per step
+      if (pf_lane) {
+#pragma unroll
+        for (int a = 1; a < kAhead; a++)
+          if (32 * a + 32 <= n_pairs) { prefetch_l2(pr + 32 * a); if (SIMPLEX) { prefetch_l2(p1 + 32 * a); prefetch_l2(p2 + 32 * a); } }
+      }
+      double2 r0 = __ldcs(pr), v = py[0];
+      double2 f0 = make_double2(0.0, 0.0), g0 = f0;
+      if (SIMPLEX) { f0 = __ldcs(p1); g0 = __ldcs(p2); }
       while (j + 32 <= n_pairs) {
         const int j_block = j;
         unsigned bad = 0u, bit = 1u;
         const int j_end = min(n_pairs - 31, j_block + 32 * 32);
         for (; j < j_end; j += 32, bit <<= 1) {
           const double S0 = value(v.x, r0.x, f0.x, g0.x), S1 = value(v.y, r0.y, f0.y, g0.y);
-          r0 = r1; if (SIMPLEX) { f0 = f1; g0 = g1; }
-          if (j + 96 <= n_pairs) { r1 = __ldcs(pr + j + 64); if (SIMPLEX) { f1 = __ldcs(p1 + j + 64); g1 = __ldcs(p2 + j + 64); } }
-          if (j + 64 <= n_pairs) v = py[j + 32];
-          const double l0 = log_tab(S0, tab), l1 = log_tab(S1, tab);
+          if (j + 64 <= n_pairs) {
+            r0 = __ldcs(pr + j + 32); v = py[j + 32];
+            if (SIMPLEX) { f0 = __ldcs(p1 + j + 32); g0 = __ldcs(p2 + j + 32); }
+          }
+          if (pf_lane && j + 32 * kAhead + 32 <= n_pairs) {
+            prefetch_l2(pr + j + 32 * kAhead);
+            if (SIMPLEX) { prefetch_l2(p1 + j + 32 * kAhead); prefetch_l2(p2 + j + 32 * kAhead); }
+          }
+          const double l0 = log_rep(S0, tl), l1 = log_rep(S1, tl);
           const bool all = __all_sync(0xffffffffu, in_range(S0) && in_range(S1));
           acc = all ? (acc + l0) + l1 : acc;
           bad |= all ? 0u : bit;
@@ -182,16 +260,20 @@ struct MixturePool {
     }
   }
 
-  BPT_D static bool serve(const Data& D, const PoolCtl& pc, int c, int cta, const PoolHalf& a, const PoolHalf&, int lane,
+  BPT_D static bool serve(const Data& D, const PoolCtl& pc, int c, int lo, int hi, const PoolHalf& a, const PoolHalf&, int lane,
                           uint32_t tab, int* err, double& s, int& cnt) {
-    int lo, hi;
-    slab(D, cta, pc.n_cta, lo, hi);
     s = 0.0; cnt = 0;
     const int type = (a.i >> 8) & 0xf, k = a.i & 0xff, aux = (a.i >> 13) & 7, K = D.K;
     const int j0 = k < K ? k : (k < 2 * K ? k - K : aux);
     const int j1 = k < 2 * K ? -1 : (aux == K - 1 ? 0 : aux + 1);
-    // this evaluation's component constants, written by the controller before the request (fenced): lanes fetch one each
-    const double mine = lane < 4 * KT ? pool_ld_f64(pc.wbuf + (size_t)c * kMaxParams + lane) : 0.0;
+    // this evaluation's component constants, written by the controller before the request (fenced)
+    const double* wb = pc.wbuf + (size_t)c * kMaxParams;
+    if (type == PR_EVAL) {
+      if (j1 < 0) cached_rows<false>(D, c, lo, hi, wb, j0, j1, lane, tab, err, s, cnt);
+      else cached_rows<true>(D, c, lo, hi, wb, j0, j1, lane, tab, err, s, cnt);
+      return false;
+    }
+    const double mine = lane < 4 * KT ? pool_ld_f64(wb + lane) : 0.0;     // lanes fetch one constant each
     Cst C;
 #pragma unroll
     for (int q = 0; q < KT; q++) {
@@ -199,9 +281,7 @@ struct MixturePool {
       C.b[q] = __shfl_sync(0xffffffffu, mine, 2 * KT + q); C.pi[q] = __shfl_sync(0xffffffffu, mine, 3 * KT + q);
     }
     if (type == PR_FIRST) { first_rows<true>(D, c, lo, hi, C, j0, j1, lane, tab, err, s, cnt); return true; }
-    if (type == PR_FULL) { first_rows<false>(D, c, lo, hi, C, -1, -1, lane, tab, err, s, cnt); return false; }
-    if (j1 < 0) cached_rows<false>(D, c, lo, hi, C, j0, j1, lane, tab, err, s, cnt);
-    else cached_rows<true>(D, c, lo, hi, C, j0, j1, lane, tab, err, s, cnt);
+    first_rows<false>(D, c, lo, hi, C, -1, -1, lane, tab, err, s, cnt);   // PR_FULL
     return false;
   }
 

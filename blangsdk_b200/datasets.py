@@ -18,15 +18,16 @@ def normal_meanvar(n=1000, seed=SEED_C1):
     return dict(family="normal", hyper=dict(m0=0.0, v0=100.0, rate=0.1), y=y)
 
 
-def logistic_regression(n=100_000, p=32, seed=SEED_C2):
-    """C2: X ~ N(0,1) with column 0 == 1, w* ~ N(0, 0.5^2), y ~ Bernoulli(logistic(X w*)); w_j ~ Normal(0,10)."""
+def logistic_regression(n=100_000, p=32, seed=SEED_C2, prior_var=10.0):
+    """C2: X ~ N(0,1) with column 0 == 1, w* ~ N(0, 0.5^2), y ~ Bernoulli(logistic(X w*)); w_j ~ Normal(0, prior_var)
+    (variance 10; the reference's own fixture F/SpikedGLM.bl:22 uses a Normal(0, 1) slab)."""
     rng = np.random.default_rng(seed)
     x = rng.standard_normal((n, p))
     x[:, 0] = 1.0
     w = rng.normal(0.0, 0.5, p)
     eta = x @ w
     y = (rng.random(n) < 1.0 / (1.0 + np.exp(-eta))).astype(np.int32)
-    return dict(family="logistic", hyper=dict(v0=10.0), x=x, y=y, w_true=w)
+    return dict(family="logistic", hyper=dict(v0=float(prior_var)), x=x, y=y, w_true=w)
 
 
 def gaussian_mixture(n=1_000_000, K=4, seed=SEED_C3):

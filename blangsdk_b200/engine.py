@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libblangpt.so")
+LIB_PATH = os.environ.get("BLANGPT_LIB") or os.path.join(_HERE, "libblangpt.so")   # BLANGPT_LIB: A/B of kernel builds (tools/build_variant.sh)
 
 FAMILIES = {"normal": 1, "logistic": 2, "mixture": 3, "ising": 4, "betabinomial": 5, "iid": 6, "hierarchical": 7, "linreg": 8, "rockets_latent": 9,
             "mixture_indicators": 10, "changepoint": 11, "anneal_pair": 12}
