@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 #include <chrono>
+#include <algorithm>
+#include <cmath>
 
 #include "kernels.cuh"
 #include "ising.cuh"
@@ -55,6 +57,9 @@ struct blangpt_handle {
   AnnealPairFam::Data annealpair{};
   IsingData ising{};
   std::vector<void*> allocs;      // every device allocation (freed in destroy)
+  // device-side staging of run_scans' per-scan outputs: kept across calls and grown on demand (a cudaMalloc /
+  // cudaFree pair per output per call costs a device synchronisation each)
+  struct OutBuf { void* p = nullptr; size_t bytes = 0; } outbuf[6];
   std::vector<double> ladder;     // host copy [R][N]
   uint64_t n_scans = 0, n_launches = 0;
   int64_t scans_in_round = 0;
@@ -136,6 +141,7 @@ extern "C" void blangpt_destroy(blangpt_handle* h) {
   for (void* p : h->peer_maps) if (p) cudaIpcCloseMemHandle(p);
   if (h->mailbox) cudaFree(h->mailbox);
   for (void* p : h->allocs) cudaFree(p);
+  for (auto& b : h->outbuf) if (b.p) cudaFree(b.p);
   pool_destroy(h->pool); h->pool = nullptr;
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -628,8 +634,11 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
     if (const char* t = getenv("BLANGPT_L2AHEAD")) h->logistic_l2ahead = atoi(t) != 0;
     // Pool kernel (pool.cuh) when there are enough chains to keep every SM busy with other chains' rows while one
     // chain's request is in flight; an explicit ctasPerChain asks for the cluster kernel.  BLANGPT_POOL=0/1 overrides.
+    // Measured on the C2 shape (profiles/configs_r02.jsonl), M evals/s pool | cluster: 64 chains 3.98 | 2.78, 128: 2.93 | 2.58,
+    // 256: 2.78 | 2.72, 512: 2.60 | 3.13, 1024: 2.42 | 2.88 -- beyond 256 chains per GPU one CTA per chain keeps every
+    // SM busy by itself and the controllers' SMs are better spent on rows.
     const int64_t local_chains = h->M_total / c.worldSize;
-    bool want_pool = local_chains >= 24 && rows >= 16384 && c.ctasPerChain == 0;
+    bool want_pool = local_chains >= 24 && local_chains <= 256 && rows >= 16384 && c.ctasPerChain == 0;
     if (const char* t = getenv("BLANGPT_POOL")) want_pool = atoi(t) != 0;
     if (want_pool) {
       const int prc = pool_create(&h->pool, (int)local_chains, c.device, BLANGPT_FAM_LOGISTIC, 0);
@@ -1015,15 +1024,27 @@ extern "C" int blangpt_run_scans(blangpt_handle* h, int32_t n_scans, const blang
   if ((rc = ensure_tables(h))) return rc;
   const int64_t M = h->M_total; const int R = h->cfg.nReplicas;
   DevOut O{}; O.n_reals = h->n_reals; O.reversible = h->cfg.reversible;
-  struct TmpBuffers { std::vector<void*> v; ~TmpBuffers() { for (void* p : v) cudaFree(p); } void push_back(void* p) { v.push_back(p); } } tmp;
+  int next_buf = 0;
+  auto staging = [&](size_t bytes, void** out_p) -> int {      // the handle's next staging buffer, at least `bytes` long
+    blangpt_handle::OutBuf& b = h->outbuf[next_buf++];
+    bytes = std::max<size_t>(1, bytes);
+    if (b.bytes < bytes) {
+      if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+      cudaError_t e = cudaMalloc(&b.p, bytes);
+      if (e != cudaSuccess) { b.p = nullptr; set_error(h, "cudaMalloc(outputs): %s", cudaGetErrorString(e)); return BLANGPT_ECUDA; }
+      b.bytes = bytes;
+    }
+    cudaMemsetAsync(b.p, 0, bytes, h->stream);
+    *out_p = b.p;
+    return 0;
+  };
   auto alloc_out = [&](auto** dptr, const void* hostptr, size_t n) -> int {
-    if (!hostptr) return 0;
+    if (!hostptr) { next_buf++; return 0; }
     using T = std::remove_pointer_t<std::remove_pointer_t<decltype(dptr)>>;
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, std::max<size_t>(1, n) * sizeof(T));
-    if (e != cudaSuccess) { set_error(h, "cudaMalloc(outputs): %s", cudaGetErrorString(e)); return BLANGPT_ECUDA; }
-    cudaMemsetAsync(p, 0, std::max<size_t>(1, n) * sizeof(T), h->stream);
-    tmp.push_back(p); *dptr = (T*)p; return 0;
+    const int rc2 = staging(n * sizeof(T), &p);
+    if (rc2) return rc2;
+    *dptr = (T*)p; return 0;
   };
   uint8_t* d_ising_samples = nullptr;
   if (out) {
@@ -1031,11 +1052,11 @@ extern "C" int blangpt_run_scans(blangpt_handle* h, int32_t n_scans, const blang
     if ((rc = alloc_out(&O.logdens, out->logDensity, (size_t)n_scans * M))) return rc;
     if ((rc = alloc_out(&O.noos, out->nOutOfSupport, (size_t)n_scans * M))) return rc;
     if ((rc = alloc_out(&O.indicators, out->swapIndicators, (size_t)n_scans * M))) return rc;
-    if (h->n_reals && (rc = alloc_out(&O.samples, out->samples, (size_t)n_scans * R * h->n_reals))) return rc;
+    if (h->n_reals) { if ((rc = alloc_out(&O.samples, out->samples, (size_t)n_scans * R * h->n_reals))) return rc; } else next_buf++;
     if (h->n_ints && out->intSamples) {
       void* p = nullptr;
-      CUDA_OK(h, cudaMalloc(&p, (size_t)n_scans * R * h->n_ints));
-      tmp.push_back(p); d_ising_samples = (uint8_t*)p;
+      if ((rc = staging((size_t)n_scans * R * h->n_ints, &p))) return rc;
+      d_ising_samples = (uint8_t*)p;
     }
   }
   CUDA_OK(h, cudaMemsetAsync(h->E.batch_counter, 0, sizeof(uint32_t) * R, h->stream));

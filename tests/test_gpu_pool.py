@@ -165,3 +165,4 @@ def test_pool_mixture_matches_cluster_kernel_and_is_deterministic(datasets, monk
     assert np.array_equal(a["swapIndicators"], b["swapIndicators"])
     assert rel(a["energy"], b["energy"]) < 1e-10 and rel(a["samples"], b["samples"]) < 1e-9
     assert np.array_equal(b["energy"], c["energy"]) and np.array_equal(b["samples"], c["samples"])      # bit-identical repeat
+

@@ -57,8 +57,16 @@ if __name__ == "__main__":
     if "C2x128" in which:    # one GPU's share of 1024 chains sharded over 8 GPUs
         run("C2 logistic 100k x 32, 128 chains on one GPU", D.logistic_regression(), 128, init="COPIES", scans=5, warm=3,
             algo_bytes=25_700_000)
+    for nc in (256, 512):    # where the pool kernel hands over to the cluster kernel (engine.cu, set_model)
+        if "C2x%d" % nc in which:
+            run("C2 logistic 100k x 32, %d chains on one GPU" % nc, D.logistic_regression(), nc, init="COPIES", scans=3, warm=2,
+                algo_bytes=25_700_000)
     if "C3" in which:
         run("C3 mixture K=4 1M obs, 256 chains", D.gaussian_mixture(), 256, init="COPIES", scans=2, warm=1, algo_bytes=8_000_000)
+    if "C3post" in which:    # every chain starts at the generating parameters: the colder chains stay near the posterior
+        run("C3 mixture K=4 1M obs, 256 chains, started at the generating parameters", D.gaussian_mixture(), 256, init="COPIES",
+            scans=3, warm=3, algo_bytes=8_000_000,
+            start=[-6.0, -2.0, 2.0, 6.0, 1.0, 0.25, 0.25, 1.0, 0.25, 0.25, 0.25, 0.25])
     if "C4" in which:
         run("C4 ising 256x256, 128 chains (1 of 8 GPUs)", D.ising(256), 128, scans=20, warm=3, algo_bytes=None)
     if "C5" in which:
