@@ -258,18 +258,23 @@ def run_gpu(args):
             barrier()                                 # a driver hiccup in create/free (seen: +0.3 s) is not the path
             t0 = time.perf_counter()
             e2 = Engine(nChains=n_chains, random=2, device=local_rank, rank=rank, worldSize=world, ctasPerChain=args.ctas)
+            t1 = time.perf_counter()
             e2.set_model(spec_p)                      # H2D of the data set (host pointers), on every rank
+            t2 = time.perf_counter()
             if world > 1:
                 connect_peers(e2)
+            t3 = time.perf_counter()
             e2.initialize("COPIES")
             out = e2.run_scans(k_e2e, want=("energy", "swapIndicators", "samples", "logDensity", "nOutOfSupport"))
             cc = e2.counters()
             torch.cuda.synchronize(dev)
-            runs.append((time.perf_counter() - t0, cc["evals"]))
+            t4 = time.perf_counter()
+            runs.append((t4 - t0, cc["evals"], {"create": t1 - t0, "set_model": t2 - t1, "peer_connect": t3 - t2,
+                                                "initialize_and_scans": t4 - t3}))
             barrier()                                 # nobody frees its mailbox while a peer may still write to it
             e2.close()
-        runs.sort()
-        dt, n_evals = runs[1]
+        runs.sort(key=lambda r: r[0])
+        dt, n_evals, phases = runs[1]
         d2h = sum(v.nbytes for v in out.values()) / k_e2e
         h2d = (xs.nbytes + ys.nbytes) / k_e2e
         e2e_value = n_evals / dt
@@ -279,6 +284,7 @@ def run_gpu(args):
             tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
             e2e_value = float(tsum[1]) / float(tmax[0])
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "phases_s_rank0": phases,
                "what": "Engine(nChains=%d, worldSize=%d) create + set_model (data set H2D from pinned host memory, every rank) + "
                        "%sinitialize + run_scans(%d) with per-scan outputs copied D2H + counters; wall clock, max over ranks, "
                        "median of 3 complete repetitions" % (n_chains, world, "peer connect + " if world > 1 else "", k_e2e)}
@@ -335,7 +341,11 @@ def run_gpu(args):
             "round_trips": int(l4["roundTrips"][0]),
             "round_trips_per_s": float(l4["roundTrips"][0]) / (l4["millis"] * 1e-3),
             "Lambda": float(l4["Lambda"][0]), "mean_swap_accept": float(l4["meanAccept"][0]),
-            "min_swap_accept": float(l4["minAccept"][0]), "logZ_stepping_stone": float(l4["logZ"][0]), "wall_s": wall4}
+            "min_swap_accept": float(l4["minAccept"][0]), "logZ_stepping_stone": float(l4["logZ"][0]), "wall_s": wall4,
+            "min_scans_per_round_trip": 2 * (n_chains - 1),
+            "note": "a particle moves one ladder position per scan at best, so one round trip takes at least 2 (nChains - 1) "
+                    "scans: with the 64 N-chain ladder of N > 1 GPUs the final round of this run is shorter than one round trip "
+                    "beyond N = 4"}
         barrier()
         e4.close()
         if rank == 0:        # BASELINE configs 0 and 2 (C1 at its named size, a down-scaled twin of C3) on this rank's GPU

@@ -182,8 +182,9 @@ def make_ladder(kind, nChains, param=None, annealingParameters=None, allowSpline
 def ladder_from_another_exec(annealing_parameters_csv, nChains, allowSplineGeneralization=False):
     """ladders/FromAnotherExec.java:27-40: the final (isAdapt == false) round's schedule of an earlier run."""
     import csv
+    from .results import open_table          # annealingParameters.csv or .csv.gz (FromAnotherExec.java:16)
     parsed = [0.0]
-    with open(annealing_parameters_csv) as f:
+    with open_table(annealing_parameters_csv) as f:
         for row in csv.DictReader(f):
             if row["isAdapt"] == "false":
                 parsed.append(float(row["value"]))
@@ -505,9 +506,10 @@ class PT:
             self.engine.set_ladder(make_ladder(self.ladder, self.nChains))
         self.engine.initialize(self.initialization)
 
-    def performInference(self, want=("energy", "swapIndicators", "samples"), results=None):
+    def performInference(self, want=("energy", "swapIndicators", "samples"), results=None, compressed=False):
         """PT.performInference (PT.java:85-113).  With `results` (a folder) the reference's samples/ and
-        monitoring/ tables are written there, one batched write per round (blangsdk_b200/results.py)."""
+        monitoring/ tables are written there, one batched write per round (blangsdk_b200/results.py);
+        `compressed` writes them as .csv.gz (experimentConfigs.tabularWriter.compressed)."""
         if results is None and self.targetAccept is None:
             res = self.engine.perform_inference(self.nScans, self.adaptFraction, self.thinning, want)
             res["finalStats"] = self.engine.round_stats()
@@ -522,7 +524,7 @@ class PT:
         if eng.R != 1:
             raise BlangPTError("result tables are written for one replica at a time")
         w = PTResultsWriter(results, eng.family, eng.N, self._spec["hyper"], thinning=self.thinning,
-                            logNormalizationEstimator=self.logNormalizationEstimator)
+                            logNormalizationEstimator=self.logNormalizationEstimator, compressed=compressed)
         rs = rounds(self.nScans, self.adaptFraction if eng.N > 1 else 0.0)
         scan, summary = 0, []
         full = ("energy", "logDensity", "nOutOfSupport", "swapIndicators", "samples")

@@ -18,9 +18,16 @@ unchanged:
                roundTimings (round,isAdapt,nExplorationSteps,value); runningTimeSummary.tsv
   logNormalizationEstimate.csv (estimator,value)
 """
+import gzip
 import os
 
 import numpy as np
+
+
+def open_table(path, mode="rt"):
+    """a tidy CSV as text, gzip-compressed when its name ends in .gz (the reference reads both: BriefIO.readLines,
+    DefaultPostProcessor.xtend:107, FromAnotherExec.java:16)"""
+    return gzip.open(path, mode) if str(path).endswith(".gz") else open(path, mode.replace("t", ""))
 
 # latent variables of each catalogue family as a Blang model would name and shape them
 VARIABLES = {
@@ -62,15 +69,18 @@ class TabularWriter:
     """One tidy CSV: the header is fixed by the first write (blang.inits TabularWriter behaviour)."""
 
     def __init__(self, path):
-        self.path = path
+        self.path = path                      # "....csv" or "....csv.gz" (experimentConfigs.tabularWriter.compressed)
         self.columns = None
         self.f = None
+
+    def _open(self):
+        os.makedirs(os.path.dirname(self.path), exist_ok=True)
+        self.f = open_table(self.path, "wt")
 
     def write(self, *pairs):
         cols = [k for k, _ in pairs]
         if self.f is None:
-            os.makedirs(os.path.dirname(self.path), exist_ok=True)
-            self.f = open(self.path, "w")
+            self._open()
             self.columns = cols
             self.f.write(",".join(cols) + "\n")
         elif cols != self.columns:
@@ -80,8 +90,7 @@ class TabularWriter:
     def write_block(self, columns, arrays):
         """vectorised: arrays are equally long 1-D arrays, one per column"""
         if self.f is None:
-            os.makedirs(os.path.dirname(self.path), exist_ok=True)
-            self.f = open(self.path, "w")
+            self._open()
             self.columns = list(columns)
             self.f.write(",".join(columns) + "\n")
         elif list(columns) != self.columns:
@@ -98,8 +107,9 @@ class TabularWriter:
 class ExperimentResults:
     """results folder with lazily created tabular writers (blang.inits ExperimentResults)."""
 
-    def __init__(self, folder):
+    def __init__(self, folder, compressed=False):
         self.folder = folder
+        self.ext = ".csv.gz" if compressed else ".csv"
         os.makedirs(folder, exist_ok=True)
         self.writers = {}
 
@@ -107,10 +117,12 @@ class ExperimentResults:
         key = (sub, name)
         if key not in self.writers:
             base = os.path.join(self.folder, sub) if sub else self.folder
-            self.writers[key] = TabularWriter(os.path.join(base, name + ".csv"))
+            self.writers[key] = TabularWriter(os.path.join(base, name + self.ext))
         return self.writers[key]
 
     def flush_all(self):
+        if self.ext.endswith(".gz"):          # "When using .csv.gz, we cannot flush part-way through" (PT.java:432)
+            return
         for w in self.writers.values():
             if w.f is not None:
                 w.f.flush()
@@ -124,8 +136,8 @@ class PTResultsWriter:
     """Writes what PT.performInference writes, one round at a time."""
 
     def __init__(self, folder, family, n_chains, hyper=None, statisticRecordedMaxChainIndex=100, thinning=1,
-                 logNormalizationEstimator="steppingStone"):
-        self.results = ExperimentResults(folder)
+                 logNormalizationEstimator="steppingStone", compressed=False):
+        self.results = ExperimentResults(folder, compressed)
         self.family, self.N = family, n_chains
         self.max_idx = statisticRecordedMaxChainIndex
         self.thinning = thinning
@@ -237,7 +249,7 @@ def replay_round_trips(swap_indicators_csv, start_scan, end_scan):
     import csv
     rows = {}
     n_chains = 0
-    with open(swap_indicators_csv) as f:
+    with open_table(swap_indicators_csv) as f:
         for r in csv.DictReader(f):
             s, c, v = int(r["sample"]), int(r["chain"]), int(r["value"])
             n_chains = max(n_chains, c + 1)

@@ -91,6 +91,43 @@ def test_results_writer_format(tmp_path):
     assert len(energies) == n * N and float(energies[5]["value"]) == out["energy"][1, 0, 1]
 
 
+def test_results_writer_compressed(tmp_path):
+    """experimentConfigs.tabularWriter.compressed: the same tables as .csv.gz; the consumers the reference ships read both
+    (DefaultPostProcessor.xtend:107, FromAnotherExec.java:16): so do replay_round_trips and ladder_from_another_exec"""
+    import gzip
+    from blangsdk_b200.results import PTResultsWriter, replay_round_trips
+    from blangsdk_b200.engine import ladder_from_another_exec
+    N, n = 4, 6
+    rng = np.random.default_rng(1)
+    outs = {}
+    for compressed in (False, True):
+        folder = tmp_path / ("gz" if compressed else "plain")
+        w = PTResultsWriter(str(folder), "normal", N, compressed=compressed)
+        ind = np.zeros((n, 1, N), dtype=np.int32)
+        for t in range(n):
+            ind[t, 0, (t % 2)::2][: (N - t % 2) // 2] = 1
+        out = dict(energy=np.arange(n * N, dtype=float).reshape(n, 1, N), logDensity=-np.ones((n, 1, N)),
+                   nOutOfSupport=np.zeros((n, 1, N), dtype=np.int32), swapIndicators=ind, samples=rng.random((n, 1, 2)))
+        w.write_scans(0, out)
+        stats = dict(swapAcceptMean=np.full((1, N - 1), 0.5), energyVariance=np.ones((1, N)), energyCovariance=np.full((1, N), 0.25))
+        diag = dict(swapLowest=0.5, swapAverage=0.5, energyCorrelationAverage=0.25, energyCorrelationHighest=0.25, Lambda=1.5,
+                    inefficiency=3.0, timeToFirstRestart=32.0, effectiveNScans=0.0, temperedRestarts=1, temperedRestartRate=1 / 6,
+                    asymptoticRoundTripCount=1.2, asymptoticRoundTripRate=0.2, nonAsymptoticRoundTripCount=0.75,
+                    nonAsymptoticRoundTripRate=0.125, logNormalizationSteppingStone=-3.5, logNormalizationThermodynamic=float("nan"),
+                    cumulativeLambda=np.linspace(0, 1.5, 99), lambdaInstantaneous=np.full(99, 1.5))
+        w.write_round(0, False, n, [1.0, 0.6, 0.3, 0.0], stats, diag, 2, 3.0, 12.3)
+        w.close()
+        ext = ".csv.gz" if compressed else ".csv"
+        opener = gzip.open if compressed else open
+        with opener(folder / "samples" / ("energy" + ext), "rt") as f:
+            outs[compressed] = f.read()
+        assert (folder / "monitoring" / ("swapIndicators" + ext)).exists() and (folder / ("logNormalizationEstimate" + ext)).exists()
+        rt = replay_round_trips(str(folder / "monitoring" / ("swapIndicators" + ext)), 0, n)
+        lad = ladder_from_another_exec(str(folder / "monitoring" / ("annealingParameters" + ext)), N)
+        assert rt >= 0 and np.allclose(lad, [1.0, 0.6, 0.3, 0.0])
+    assert outs[False] == outs[True] and outs[True].startswith("sample,chain,value\n")
+
+
 @pytest.mark.gpu
 def test_run_to_disk_and_read_back(tmp_path, datasets):
     from blangsdk_b200.engine import PT, ladder_from_another_exec
