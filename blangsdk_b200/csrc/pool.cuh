@@ -80,13 +80,17 @@ BPT_D void pool_st_half(PoolHalf* p, double v, uint32_t seq, int i) {
                "r"((uint32_t)__double2hiint(v)), "r"(seq), "r"((uint32_t)i) : "memory");
 }
 
-// The doorbell: idle worker warps sleep in hardware on an mbarrier phase instead of polling shared memory (ncu on
-// the polling version: a quarter of all issued instructions were idle workers' polls, competing with the working
-// warps of their scheduler).  The dispatcher arrives once per publication; a waiter names the phase by its parity.
+// The doorbell (BLANGPT_POOL_BELL=1, off by default): idle worker warps sleep in hardware on an mbarrier phase instead
+// of polling shared memory with nanosleep; the dispatcher arrives once per publication, a waiter names the phase by
+// its parity.  ncu counts the polls as a sixth of all issued instructions, but the workers are busy ~90 % of the time
+// and the polls mostly fill issue slots nobody wants: measured 3.975 M evals/s with the bell, 3.990 M without
+// (profiles/ab_pool_r02.md), so polling stays the default.
 BPT_D void bell_init(unsigned long long* b) {
+  if (!BLANGPT_POOL_BELL) return;
   asm volatile("mbarrier.init.shared.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
 }
 BPT_D void bell_ring(unsigned long long* b) {
+  if (!BLANGPT_POOL_BELL) return;
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared.b64 st, [%0];\n\t}" :: "r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
 }
 // sleeps until phase `parity` of the bell has completed, or for the hardware's time limit (then false)
