@@ -38,7 +38,8 @@ final class Native {
   static final int OK = 0, EINVAL = 1, ECUDA = 2, ESTATE = 3, ENUMERIC = 4, EUNSUPPORTED = 5;
   // model families (blangpt.h BLANGPT_FAM_*)
   static final int FAM_NORMAL = 1, FAM_LOGISTIC = 2, FAM_MIXTURE = 3, FAM_ISING = 4, FAM_BETABINOMIAL = 5, FAM_IID = 6,
-      FAM_HIERARCHICAL = 7, FAM_LINREG = 8, FAM_ROCKETS_LATENT = 9, FAM_CATEGORICAL = 10;
+      FAM_HIERARCHICAL = 7, FAM_LINREG = 8, FAM_ROCKETS_LATENT = 9, FAM_MIXTURE_INDICATORS = 10, FAM_CHANGEPOINT = 11,
+      FAM_ANNEAL_PAIR = 12;
   static final int F64 = 0, I32 = 1;
   static final int INIT_COPIES = 0, INIT_FORWARD = 1, INIT_SCM = 2;      // PT.InitType ordinals (PT.java:267)
   static final int LADDER_EQUALLY_SPACED = 0, LADDER_GEOMETRIC = 1, LADDER_POLYNOMIAL = 2, LADDER_USER = 3;
