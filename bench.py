@@ -17,8 +17,10 @@ variable, R/mcmc/RealSliceSampler.java:156-161; counted on the device).
   python bench.py --impl reference --gpus N --steps K --warmup W   # CPU restatement of the reference engine
 
 N > 1 is launched by torchrun, one rank per GPU: chain slots are sharded (64 chains per GPU,
-one 64*N-chain ladder, weak scaling), the per-chain scalar table is all-gathered over NCCL
-each scan, every rank takes the same swap decisions.
+one 64*N-chain ladder, weak scaling); the ranks exchange their mailbox handles once
+(connect_peers), after which every chain's 32-byte record is stored into every rank's mailbox
+by the exploration kernel itself -- no collective and no host code per scan -- and every rank
+takes the same swap decisions.  Both `value` and `e2e` drive that sharded engine.
 """
 import argparse
 import json

@@ -433,6 +433,7 @@ struct NormalFam {
 enum {
   IID_POISSON = 1, IID_BINOMIAL, IID_NEGBINOMIAL, IID_STUDENTT, IID_GEOMETRIC, IID_LAPLACE, IID_EXPONENTIAL, IID_GAMMA,
   IID_WEIBULL, IID_GUMBEL, IID_LOGISTICDIST, IID_HALFSTUDENTT, IID_LOGLOGISTIC, IID_GOMPERTZ, IID_YULESIMON,
+  IID_UNIFORM_MAX,
   IID_N_DISTS
 };
 enum { PRIOR_NORMAL = 0, PRIOR_GAMMA = 1, PRIOR_EXPONENTIAL = 2, PRIOR_BETA = 3, PRIOR_UNIFORM = 4 };
@@ -457,6 +458,7 @@ BPT_HD IidShape iid_shape(int dist) {
     case IID_LOGLOGISTIC:  return {2, 3, {3, 3, 3, 0}, {0, 1, 1, 0}};   // scale, shape
     case IID_GOMPERTZ:     return {2, 2, {3, 3, 0, 0}, {0, 1, 0, 0}};   // shape, scale
     case IID_YULESIMON:    return {1, 1, {1, 0, 0, 0}, {1, 0, 0, 0}};   // rho
+    case IID_UNIFORM_MAX:  return {1, 2, {1, 1, 0, 0}, {0, 1, 0, 0}};   // max (min = 0.0: F/Doomsday.bl:9)
   }
   return {0, 0, {0, 0, 0, 0}, {0, 0, 0, 0}};
 }
@@ -553,6 +555,11 @@ BPT_D double iid_law(int dist, int law, const double* th, double y, double x) {
       if (law == 0) return (shape <= 0.0 || scale <= 0.0) ? ninf : log(shape / scale);
       if (y < 0.0 || scale <= 0.0 || shape <= 0.0) return ninf;
       return (y / scale) - (shape * (exp(y / scale) - 1.0));
+    }
+    case IID_UNIFORM_MAX: {                               // ContinuousUniform.bl:14-23 with min = 0.0
+      const double mn = 0.0, mx = th[0];
+      if (law == 0) return (mx - mn <= 0.0) ? ninf : -log(mx - mn);
+      return (mn <= y && y <= mx) ? 0.0 : ninf;
     }
     default: {                                            // YuleSimon.bl:10-16
       const double rho = th[0];

@@ -73,7 +73,7 @@ def iid_observations(dist="poisson", n=2000, seed=SEED_IID):
     reference's declaration order: poisson (mean), binomial (p; trials are data), negbinomial (r, p),
     studentt (nu, mu, sigma), geometric (p), laplace (location, scale), exponential (rate), gamma (shape, rate),
     weibull (scale, shape), gumbel (location, scale), logisticdist (location, scale), halfstudentt (nu, sigma),
-    loglogistic (scale, shape), gompertz (shape, scale), yulesimon (rho)."""
+    loglogistic (scale, shape), gompertz (shape, scale), yulesimon (rho), uniformmax (max; ContinuousUniform(0, max))."""
     rng = np.random.default_rng(seed + sum(map(ord, dist)))
     spec = dict(family="iid", trials=None)
     if dist == "poisson":
@@ -126,6 +126,9 @@ def iid_observations(dist="poisson", n=2000, seed=SEED_IID):
         w = rng.exponential(1.0 / 2.5, n)
         spec["y"] = (rng.geometric(np.exp(-w)) - 1).astype(np.float64)
         priors = [("exponential", 0.3)]
+    elif dist == "uniformmax":
+        spec["y"] = rng.uniform(0.0, 3.0, n)
+        priors = [("exponential", 0.4)]
     else:
         raise ValueError(dist)
     spec["hyper"] = dict(dist=dist, priors=priors)
@@ -133,8 +136,16 @@ def iid_observations(dist="poisson", n=2000, seed=SEED_IID):
     spec["truth"] = dict(poisson=[4.2], binomial=[0.3], negbinomial=[3.0, 0.6], studentt=[4.0, 1.0, 2.0], geometric=[0.25],
                          laplace=[-0.5, 1.5], exponential=[1.7], gamma=[2.5, 1.2], weibull=[2.0, 1.5], gumbel=[0.5, 1.2],
                          logisticdist=[1.0, 0.8], halfstudentt=[4.0, 1.5], loglogistic=[2.0, 3.0], gompertz=[0.8, 1.5],
-                         yulesimon=[2.5])[dist]
+                         yulesimon=[2.5], uniformmax=[3.2])[dist]
     return spec
+
+
+def doomsday(y=1.2, rate=1.0):
+    """F/Doomsday.bl, the model of the SDK's Getting Started page and of T/TestEndToEnd: z ~ Exponential(rate),
+    y | z ~ ContinuousUniform(0.0, z), run there with --model.rate 1.0 --model.y 1.2 --model.z NA.  Its evidence is
+    closed form: Z = rate * E1(rate * y)."""
+    return dict(family="iid", trials=None, y=np.array([float(y)]), hyper=dict(dist="uniformmax", priors=[("exponential", float(rate))]),
+                truth=[2.0 * y])
 
 
 def hierarchical_rockets(groups=12, seed=20240007):

@@ -25,7 +25,7 @@ FAMILIES = {"normal": 1, "logistic": 2, "mixture": 3, "ising": 4, "betabinomial"
 # family "iid" (include/blangpt.h BLANGPT_IID_* / BLANGPT_PRIOR_*): observation laws and priors
 IID_DISTS = {"poisson": 1, "binomial": 2, "negbinomial": 3, "studentt": 4, "geometric": 5, "laplace": 6,
              "exponential": 7, "gamma": 8, "weibull": 9, "gumbel": 10, "logisticdist": 11, "halfstudentt": 12,
-             "loglogistic": 13, "gompertz": 14, "yulesimon": 15}
+             "loglogistic": 13, "gompertz": 14, "yulesimon": 15, "uniformmax": 16}
 IID_PRIORS = {"normal": 0, "gamma": 1, "exponential": 2, "beta": 3, "uniform": 4}
 INIT = {"COPIES": 0, "FORWARD": 1, "SCM": 2}
 

@@ -47,7 +47,7 @@ IID_VARIABLES = {
     "studentt": ["nu", "mu", "sigma"], "geometric": ["p"], "laplace": ["location", "scale"],
     "exponential": ["rate"], "gamma": ["shape", "rate"], "weibull": ["scale", "shape"], "gumbel": ["location", "scale"],
     "logisticdist": ["location", "scale"], "halfstudentt": ["nu", "sigma"], "loglogistic": ["scale", "shape"],
-    "gompertz": ["shape", "scale"], "yulesimon": ["rho"],
+    "gompertz": ["shape", "scale"], "yulesimon": ["rho"], "uniformmax": ["max"],
 }
 
 

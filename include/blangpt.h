@@ -90,7 +90,8 @@ enum {
   BLANGPT_IID_HALFSTUDENTT = 12,/* nu, sigma            */
   BLANGPT_IID_LOGLOGISTIC = 13, /* scale, shape         */
   BLANGPT_IID_GOMPERTZ = 14,    /* shape, scale         */
-  BLANGPT_IID_YULESIMON = 15    /* rho                  */
+  BLANGPT_IID_YULESIMON = 15,   /* rho                  */
+  BLANGPT_IID_UNIFORM_MAX = 16  /* max: y_i ~ ContinuousUniform(0.0, max), the likelihood of F/Doomsday.bl */
 };
 /* family 6: priors; (a, b) = (mean, variance) | (shape, rate) | (rate, unused) | (alpha, beta) | (min, max) */
 enum {

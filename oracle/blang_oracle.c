@@ -285,14 +285,14 @@ struct orc_model {
  * IID_MASK[d][l] = which parameters the block's signature names (bit j = parameter j): the samplers of those
  * parameters see the factor; IID_READS_Y = whether it names the realization. */
 #define IID_MAX_LAWS 4
-static const int IID_NPARAMS[16] = {0, 1, 1, 2, 3, 1, 2, 1, 2, 2, 2, 2, 2, 2, 2, 1};
-static const int IID_NLAWS[16]   = {0, 3, 2, 2, 4, 1, 1, 4, 4, 3, 2, 3, 3, 3, 2, 1};
-static const int IID_MASK[16][IID_MAX_LAWS] = {
+static const int IID_NPARAMS[17] = {0, 1, 1, 2, 3, 1, 2, 1, 2, 2, 2, 2, 2, 2, 2, 1, 1};
+static const int IID_NLAWS[17]   = {0, 3, 2, 2, 4, 1, 1, 4, 4, 3, 2, 3, 3, 3, 2, 1, 2};
+static const int IID_MASK[17][IID_MAX_LAWS] = {
   {0}, {1, 1, 0}, {1, 0}, {1, 3}, {0, 4, 1, 7}, {1}, {3}, {1, 1, 0, 1}, {3, 2, 1, 2}, {3, 3, 3}, {3, 3},
-  {2, 3, 3}, {1, 2, 3}, {3, 3, 3}, {3, 3}, {1}};
-static const int IID_READS_Y[16][IID_MAX_LAWS] = {
+  {2, 3, 3}, {1, 2, 3}, {3, 3, 3}, {3, 3}, {1}, {1, 1}};
+static const int IID_READS_Y[17][IID_MAX_LAWS] = {
   {0}, {1, 0, 1}, {1, 1}, {1, 1}, {0, 0, 0, 1}, {1}, {1}, {1, 1, 0, 0}, {1, 1, 0, 0}, {0, 1, 1}, {0, 1},
-  {0, 1, 1}, {0, 0, 1}, {0, 1, 1}, {0, 1}, {1}};
+  {0, 1, 1}, {0, 0, 1}, {0, 1, 1}, {0, 1}, {1}, {0, 1}};
 
 static double gamma_law(int law, double shape, double rate, double y) {   /* Gamma.bl:14-31 */
   switch (law) {
@@ -410,6 +410,12 @@ static double iid_law(int dist, int law, const double* th, double y, double x) {
       if (rho <= 0) return NEG_INF;
       if (y < 0) return NEG_INF;
       return log(rho) + (orc_lngamma(1.0 + y) + orc_lngamma(rho + 1) - orc_lngamma(1.0 + y + (rho + 1)));
+    }
+    case ORC_IID_UNIFORM_MAX: {                   /* ContinuousUniform.bl:14-23 with min = 0.0, max latent (F/Doomsday.bl:9) */
+      const double mn = 0.0, mx = th[0];
+      if (law == 0) { if (mx - mn <= 0.0) return NEG_INF; return -log(mx - mn); }
+      if (mn <= y && y <= mx) return 0.0;
+      return NEG_INF;
     }
   }
   return NAN;
@@ -694,7 +700,7 @@ static void b_uniform_prior(Builder* b, int sampler, int var, double mn, double 
  * `y.get(i) | theta ~ Dist(theta)` n times produces, and it is what nOutOfSupport counts. */
 orc_model* orc_model_iid(int dist, const double* y, const double* trials, int n, const int32_t* prior_kind,
                          const double* prior_a, const double* prior_b) {
-  if (dist < ORC_IID_POISSON || dist > ORC_IID_YULESIMON) return NULL;
+  if (dist < ORC_IID_POISSON || dist > ORC_IID_UNIFORM_MAX) return NULL;
   const int P = IID_NPARAMS[dist];
   Builder b = b_begin(ORC_FAM_IID, P, 0, P);
   orc_model* m = b.m;

@@ -175,7 +175,8 @@ def adapt_ladder(betas_asc, accept_asc):
 
 
 IID_DISTS = dict(poisson=1, binomial=2, negbinomial=3, studentt=4, geometric=5, laplace=6, exponential=7, gamma=8,
-                 weibull=9, gumbel=10, logisticdist=11, halfstudentt=12, loglogistic=13, gompertz=14, yulesimon=15)
+                 weibull=9, gumbel=10, logisticdist=11, halfstudentt=12, loglogistic=13, gompertz=14, yulesimon=15,
+                 uniformmax=16)
 IID_PRIORS = dict(normal=0, gamma=1, exponential=2, beta=3, uniform=4)
 
 

@@ -26,7 +26,7 @@ def _case(D, rng):
         spec = D.hierarchical_rockets(int(rng.integers(1, 63)), seed=int(rng.integers(1, 1 << 30)))
     elif fam == "iid":
         dists = ["poisson", "binomial", "negbinomial", "studentt", "geometric", "laplace", "exponential", "gamma", "weibull",
-                 "gumbel", "logisticdist", "halfstudentt", "loglogistic", "gompertz", "yulesimon"]
+                 "gumbel", "logisticdist", "halfstudentt", "loglogistic", "gompertz", "yulesimon", "uniformmax"]
         dist = dists[rng.integers(0, len(dists))]
         spec = D.iid_observations(dist, int(rng.integers(1, 3000)), seed=int(rng.integers(1, 1 << 30)))
     else:

@@ -11,7 +11,7 @@ from gpu_util import assert_trajectory_parity, make_pair, rel, start_from
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
 DISTS = ["poisson", "binomial", "negbinomial", "studentt", "geometric", "laplace", "exponential", "gamma", "weibull",
-         "gumbel", "logisticdist", "halfstudentt", "loglogistic", "gompertz", "yulesimon"]
+         "gumbel", "logisticdist", "halfstudentt", "loglogistic", "gompertz", "yulesimon", "uniformmax"]
 
 
 def _state(rng, dist, kind):
@@ -24,12 +24,12 @@ def _state(rng, dist, kind):
           "weibull": [rng.gamma(2.0, 1.0), rng.gamma(2.0, 1.0)], "gumbel": [rng.normal(0.0, 2.0), rng.gamma(2.0, 1.0)],
           "logisticdist": [rng.normal(0.0, 2.0), rng.gamma(2.0, 1.0)], "halfstudentt": [rng.gamma(2.0, 2.0), rng.gamma(2.0, 1.0)],
           "loglogistic": [rng.gamma(2.0, 1.0), rng.gamma(2.0, 1.0)], "gompertz": [rng.gamma(2.0, 0.5), rng.gamma(2.0, 1.0)],
-          "yulesimon": [rng.gamma(2.0, 1.0)]}[dist]
+          "yulesimon": [rng.gamma(2.0, 1.0)], "uniformmax": [rng.uniform(1.0, 6.0)]}[dist]
     if kind == "oos":
         j = {"poisson": 0, "binomial": 0, "negbinomial": int(rng.integers(0, 2)), "studentt": int(rng.choice([0, 2])),
              "geometric": 0, "laplace": 1, "exponential": 0, "gamma": int(rng.integers(0, 2)),
              "weibull": int(rng.integers(0, 2)), "gumbel": 1, "logisticdist": 1, "halfstudentt": int(rng.integers(0, 2)),
-             "loglogistic": int(rng.integers(0, 2)), "gompertz": int(rng.integers(0, 2)), "yulesimon": 0}[dist]
+             "loglogistic": int(rng.integers(0, 2)), "gompertz": int(rng.integers(0, 2)), "yulesimon": 0, "uniformmax": 0}[dist]
         th[j] = -abs(th[j]) - 0.1
     return th
 
@@ -201,3 +201,35 @@ def test_iid_posterior_against_conjugate_answers(tmp_path, datasets):
     tail = p[len(p) // 2:]
     assert abs(tail.mean() - a / (a + b)) < 5 * sd / math.sqrt(len(tail) / 4.0)
     pt.engine.close()
+
+
+def test_doomsday_on_the_device(oracle, datasets):
+    """F/Doomsday.bl with the arguments of the reference's Getting Started transcript and of T/TestEndToEnd.xtend:38-47
+    (rate 1.0, y 1.2, z latent): draw-for-draw parity with the oracle from PT's default SCM initialisation, the same SCM
+    evidence estimate, and the device's stepping-stone log Z against the closed form log E1(1.2) and the number the JVM
+    printed (-1.8657991502743467, GettingStarted.xtend:255)."""
+    import math
+    from scipy.special import exp1
+    from blangsdk_b200.engine import Engine, PT
+    spec = datasets.doomsday(1.2, 1.0)
+    exact, jvm = math.log(exp1(1.2)), -1.8657991502743467
+    eng = Engine(nChains=8, random=77)
+    eng.set_model(spec)
+    eng.initialize("SCM", nParticles=200)
+    ref = oracle.PT(oracle.Model(spec), nChains=8, seed=77)
+    rs, gs = ref.initialize_scm(nParticles=200), eng.scm_summary()
+    assert gs["nTemperatures"] == rs["nTemperatures"] and gs["nResamplings"] == rs["nResamplings"]
+    assert abs(gs["logNormEstimate"] - rs["logNormEstimate"]) < 1e-9
+    assert_trajectory_parity(eng, ref, 25)
+    eng.close()
+    est = []
+    for seed in range(10):
+        pt = PT(nChains=8, nScans=1000, adaptFraction=0.5, random=900 + seed, initialization="FORWARD")
+        pt.setSampledModel(spec)
+        res = pt.performInference(want=())
+        est.append(float(res["rounds"][-1]["logZ"][0]))
+        pt.engine.close()
+    est = np.array(est)
+    se = est.std(ddof=1) / math.sqrt(len(est))
+    assert abs(est.mean() - exact) < 4 * se + 1e-3, (est.mean(), exact, se)
+    assert abs(est.mean() - jvm) < abs(jvm - exact) + 4 * se + 1e-3

@@ -187,6 +187,7 @@ _IID_EIT = {
                  lambda r, t: t[1] * np.log(1.0 - np.log(1.0 - r.uniform(0.0, 1 - 1e-12, N_OBS)) / t[0])),
     "yulesimon": ([("gamma", 2.0, 1.0)], lambda r: [_pos(r)],
                   lambda r, t: r.geometric(np.exp(-r.exponential(1.0 / t[0], N_OBS))) - 1),
+    "uniformmax": ([("gamma", 2.0, 1.0)], lambda r: [_pos(r)], lambda r, t: r.uniform(0.0, t[0], N_OBS)),
 }
 
 

@@ -84,7 +84,7 @@ def _iid_loglik(oracle, dist, y, theta, trials=None):
               "geometric": [("uniform", 0.0, 1.0)], "laplace": [("normal", 0.0, 25.0), ("gamma", 2.0, 1.0)]}.get(dist)
     if priors is None:
         n_par = dict(exponential=1, gamma=2, weibull=2, gumbel=2, logisticdist=2, halfstudentt=2, loglogistic=2,
-                     gompertz=2, yulesimon=1)[dist]
+                     gompertz=2, yulesimon=1, uniformmax=1)[dist]
         priors = [("exponential", 0.5)] * n_par
     spec = dict(family="iid", hyper=dict(dist=dist, priors=priors), y=np.array([float(y)]),
                 trials=None if trials is None else np.array([float(trials)]))
@@ -122,6 +122,8 @@ def test_iid_laws_normalise(oracle):
     assert abs(_simpson(pdf("gompertz", [0.8, 1.5]), 0.0, 12.0, 4000) - 1.0) < 1e-6
     tot = sum(math.exp(_iid_loglik(oracle, "yulesimon", y, [2.5])["loglik"]) for y in range(0, 3000))
     assert abs(tot - 1.0) < 1e-6      # tail ~ Gamma(3.5) k^-2.5: 3000^-2.5 * 3.3 = 7e-9
+    assert abs(_simpson(pdf("uniformmax", [2.3]), 0.0, 2.3, 200) - 1.0) < 1e-9      # ContinuousUniform(0, 2.3)
+    assert _iid_loglik(oracle, "uniformmax", 2.4, [2.3])["noos"] == 1 and _iid_loglik(oracle, "uniformmax", 0.5, [-1.0])["noos"] == 2
     assert _iid_loglik(oracle, "gamma", 1.3, [-1.0, 2.0])["noos"] == 2 and _iid_loglik(oracle, "gamma", 1.3, [1.0, -2.0])["noos"] == 3
     assert _iid_loglik(oracle, "weibull", -1.0, [1.0, 2.0])["noos"] == 2
     # out-of-support parameters: every law that reads them is -inf, one count per observation and law
@@ -353,3 +355,45 @@ def test_lngamma_switch_moves_every_lgamma_based_density_by_less_than_1e9(oracle
                     worst = max(worst, abs(a[key] - b[key]) / max(1.0, abs(a[key])))
             assert a["noos"] == b["noos"]
     assert 0.0 < worst < 1e-9, worst          # the switch does something, and stays inside the bar
+
+
+def test_doomsday_evidence_exact_and_the_jvm_transcript(oracle, datasets):
+    """The one number in the reference tree that a JVM run of the reference produced for this path: the Getting Started page
+    prints the console output of `blang --model Doomsday --model.rate 1.0 --model.y 1.2 --model.z NA`
+    (R/runtime/internals/doc/contents/GettingStarted.xtend:248-263): "Normalization constant estimate:
+    -1.8657991502743467".  F/Doomsday.bl: z ~ Exponential(rate), y | z ~ ContinuousUniform(0.0, z); its evidence is
+    closed form, Z = int_y^inf rate e^(-rate z) / z dz = rate E1(rate y), log Z = -1.84258 at (1.0, 1.2): the transcript's
+    Monte Carlo estimate is 0.023 away from it.  The oracle's PT (the reference's algorithm: stepping-stone estimator over
+    adapted ladders) and its SCM initialisation (the estimator of the engine that produced the transcript) must agree with
+    the exact value within their own Monte Carlo error, and therefore with the JVM's number as closely as it agrees
+    with the truth."""
+    from scipy.special import exp1
+    jvm = -1.8657991502743467
+    exact = math.log(exp1(1.2))
+    assert abs(exact - (-1.84258)) < 1e-5 and abs(jvm - exact) < 0.03
+    spec = datasets.doomsday(1.2, 1.0)
+    # the annealed density of the model, factor by factor: prior Exponential(1) on z, then -log(z) and the support y <= z
+    d = oracle.Model(spec).log_density([2.0])
+    assert abs(d["loglik"] - (-math.log(2.0))) < 1e-15 and abs(d["fixed"] - (-2.0)) < 1e-12 and d["noos"] == 0
+    assert oracle.Model(spec).log_density([1.1])["noos"] == 1                       # z < y: out of support
+    est = []
+    for seed in range(12):
+        pt = oracle.PT(oracle.Model(spec), nChains=8, seed=300 + seed)
+        pt.initialize(oracle.INIT_FORWARD)
+        res = pt.perform_inference(1000, 0.5)
+        est.append(res["rounds"][-1]["logZ"])
+    est = np.array(est)
+    se = est.std(ddof=1) / math.sqrt(len(est))
+    assert abs(est.mean() - exact) < 4 * se + 1e-3, (est.mean(), exact, se)
+    assert abs(est.mean() - jvm) < abs(jvm - exact) + 4 * se + 1e-3
+    scm = []
+    for seed in range(40):
+        pt = oracle.PT(oracle.Model(spec), nChains=2, seed=500 + seed)
+        scm.append(pt.initialize_scm(nParticles=1000)["logNormEstimate"])
+    scm = np.array(scm)
+    # E[Z_hat] = Z (T/TestSMCUnbiasness): compare on the Z scale
+    zs = np.exp(scm)
+    assert abs(zs.mean() - math.exp(exact)) < 4 * zs.std(ddof=1) / math.sqrt(len(zs))
+    assert abs(scm.mean() - jvm) < 0.05
+    # the JVM's single run as one draw from the SCM estimator's distribution (40 seeds here: mean -1.849, sd 0.060)
+    assert abs(jvm - scm.mean()) < 2.5 * scm.std(ddof=1)
