@@ -25,29 +25,8 @@ import sys
 from decimal import Decimal
 
 from .engine import Engine
+from .results import java_double_to_string  # noqa: F401  (re-exported: the protocol prints numbers as Java does)
 
-
-def java_double_to_string(x):
-    """java.lang.Double.toString: shortest digits that round-trip; plain notation for 1e-3 <= |x| < 1e7, otherwise
-    computerised scientific notation d.dddE[-]n; always at least one digit after the point"""
-    x = float(x)
-    if x != x:
-        return "NaN"
-    if x in (float("inf"), float("-inf")):
-        return "Infinity" if x > 0 else "-Infinity"
-    if x == 0.0:
-        return "-0.0" if str(x).startswith("-") else "0.0"
-    sign, digits, exp = Decimal(repr(x)).as_tuple()
-    digits = "".join(map(str, digits)).rstrip("0") or "0"
-    exp10 = len("".join(map(str, Decimal(repr(x)).as_tuple().digits))) + exp - 1     # exponent of the leading digit
-    neg = "-" if sign else ""
-    if 1e-3 <= abs(x) < 1e7:
-        if exp10 >= 0:
-            whole, frac = digits[:exp10 + 1].ljust(exp10 + 1, "0"), digits[exp10 + 1:]
-        else:
-            whole, frac = "0", "0" * (-exp10 - 1) + digits
-        return neg + whole + "." + (frac or "0")
-    return neg + digits[0] + "." + (digits[1:] or "0") + "E" + str(exp10)
 
 _LOG = re.compile(r"^log_potential\((.*)\)$")
 _SAMPLE = re.compile(r"^call_sampler!\((.*)\)$")

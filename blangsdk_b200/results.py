@@ -19,6 +19,7 @@ unchanged:
   logNormalizationEstimate.csv (estimator,value)
 """
 import gzip
+from decimal import Decimal
 import os
 
 import numpy as np
@@ -51,17 +52,39 @@ IID_VARIABLES = {
 }
 
 
+def java_double_to_string(x):
+    """java.lang.Double.toString: shortest digits that round-trip; plain notation for 1e-3 <= |x| < 1e7, otherwise
+    computerised scientific notation d.dddE[-]n; always at least one digit after the point"""
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "Infinity" if x > 0 else "-Infinity"
+    if x == 0.0:
+        return "-0.0" if str(x).startswith("-") else "0.0"
+    sign, digits, exp = Decimal(repr(x)).as_tuple()
+    digits = "".join(map(str, digits)).rstrip("0") or "0"
+    exp10 = len("".join(map(str, Decimal(repr(x)).as_tuple().digits))) + exp - 1     # exponent of the leading digit
+    neg = "-" if sign else ""
+    if 1e-3 <= abs(x) < 1e7:
+        if exp10 >= 0:
+            whole, frac = digits[:exp10 + 1].ljust(exp10 + 1, "0"), digits[exp10 + 1:]
+        else:
+            whole, frac = "0", "0" * (-exp10 - 1) + digits
+        return neg + whole + "." + (frac or "0")
+    return neg + digits[0] + "." + (digits[1:] or "0") + "E" + str(exp10)
+
+
 def _fmt(v):
     if isinstance(v, (bool, np.bool_)):
         return "true" if v else "false"
     if isinstance(v, (int, np.integer)):
         return str(int(v))
     if isinstance(v, (float, np.floating)):
-        if np.isnan(v):
-            return "NaN"
-        if np.isinf(v):
-            return "Infinity" if v > 0 else "-Infinity"
-        return repr(float(v))
+        v = float(v)
+        if 1e-3 <= abs(v) < 1e7:              # Python's shortest repr is Double.toString's plain notation in this range
+            return repr(v)
+        return java_double_to_string(v)       # NaN, +-Infinity, 0.0, and d.dddE[-]n outside it
     return str(v)
 
 

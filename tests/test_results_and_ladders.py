@@ -254,3 +254,16 @@ def test_batched_pigeons_server(oracle, datasets):
     with pytest.raises(ValueError):
         srv.handle("log_potential(1.0)")       # vector form needs one exponent per replica
     srv.engine.close()
+
+
+def test_tables_use_java_number_format(tmp_path):
+    """the `value` column is Double.toString / Integer.toString of the recorded number (InputOutput.xtend:221-230 shows
+    0.45370104866569855; small and large magnitudes are d.dddE[-]n, not Python's 1e-05)"""
+    from blangsdk_b200.results import TabularWriter, _fmt
+    assert _fmt(0.45370104866569855) == "0.45370104866569855"
+    assert _fmt(1e-5) == "1.0E-5" and _fmt(1.23456789e7) == "1.23456789E7" and _fmt(-2.5e-7) == "-2.5E-7"
+    assert _fmt(float("nan")) == "NaN" and _fmt(float("-inf")) == "-Infinity" and _fmt(0.0) == "0.0" and _fmt(7) == "7"
+    w = TabularWriter(str(tmp_path / "samples" / "x.csv"))
+    w.write_block(["index_0", "sample", "value"], [np.array([0, 1]), np.array([0, 0]), np.array([0.45370104866569855, 1e-12])])
+    w.close()
+    assert open(tmp_path / "samples" / "x.csv").read() == "index_0,sample,value\n0,0,0.45370104866569855\n1,0,1.0E-12\n"
