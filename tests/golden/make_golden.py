@@ -48,6 +48,8 @@ def main():
     specs["hierarchical"] = D.hierarchical_rockets(6)
     specs["linreg"] = D.linear_regression(50, 3)
     specs["rockets_latent"] = D.rockets_latent(5)
+    # appended last (earlier vectors unchanged): F/Doomsday.bl with the arguments of the reference's Getting Started transcript
+    specs["iid_uniformmax"] = D.doomsday(1.2, 1.0)
     rng = np.random.default_rng(20240600)
     cases = []
     for name, spec in specs.items():
