@@ -166,3 +166,25 @@ def test_pool_mixture_matches_cluster_kernel_and_is_deterministic(datasets, monk
     assert rel(a["energy"], b["energy"]) < 1e-10 and rel(a["samples"], b["samples"]) < 1e-9
     assert np.array_equal(b["energy"], c["energy"]) and np.array_equal(b["samples"], c["samples"])      # bit-identical repeat
 
+
+def test_pool_mixture_rounds_adaptation_against_the_oracle(oracle, datasets, pool_on):
+    """a down-scaled twin of BASELINE config 2 (bimodal mixture, K = 4) through PT.performInference on the pool kernel:
+    the adapted ladder, Lambda, log Z, swap acceptance and the round-trip count of every round equal the oracle's"""
+    from blangsdk_b200.engine import PT
+    spec = datasets.gaussian_mixture(1_500, seed=77)
+    pt = PT(nChains=6, nScans=200, adaptFraction=0.5, random=31, initialization="FORWARD")
+    pt.setSampledModel(spec)
+    assert pt.engine.kernel_variant == 1
+    res = pt.performInference()
+    ref = oracle.PT(oracle.Model(spec), nChains=6, seed=31)
+    ref.initialize()
+    rres = ref.perform_inference(200, 0.5)
+    assert [r["nScans"] for r in res["rounds"]] == [r["nScans"] for r in rres["rounds"]]
+    assert np.array_equal(res["swapIndicators"][:, 0, :], rres["indicators"])
+    assert rel(res["energy"][:, 0, :], rres["energies"]) < 1e-9
+    assert rel(res["ladder"][0], ref.get_ladder()) < 1e-9
+    for a, b in zip(res["rounds"], rres["rounds"]):
+        assert int(a["roundTrips"][0]) == b["roundTrips"]
+        assert rel(a["Lambda"][0], b["Lambda"]) < 1e-9 and rel(a["logZ"][0], b["logZ"]) < 1e-9
+        assert rel(a["minAccept"][0], b["minAccept"]) < 1e-9 and rel(a["meanAccept"][0], b["meanAccept"]) < 1e-9
+    pt.engine.close()
