@@ -16,6 +16,7 @@ struct PoolState {
   size_t control_bytes = 0;
   void* results = nullptr;      // wbuf
   unsigned long long* prof = nullptr; int launches = 0;
+  void* win_base = nullptr; size_t win_bytes = 0; float win_ratio = 0.f;   // L2 access-policy window (pool_set_l2_window)
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -88,6 +89,11 @@ static void pool_report(PoolState* ps) {
           n_ctrl, evals, cyc_ctrl / std::max(1.0, evals), cyc_wait / std::max(1.0, evals), cyc_wait / std::max(1.0, cyc_ctrl));
 }
 
+void pool_set_l2_window(PoolState* ps, void* base, size_t bytes, float hit_ratio) {
+  if (!ps) return;
+  ps->win_base = base; ps->win_bytes = bytes; ps->win_ratio = hit_ratio;
+}
+
 void pool_destroy(PoolState* ps) {
   if (!ps) return;
   if (ps->prof) { pool_report(ps); cudaFree(ps->prof); }
@@ -119,10 +125,19 @@ static int pool_launch_t(const PoolState* psp, const DevEngine& E, const typenam
   lc.blockDim = dim3((unsigned)kPoolThreads);
   lc.dynamicSmemBytes = kPoolDynSmemBytes;
   lc.stream = stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeCooperative;
   at[0].val.cooperative = 1;
   lc.attrs = at; lc.numAttrs = 1;
+  if (ps.win_base && ps.win_bytes && ps.win_ratio > 0.f) {
+    at[1].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[1].val.accessPolicyWindow.base_ptr = ps.win_base;
+    at[1].val.accessPolicyWindow.num_bytes = ps.win_bytes;
+    at[1].val.accessPolicyWindow.hitRatio = ps.win_ratio;
+    at[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    lc.numAttrs = 2;
+  }
   e = cudaLaunchKernelEx(&lc, pool_kernel<PF>, E, D, ps.ctl, mode);
   return (int)e;
 }

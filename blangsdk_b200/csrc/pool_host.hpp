@@ -13,6 +13,9 @@ struct PoolState;   // opaque: global-memory request / result blocks of one hand
 // a cudaError_t (> 0) when an allocation fails.
 int pool_create(PoolState** out, int chains, int device, int family /* BLANGPT_FAM_LOGISTIC | BLANGPT_FAM_MIXTURE */, int mixture_K);
 void pool_destroy(PoolState* ps);
+// L2 residency control for working sets beyond the L2: launches carry an access-policy window over [base, base + bytes)
+// (the per-chain caches) in which a fraction `hit_ratio` of the lines persists and the rest streams
+void pool_set_l2_window(PoolState* ps, void* base, size_t bytes, float hit_ratio);
 // one launch = one exploration pass (mode: ExploreMode) of every local chain; returns a cudaError_t
 int pool_launch_logistic(const PoolState* ps, const DevEngine& E, const LogisticFam::Data& D, int mode, cudaStream_t stream);
 int pool_launch_mixture(const PoolState* ps, const DevEngine& E, const MixtureFam<4>::Data& D, int mode, cudaStream_t stream);
