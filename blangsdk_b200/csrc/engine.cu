@@ -85,11 +85,29 @@ static void set_error(blangpt_handle* h, const char* fmt, ...) {
   if (h) h->error = buf; else g_create_error = buf;
 }
 
+// Device memory of a handle comes from the device's stream-ordered pool (cudaMallocAsync on the handle's stream), with
+// the pool told to keep what is freed: a create -> run -> destroy cycle then costs no device synchronisation and no
+// trip to the OS per buffer (a plain cudaMalloc / cudaFree pair per buffer cost 10-25 ms per engine).  The mailbox of the
+// multi-GPU exchange stays a cudaMalloc allocation (CUDA IPC needs one).
+static void keep_freed_memory(int device) {
+  static bool done[64] = {};
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool = nullptr;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+  done[device] = true;
+}
+static void dev_free(blangpt_handle* h, void* p) { if (p) cudaFreeAsync(p, h->stream); }
+
 template <class T>
 static int dev_alloc(blangpt_handle* h, T** out, size_t n, bool zero = true) {
   void* p = nullptr;
   const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
-  CUDA_OK(h, cudaMalloc(&p, bytes));
+  keep_freed_memory(h->cfg.device);
+  CUDA_OK(h, cudaMallocAsync(&p, bytes, h->stream));
   if (zero) CUDA_OK(h, cudaMemsetAsync(p, 0, bytes, h->stream));
   h->allocs.push_back(p);
   *out = (T*)p;
@@ -124,9 +142,10 @@ extern "C" int blangpt_create(const blangpt_config* cfg, blangpt_handle** out) {
   if (cfg->device < 0 || cfg->device >= ndev) { set_error(nullptr, "device %d out of range", cfg->device); return BLANGPT_EINVAL; }
   e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { set_error(nullptr, "cudaSetDevice: %s", cudaGetErrorString(e)); return BLANGPT_ECUDA; }
-  cudaDeviceProp prop;
-  cudaGetDeviceProperties(&prop, cfg->device);
-  if (prop.major < 10) { set_error(nullptr, "device sm_%d%d is not Blackwell (kernels are built for sm_100a only)", prop.major, prop.minor); return BLANGPT_ECUDA; }
+  int cc_major = 0, cc_minor = 0;      // two attribute reads; cudaGetDeviceProperties costs 3-14 ms per call
+  cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, cfg->device);
+  cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, cfg->device);
+  if (cc_major < 10) { set_error(nullptr, "device sm_%d%d is not Blackwell (kernels are built for sm_100a only)", cc_major, cc_minor); return BLANGPT_ECUDA; }
   blangpt_handle* h = new blangpt_handle();
   h->cfg = *cfg;
   if (const char* t = getenv("BLANGPT_LOGISTIC_THREADS")) h->logistic_threads = atoi(t) == 1024 ? 1024 : 512;
@@ -141,8 +160,9 @@ extern "C" void blangpt_destroy(blangpt_handle* h) {
   cudaDeviceSynchronize();
   for (void* p : h->peer_maps) if (p) cudaIpcCloseMemHandle(p);
   if (h->mailbox) cudaFree(h->mailbox);
-  for (void* p : h->allocs) cudaFree(p);
+  for (void* p : h->allocs) dev_free(h, p);
   for (auto& b : h->outbuf) if (b.p) cudaFree(b.p);
+  cudaStreamSynchronize(h->stream);
   if (h->l2_persist) cudaCtxResetPersistingL2Cache();
   pool_destroy(h->pool); h->pool = nullptr;
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -476,8 +496,8 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
       transpose_kernel<<<grid, block, 0, h->stream>>>(xr, ones, xt, n, p, npad);
       CUDA_OK(h, cudaGetLastError());
       CUDA_OK(h, cudaStreamSynchronize(h->stream));
-      CUDA_OK(h, cudaFree(xr)); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), (void*)xr));
-      CUDA_OK(h, cudaFree(ones)); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), (void*)ones));
+      dev_free(h, xr); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), (void*)xr));
+      dev_free(h, ones); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), (void*)ones));
       h->linreg = {xt, yd, res, n, npad, p, hyper[0], hyper[1]};
       h->n_reals = p + 1; h->n_samplers = p + 1; rows = n;
     } break;
@@ -540,7 +560,7 @@ extern "C" int blangpt_set_model(blangpt_handle* h, int32_t family, const blangp
       transpose_kernel<<<grid, block, 0, h->stream>>>(xr, y8, xt, n, p, npad);
       CUDA_OK(h, cudaGetLastError());
       CUDA_OK(h, cudaStreamSynchronize(h->stream));
-      CUDA_OK(h, cudaFree(xr)); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), (void*)xr));
+      dev_free(h, xr); h->allocs.erase(std::find(h->allocs.begin(), h->allocs.end(), (void*)xr));
       h->logistic = {xt, y8, eta, n, npad, p, hyper[0]};
       h->n_reals = p; h->n_samplers = p; rows = n;
     } break;
@@ -866,7 +886,7 @@ static int scm_initialize(blangpt_handle* h) {
   c->n_reals = h->n_reals; c->n_ints = h->n_ints; c->n_samplers = h->n_samplers;
   c->normal = h->normal; c->iid = h->iid; c->hier = h->hier; c->linreg = h->linreg; c->rockets = h->rockets; c->logistic = h->logistic; c->mixture = h->mixture; c->betabin = h->betabin; c->ising = h->ising; c->mixind = h->mixind; c->changepoint = h->changepoint; c->annealpair = h->annealpair;
   c->betabin.chains_per_replica = P;
-  auto fail = [&](int code) { for (void* p : c->allocs) cudaFree(p); if (code) h->error = c->error; delete c; return code; };
+  auto fail = [&](int code) { for (void* p : c->allocs) dev_free(c, p); cudaStreamSynchronize(c->stream); if (code) h->error = c->error; delete c; return code; };
   // CUDA calls on the child go through fail(): the child's allocations are released and its message reaches the caller
 #define SCM_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
     set_error(c, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); return fail(BLANGPT_ECUDA); } } while (0)
