@@ -23,7 +23,8 @@ if stale "$OBJ/engine.o" "$HERE/engine.cu" "$HERE/ising.cuh" "$HERE/schedule.hpp
   "$NVCC" $FLAGS -c "$HERE/engine.cu" -o "$OBJ/engine.o" & PIDS="$PIDS $!"
 fi
 if stale "$OBJ/pool.o" "$HERE/pool.cu" "$HERE/pool.cuh" "$HERE/pool_mixture.cuh" $COMMON; then
-  "$NVCC" $FLAGS -c "$HERE/pool.cu" -o "$OBJ/pool.o" & PIDS="$PIDS $!"
+  # --register-usage-level=8: the row loop loses two register moves per step (96 -> 94 instructions; 3.98 -> 4.02 M evals/s)
+  "$NVCC" $FLAGS -Xptxas --register-usage-level=8 -c "$HERE/pool.cu" -o "$OBJ/pool.o" & PIDS="$PIDS $!"
 fi
 for p in $PIDS; do wait "$p"; done
 "$NVCC" -ccbin "$CCBIN" -shared -gencode arch=compute_100a,code=sm_100a -o "$HERE/../libblangpt.so" "$OBJ/engine.o" "$OBJ/pool.o"
