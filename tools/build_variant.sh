@@ -7,7 +7,7 @@ ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 NAME="$1"; shift
 CS="$ROOT/blangsdk_b200/csrc"
 mkdir -p "$ROOT/scratch/libs" "$ROOT/scratch/obj"
-/usr/local/cuda/bin/nvcc -ccbin /usr/bin/g++ -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC "$@" \
+/usr/local/cuda/bin/nvcc -ccbin /usr/bin/g++ -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas --register-usage-level=8 "$@" \
   -c "$CS/pool.cu" -o "$ROOT/scratch/obj/pool_$NAME.o"
 /usr/local/cuda/bin/nvcc -ccbin /usr/bin/g++ -shared -gencode arch=compute_100a,code=sm_100a \
   -o "$ROOT/scratch/libs/libblangpt_$NAME.so" "$CS/build/engine.o" "$ROOT/scratch/obj/pool_$NAME.o"
