@@ -843,31 +843,49 @@ static int scm_read_table(blangpt_handle* c, std::vector<ScmParticle>& ps) {
   return 0;
 }
 
-// new particle i = old particle ancestors[i] (ParticlePopulation.resample + deepCopyParticles :149-170)
+// new particle i = old particle ancestors[i] (ParticlePopulation.resample + deepCopyParticles :149-170), on the
+// device: the particle states never visit the host, whatever the number of particles and the size of a state.
+// dst[r * row_stride + i * rec + b] = src[r * row_stride + anc[i] * rec + b], elements of T; variable-major arrays
+// are `rows` rows of P one-element records, particle-major arrays one row of P records of `rec` elements.
+template <class T>
+__global__ void scm_gather_kernel(T* __restrict__ dst, const T* __restrict__ src, const int* __restrict__ anc, int P, size_t rec, size_t rows) {
+  const size_t per_row = (size_t)P * rec, total = per_row * rows;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = t / per_row, q = t - r * per_row, i = q / rec, b = q - i * rec;
+    dst[t] = src[r * per_row + (size_t)anc[i] * rec + b];
+  }
+}
+template <class T>
+static int scm_gather(blangpt_handle* c, T* arr, const int* d_anc, size_t rec, size_t rows) {
+  const size_t total = (size_t)c->cfg.nChains * rec * rows;
+  if (!total) return 0;
+  T* tmp = nullptr;
+  CUDA_OK(c, cudaMallocAsync((void**)&tmp, total * sizeof(T), c->stream));
+  const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+  scm_gather_kernel<T><<<grid, 256, 0, c->stream>>>(tmp, arr, d_anc, c->cfg.nChains, rec, rows);
+  c->n_launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(arr, tmp, total * sizeof(T), cudaMemcpyDeviceToDevice, c->stream);
+  cudaFreeAsync(tmp, c->stream);
+  if (e != cudaSuccess) { set_error(c, "SCM resampling gather failed: %s", cudaGetErrorString(e)); return BLANGPT_ECUDA; }
+  return 0;
+}
 static int scm_permute(blangpt_handle* c, const std::vector<int>& anc) {
   const int P = c->cfg.nChains;
-  if (c->n_reals) {
-    std::vector<double> a((size_t)c->n_reals * P), b(a.size());
-    CUDA_OK(c, cudaMemcpy(a.data(), c->E.reals, a.size() * 8, cudaMemcpyDeviceToHost));
-    for (int v = 0; v < c->n_reals; v++) for (int i = 0; i < P; i++) b[(size_t)v * P + i] = a[(size_t)v * P + anc[i]];
-    CUDA_OK(c, cudaMemcpy(c->E.reals, b.data(), b.size() * 8, cudaMemcpyHostToDevice));
-  }
-  if (c->n_ints) {
-    const size_t S = c->n_ints;
-    std::vector<uint8_t> a(S * P), b(S * P);
-    CUDA_OK(c, cudaMemcpy(a.data(), c->ising.spins, a.size(), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < P; i++) memcpy(&b[S * i], &a[S * anc[i]], S);
-    CUDA_OK(c, cudaMemcpy(c->ising.spins, b.data(), b.size(), cudaMemcpyHostToDevice));
-  }
-  {   // the sampler order travels with the state (SampledModel.currentSamplingOrder is deep-cloned)
-    const size_t sm = c->E.s_max;
-    std::vector<int> o(sm * P), o2(sm * P), cp(P), cp2(P);
-    CUDA_OK(c, cudaMemcpy(o.data(), c->E.order, o.size() * 4, cudaMemcpyDeviceToHost));
-    CUDA_OK(c, cudaMemcpy(cp.data(), c->E.curpos, cp.size() * 4, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < P; i++) { memcpy(&o2[sm * i], &o[sm * anc[i]], sm * 4); cp2[i] = cp[anc[i]]; }
-    CUDA_OK(c, cudaMemcpy(c->E.order, o2.data(), o2.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_OK(c, cudaMemcpy(c->E.curpos, cp2.data(), cp2.size() * 4, cudaMemcpyHostToDevice));
-  }
+  int* d_anc = nullptr;
+  CUDA_OK(c, cudaMallocAsync((void**)&d_anc, (size_t)P * sizeof(int), c->stream));
+  int rc = 0;
+  cudaError_t e = cudaMemcpyAsync(d_anc, anc.data(), (size_t)P * sizeof(int), cudaMemcpyHostToDevice, c->stream);
+  if (e != cudaSuccess) { set_error(c, "SCM resampling upload failed: %s", cudaGetErrorString(e)); rc = BLANGPT_ECUDA; }
+  if (!rc && c->n_reals) rc = scm_gather(c, c->E.reals, d_anc, 1, (size_t)c->n_reals);          // reals[v][particle]
+  if (!rc && c->n_ints) rc = scm_gather(c, c->ising.spins, d_anc, (size_t)c->n_ints, 1);          // spins[particle][S]
+  // the sampler order travels with the state (SampledModel.currentSamplingOrder is deep-cloned)
+  if (!rc) rc = scm_gather(c, c->E.order, d_anc, (size_t)c->E.s_max, 1);
+  if (!rc) rc = scm_gather(c, c->E.curpos, d_anc, 1, 1);
+  // anc is pageable host memory: the copy above has completed on return only for the staging part; wait before it dies
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess && !rc) { set_error(c, "SCM resampling failed on the device"); rc = BLANGPT_ECUDA; }
+  cudaFreeAsync(d_anc, c->stream);
+  if (rc) return rc;
   return launch_explore(c, MODE_EVAL);   // rebuild per-particle caches and the table
 }
 
