@@ -42,7 +42,7 @@ KERNEL_BYTES_PER_EVAL = N_ROWS * (8 + 8)                 # what the eta-cached k
 # fp64-pipe instructions (DFMA + DADD + DMUL [+ DSETP]) per row of one evaluation, counted in the SASS of the inner
 # loop of each exploration kernel (profiles/sass_pool_inner_loop_r02.md, tools/sass_loops.py): the kernel's roofline is
 # the fp64 pipe (one fp64 instruction per lane per 2 cycles per SM sub-partition), not HBM -- the rows come from L2.
-FP64_INSTR_PER_ROW = {1: ("pool_kernel<LogisticPool>", 22), 0: ("explore_kernel<LogisticFam>", 26)}
+FP64_INSTR_PER_ROW = {1: ("pool_kernel<LogisticPool>", 20), 0: ("explore_kernel<LogisticFam>", 24)}
 NRPT_SCANS = 400                                          # scans of the adaptive NRPT run that measures round trips/s
 METRIC = "annealed log-density evals/s (NRPT, logistic 100k x 32, 64 chains/GPU)"
 UNIT = "evals/s"
@@ -394,7 +394,9 @@ def run_gpu(args):
                                    "MEASURED_PEAKS.json has no fp64 figure",
                     "how": "rows/s x %d fp64-pipe instructions per row (DFMA+DADD+DMUL in the inner-loop SASS) x 2, over the "
                            "explore kernel's CUDA-event time; ncu sm__pipe_fp64_cycles_active of the same kernel: "
-                           "profiles/pool_logistic_r02.md" % per_row,
+                           "profiles/pool_logistic_r02.md.  The count is of the work the kernel does, not of the work it "
+                           "avoids: the last build of round 2 took 2 of 22 fp64 instructions out of the row term (4.01 -> 4.11 M "
+                           "evals/s), which lowers this fraction (0.50 -> 0.47) while the throughput rises" % per_row,
                     "fp64_instr_per_row": per_row, "rows_per_s": rows_per_s, "evals_per_launch": evals_per_launch,
                     "ms_per_launch": explore_s * 1e3, "traffic": traffic, "traffic_source": traffic_src,
                     "hbm_side": {"note": "SURVEY 8(d) counts one full pass over X,y (25.7 MB) per evaluation; the engine keeps "

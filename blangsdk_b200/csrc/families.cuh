@@ -63,12 +63,18 @@ BPT_D void acc_term(double t, double& s, int& c, int* err) {
 // degree-5 polynomial is exact to 4e-17.  log(u) for u in (1, 2]: u = c_j (1 + rr) with c_j the centre of the
 // j-th of 256 mantissa intervals, rr = u * fl(1/c_j) - 1, |rr| <= 1/512, log u = -log fl(1/c_j) + log1p(rr)
 // (series to rr^5, truncation < 1e-17); the table holds the log of the value really multiplied by, so the
-// identity is exact up to rounding.  No division, no reciprocal; 25 fp64 instructions per row.
+// identity is exact up to rounding.  No division, no reciprocal; 20 fp64 instructions per row (round 1: 25, with a
+// Cody-Waite pair for r and the log series as rr + rr^2 q).
 // {-64 log2(e), 1.5*2^52, -ln2/64 hi (21 low bits zero: m * hi exact), -ln2/64 lo}
 static __constant__ double kLgtK[4] = {-92.33248261689366, 6755399441055744.0, -0.01083042469326756, -2.9815858269852933e-12};
 static __constant__ double kLgtExpC[6] = {   // 1/5! .. 1/0!
     8.33333333333333333333e-03, 4.16666666666666666667e-02, 1.66666666666666666667e-01, 0.5, 1.0, 1.0};
 static __constant__ double kLgtLogC[4] = {0.2, -0.25, 3.33333333333333333333e-01, -0.5};
+// the logistic row term takes exp(-a) = 2^((m + f)/64) with f = a * (-64 log2 e) - m from ONE fma (|f| <= 1/2; the
+// rounding of the constant costs a relative a * 7.7e-17 on exp(-a), < 3e-17 absolute on log1p(exp(-a))): polynomial in
+// f, coefficients (ln2/64)^i / i!, i = 5 .. 0 (tools/gen_logit_tables.py)
+static __constant__ double kLgtExp2C[6] = {1.2417843701716925e-12, 5.732851688640402e-10, 2.1173137155464776e-07,
+                                           5.86490495505617e-05, 0.010830424696249145, 1.0};
 static __constant__ double kLgtExpTabC[64] = {
     1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
     1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
@@ -242,14 +248,13 @@ BPT_D void logit_fast(const double (&z)[W], double& s, uint32_t tab) {
     m[w] = __double2loint(kd[w]);
     kd[w] -= kLgtK[1];
     asm("ld.shared.f64 %0, [%1];" : "=d"(te[w]) : "r"(tab + 4096u + ((uint32_t)(m[w] & 63) << 3)));
-    r[w] = fma(kd[w], kLgtK[2], -a);
-    r[w] = fma(kd[w], kLgtK[3], r[w]);
-    p[w] = kLgtExpC[0];
+    r[w] = fma(a, kLgtK[0], -kd[w]);        // f = -a * 64 log2 e - m, one rounding
+    p[w] = kLgtExp2C[0];
   }
 #pragma unroll
   for (int i = 1; i < 6; i++)
 #pragma unroll
-    for (int w = 0; w < W; w++) p[w] = fma(p[w], r[w], kLgtExpC[i]);
+    for (int w = 0; w < W; w++) p[w] = fma(p[w], r[w], kLgtExp2C[i]);
   double q[W], rr[W], lc[W];
 #pragma unroll
   for (int w = 0; w < W; w++) {
@@ -270,7 +275,7 @@ BPT_D void logit_fast(const double (&z)[W], double& s, uint32_t tab) {
     for (int w = 0; w < W; w++) q[w] = fma(q[w], rr[w], kLgtLogC[i]);
 #pragma unroll
   for (int w = 0; w < W; w++) {
-    const double l = fma(rr[w] * rr[w], q[w], rr[w]) + lc[w];     // log1p(exp(-|z|))
+    const double l = fma(rr[w], fma(rr[w], q[w], 1.0), lc[w]);    // log1p(exp(-|z|)) = log c_j + rr (1 + rr q)
     s += fma(0.5, z[w] - fabs(z[w]), -l);                           // min(z,0) - log1p(exp(-|z|))
   }
 }

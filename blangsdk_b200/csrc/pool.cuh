@@ -159,14 +159,13 @@ BPT_D bool logit_fast2_rep(double z0, double z1, double& s, uint32_t tl, uint32_
     uint32_t ea;
     asm("{\n\t.reg .u32 t;\n\tand.b32 t, %1, 63;\n\tmad.lo.u32 %0, t, 128, %2;\n\t}" : "=r"(ea) : "r"(m[w]), "r"(te_base));
     asm("ld.shared.f64 %0, [%1];" : "=d"(te[w]) : "r"(ea));
-    r[w] = fma(kd[w], kLgtK[2], -a);
-    r[w] = fma(kd[w], kLgtK[3], r[w]);
-    p[w] = kLgtExpC[0];
+    r[w] = fma(a, kLgtK[0], -kd[w]);        // f = -a * 64 log2 e - m, one rounding
+    p[w] = kLgtExp2C[0];
   }
 #pragma unroll
   for (int i = 1; i < 6; i++)
 #pragma unroll
-    for (int w = 0; w < 2; w++) p[w] = fma(p[w], r[w], kLgtExpC[i]);
+    for (int w = 0; w < 2; w++) p[w] = fma(p[w], r[w], kLgtExp2C[i]);
   double q[2], rr[2], lc[2];
 #pragma unroll
   for (int w = 0; w < 2; w++) {
@@ -189,7 +188,7 @@ BPT_D bool logit_fast2_rep(double z0, double z1, double& s, uint32_t tl, uint32_
   bool ok = true;
 #pragma unroll
   for (int w = 0; w < 2; w++) {
-    const double l = fma(rr[w] * rr[w], q[w], rr[w]) + lc[w];     // log1p(exp(-|z|))
+    const double l = fma(rr[w], fma(rr[w], q[w], 1.0), lc[w]);    // log1p(exp(-|z|)) = log c_j + rr (1 + rr q)
     const double wz = z[w] - fabs(z[w]);                           // 2 min(z, 0)
     ok = ok && (unsigned)__double2hiint(wz) < 0xC0380000u && ((unsigned)__double2hiint(z[w]) & 0x7fffffffu) < 0x4085E000u;
     s += fma(0.5, wz, -l);                                         // min(z,0) - log1p(exp(-|z|))

@@ -26,3 +26,12 @@ hi = struct.unpack("<d", struct.pack("<Q", b))[0]
 lo = d2f(ln2 / NE - Decimal(hi))
 print("// -64*log2(e), ln2/64 hi, lo")
 print(repr(d2f(-Decimal(NE) / ln2)), repr(hi), repr(lo))
+# exp(-a) = 2^((m + f)/64) with f = a * (-64 log2 e) - m taken by ONE fma (no Cody-Waite pair): the polynomial is in f,
+# coefficients (ln2/64)^i / i!, i = 5 .. 0
+print("// (ln2/64)^i / i!, i = 5 .. 0")
+fact = 1
+cs = []
+for i in range(6):
+    cs.append(repr(d2f((ln2 / NE) ** i / fact)))
+    fact *= (i + 1)
+print(", ".join(reversed(cs)))
