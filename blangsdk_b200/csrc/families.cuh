@@ -59,8 +59,9 @@ BPT_D void acc_term(double t, double& s, int& c, int* err) {
 // Coefficients live in constant memory so each one is a direct DFMA operand.
 //
 // Tables for the logistic row term (tools/gen_logit_tables.py writes them, 60-digit arithmetic, rounded once).
-// exp(-a) = 2^k * 2^(j/64) * exp(r): m = round(-a * 64 log2 e) = 64 k + j, r = -a - m ln2/64, |r| <= ln2/128, so a
-// degree-5 polynomial is exact to 4e-17.  log(u) for u in (1, 2]: u = c_j (1 + rr) with c_j the centre of the
+// exp(-a) = 2^k * 2^(j/64) * 2^(f/64): m = round(-a * 64 log2 e) = 64 k + j, f = -a * 64 log2 e - m, |f| <= 1/2, so a
+// degree-5 polynomial in f is exact to 4e-17 (exp_tab() of the mixture family keeps r = x - m ln2/64 by a Cody-Waite
+// pair and the polynomial in r).  log(u) for u in (1, 2]: u = c_j (1 + rr) with c_j the centre of the
 // j-th of 256 mantissa intervals, rr = u * fl(1/c_j) - 1, |rr| <= 1/512, log u = -log fl(1/c_j) + log1p(rr)
 // (series to rr^5, truncation < 1e-17); the table holds the log of the value really multiplied by, so the
 // identity is exact up to rounding.  No division, no reciprocal; 20 fp64 instructions per row (round 1: 25, with a
