@@ -290,7 +290,7 @@ static const int IID_NLAWS[17]   = {0, 3, 2, 2, 4, 1, 1, 4, 4, 3, 2, 3, 3, 3, 2,
 static const int IID_MASK[17][IID_MAX_LAWS] = {
   {0}, {1, 1, 0}, {1, 0}, {1, 3}, {0, 4, 1, 7}, {1}, {3}, {1, 1, 0, 1}, {3, 2, 1, 2}, {3, 3, 3}, {3, 3},
   {2, 3, 3}, {1, 2, 3}, {3, 3, 3}, {3, 3}, {1}, {1, 1}};
-static const int IID_READS_Y[17][IID_MAX_LAWS] = {
+static const int IID_READS_Y[17][IID_MAX_LAWS] __attribute__((unused)) = {   /* documentation of the .bl signatures; no code path needs it */
   {0}, {1, 0, 1}, {1, 1}, {1, 1}, {0, 0, 0, 1}, {1}, {1}, {1, 1, 0, 0}, {1, 1, 0, 0}, {0, 1, 1}, {0, 1},
   {0, 1, 1}, {0, 0, 1}, {0, 1, 1}, {0, 1}, {1}, {0, 1}};
 
@@ -1375,7 +1375,8 @@ typedef struct { double log_sum; int64_t n; } LogSum;
 /* monotone cubic spline (R/engines/internals/Spline.java:129-203)      */
 /* ------------------------------------------------------------------ */
 void orc_monotone_spline_build(const double* x, const double* y, int n, double* m) {
-  double* d = (double*)malloc(sizeof(double) * (n > 1 ? n - 1 : 1));
+  if (n < 2) { for (int i = 0; i < n; i++) m[i] = NAN; return; }   /* the reference throws: "at least two control points" (:130-133) */
+  double* d = (double*)malloc(sizeof(double) * (n - 1));
   for (int i = 0; i < n - 1; i++) { double h = x[i + 1] - x[i]; d[i] = (y[i + 1] - y[i]) / h; }
   m[0] = d[0];
   for (int i = 1; i < n - 1; i++) m[i] = (d[i - 1] + d[i]) * 0.5;
