@@ -42,6 +42,38 @@ double row_term(double z) {
   const double l = fma(rr, fma(rr, q, 1.0), kLgtLogTabC[j][1]);
   return fma(0.5, z - fabs(z), -l);
 }
+/* families.cuh::exp_tab / log_tab (the mixture kernels): Cody-Waite reduction, polynomial in r; table log */
+double exp_tab(double x) {
+  double kd = fma(x, -kLgtK[0], kLgtK[1]);
+  const int m = lo32(kd);
+  kd -= kLgtK[1];
+  const double te = kLgtExpTabC[m & 63];
+  double r = fma(kd, kLgtK[2], x);
+  r = fma(kd, kLgtK[3], r);
+  double p = kLgtExpC[0];
+  for (int i = 1; i < 6; i++) p = fma(p, r, kLgtExpC[i]);
+  const double tp = te * p;
+  return mk(hi32(tp) + ((m >> 6) << 20), lo32(tp));
+}
+double log_tab(double a) {
+  const int hi = hi32(a);
+  const int e = (hi >> 20) - 1023;
+  const double m = mk((hi & 0x000fffff) | 0x3ff00000, lo32(a));
+  const unsigned j = ((unsigned)hi & 0x000ff000u) >> 12;
+  const double rr = fma(m, kLgtLogTabC[j][0], -1.0);
+  double q = kLgtLogC[0];
+  for (int i = 1; i < 4; i++) q = fma(q, rr, kLgtLogC[i]);
+  const double lm = fma(rr * rr, q, rr) + kLgtLogTabC[j][1];
+  return fma((double)e, 6.93147180559945309417e-01, lm);
+}
+void exp_log_errors(const double* x, int n, double* rel_exp, double* abs_log) {   /* x <= 0: exp(x), log(exp-ish positive) */
+  for (int i = 0; i < n; i++) {
+    const long double ex = expl((long double)x[i]);
+    rel_exp[i] = (double)(((long double)exp_tab(x[i]) - ex) / ex);
+    const double a = (double)expl((long double)x[i] * 0.5L) * 3.7;      /* positive, exponents from -500 to 2 */
+    abs_log[i] = (double)((long double)log_tab(a) - logl((long double)a));
+  }
+}
 void row_terms(const double* z, int n, double* out, double* err) {
   for (int i = 0; i < n; i++) {
     out[i] = row_term(z[i]);
@@ -66,7 +98,7 @@ def _build(tmp_path):
     ex, lg = _array(text, "kLgtExpTabC"), _array(text, "kLgtLogTabC")
     assert (len(k), len(e2), len(lc), len(ex), len(lg)) == (4, 6, 4, 64, 512)
     with open(tmp_path / "tables.h", "w") as f:
-        for name, v in (("kLgtK", k), ("kLgtExp2C", e2), ("kLgtLogC", lc), ("kLgtExpTabC", ex)):
+        for name, v in (("kLgtK", k), ("kLgtExp2C", e2), ("kLgtLogC", lc), ("kLgtExpTabC", ex), ("kLgtExpC", _array(text, "kLgtExpC"))):
             f.write("static const double %s[%d] = {%s};\n" % (name, len(v), ", ".join(repr(x) for x in v)))
         f.write("static const double kLgtLogTabC[256][2] = {%s};\n" % ", ".join("{%r, %r}" % (lg[2 * i], lg[2 * i + 1]) for i in range(256)))
     (tmp_path / "emul.c").write_text(EMUL)
@@ -75,6 +107,7 @@ def _build(tmp_path):
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(tmp_path / "emul.c"), "-lm"])
     lib = ctypes.CDLL(str(so))
     lib.row_terms.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.exp_log_errors.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     return lib, (k, e2, ex, lg)
 
 
@@ -108,3 +141,18 @@ def test_row_term_emulation_against_extended_precision(tmp_path):
     assert np.all(np.abs(err) <= 2.5e-16 + np.spacing(np.abs(out)))
     assert np.max(np.abs(err)) < 1.1e-15                       # worst case is the output's own rounding near z = -12
     assert abs(np.mean(err)) < 5e-17                           # no systematic offset (sums of 1e5 rows stay below 1e-11)
+
+
+def test_mixture_exp_and_log_emulation(tmp_path):
+    """families.cuh::exp_tab / log_tab, the table-driven exp and log of the mixture kernels (C3), same emulation"""
+    lib, (k, _, _, _) = _build(tmp_path)
+    ln2 = np.log(np.longdouble(2))
+    hi, lo = k[2], k[3]                       # -ln2/64 split: hi has 21 low mantissa bits clear, hi + lo = -ln2/64
+    assert np.float64(hi).view(np.uint64) & np.uint64((1 << 21) - 1) == 0
+    assert abs((np.longdouble(hi) + np.longdouble(lo)) + ln2 / 64) < 1e-19    # what an 80-bit sum can resolve
+    rng = np.random.default_rng(12)
+    x = np.ascontiguousarray(np.concatenate([rng.uniform(-700, 0, 300_000), rng.uniform(-40, 0, 300_000), [0.0, -700.0, -1e-300]]))
+    rel, lg = np.empty_like(x), np.empty_like(x)
+    lib.exp_log_errors(x.ctypes.data, x.size, rel.ctypes.data, lg.ctypes.data)
+    assert np.max(np.abs(rel)) < 4e-16    # table entry, polynomial and product each round once: under two ulps of exp(x)
+    assert np.max(np.abs(lg) / np.maximum(1.0, np.abs(0.5 * x + np.log(3.7)))) < 2.3e-16
